@@ -1,0 +1,98 @@
+"""ctypes binding of libflb.so (the C ABI declared in include/flb.h).
+
+There is deliberately no fallback: if the shared library is missing, or no sm_100 device is
+visible, every compute entry raises ``FlbError`` instead of silently running PyTorch ops."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libflb.so")
+
+
+class FlbError(RuntimeError):
+    """A libflb.so call failed (or the library / device is unavailable)."""
+
+
+_vp, _i, _ll, _ull, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_double
+
+# name -> argtypes; mirrors include/flb.h one-to-one (tests/test_cabi.py checks both directions)
+SIGNATURES = {
+    "flb_version": [],
+    "flb_init": [_i],
+    "flb_fedavg_weighted_sum": [_vp, _ll, _vp, _vp, _i, _ll, _i, _vp],
+    "flb_fedavg_weighted_sum_ptrs": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
+    "flb_fedavg_weighted_sum_q8": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
+    "flb_dp_sumsq": [_vp, _ll, _vp, _vp, _i, _ll, _vp],
+    "flb_dp_clip_noise": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _i, _ll, _vp],
+    "flb_dp_add_noise": [_vp, _ll, _vp, _vp, _d, _ull, _ull, _i, _ll, _vp],
+    "flb_philox_normal": [_vp, _ll, _ull, _ull, _vp],
+    "flb_philox_raw": [_vp, _ll, _ull, _ull, _ull, _vp],
+    "flb_q8_quantize": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp],
+    "flb_q8_dequantize": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
+}
+
+_lock = threading.Lock()
+_lib: Optional[C.CDLL] = None
+_inited = set()
+
+
+def load() -> C.CDLL:
+    """dlopen libflb.so and type its entry points.  Needs no GPU (symbol check only)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise FlbError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.flb_last_error.restype = C.c_char_p
+        lib.flb_last_error.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here == header/library drift
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def ensure_device(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise FlbError(f"flb200 kernels need a CUDA (sm_100a) device, got '{device}'; there is no CPU fallback")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _inited:
+        return
+    lib = load()
+    rc = lib.flb_init(idx)
+    if rc != 0:
+        raise FlbError(lib.flb_last_error().decode())
+    _inited.add(idx)
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FlbError(f"{name}: {lib.flb_last_error().decode()} (code {rc})")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device: Optional[torch.device] = None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise FlbError(f"{what}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise FlbError(f"{what}: expected float32, got {t.dtype}")
+    return t

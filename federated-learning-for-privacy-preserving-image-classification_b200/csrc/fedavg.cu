@@ -1,0 +1,188 @@
+// FedAvg weighted aggregation kernels (HBM-bound; one read of every client row, one write).
+//
+// Replaces the K x L python-level axpy loop of FedAvgAggregator._weighted_average
+// (reference src/aggregation/fedavg.py:267-289).  The arithmetic is kept identical to that
+// loop -- out = 0; out = out + fp32(w_k) * theta_k for k = 0..K-1, fp32 multiply and fp32 add
+// rounded separately (no FMA contraction) -- so the result is BIT-EXACT with the reference on
+// the same inputs; only the loop nest is turned inside out (each thread owns 4 columns and walks
+// the client axis, so every byte of theta is read exactly once, fully coalesced, 16 B per lane).
+#include "flb_common.cuh"
+#include "../../include/flb.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 8;      // client rows in flight per thread (8 x 16 B loads outstanding)
+constexpr int kWChunk = 1024;   // weights staged in shared memory per pass
+
+// theta: [K, ld] fp32 row-major, rows 16 B aligned (ld % 4 == 0).  out: [P].
+__global__ void __launch_bounds__(kThreads)
+fedavg_flat_vec4_kernel(const float* __restrict__ theta, long long ld, const float* __restrict__ w,
+                        float* __restrict__ out, int K, long long P4, int accumulate) {
+    __shared__ float sw[kWChunk];
+    const long long stride = (long long)gridDim.x * kThreads;
+    const float4* __restrict__ t4 = reinterpret_cast<const float4*>(theta);
+    const long long ld4 = ld >> 2;
+    for (long long base = (long long)blockIdx.x * kThreads; base < P4; base += stride) {
+        const long long c = base + threadIdx.x;
+        const bool live = c < P4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate && live) acc = reinterpret_cast<const float4*>(out)[c];
+        for (int k0 = 0; k0 < K; k0 += kWChunk) {
+            const int kc = min(kWChunk, K - k0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < kc; i += kThreads) sw[i] = w[k0 + i];
+            __syncthreads();
+            if (!live) continue;
+            int k = 0;
+            for (; k + kUnroll <= kc; k += kUnroll) {
+                float4 v[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) v[u] = __ldcs(&t4[(long long)(k0 + k + u) * ld4 + c]);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const float wk = sw[k + u];
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(wk, v[u].x));
+                    acc.y = __fadd_rn(acc.y, __fmul_rn(wk, v[u].y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(wk, v[u].z));
+                    acc.w = __fadd_rn(acc.w, __fmul_rn(wk, v[u].w));
+                }
+            }
+            for (; k < kc; ++k) {
+                const float4 v = __ldcs(&t4[(long long)(k0 + k) * ld4 + c]);
+                const float wk = sw[k];
+                acc.x = __fadd_rn(acc.x, __fmul_rn(wk, v.x));
+                acc.y = __fadd_rn(acc.y, __fmul_rn(wk, v.y));
+                acc.z = __fadd_rn(acc.z, __fmul_rn(wk, v.z));
+                acc.w = __fadd_rn(acc.w, __fmul_rn(wk, v.w));
+            }
+        }
+        if (live) reinterpret_cast<float4*>(out)[c] = acc;
+    }
+}
+
+// scalar columns [p0, P): tail of the vector path, or everything when rows are not 16 B aligned
+__global__ void __launch_bounds__(kThreads)
+fedavg_flat_scalar_kernel(const float* __restrict__ theta, long long ld, const float* __restrict__ w,
+                          float* __restrict__ out, int K, long long p0, long long P, int accumulate) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long p = p0 + (long long)blockIdx.x * kThreads + threadIdx.x; p < P; p += stride) {
+        float acc = accumulate ? out[p] : 0.f;
+        for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(&w[k]), __ldcs(&theta[(long long)k * ld + p])));
+        out[p] = acc;
+    }
+}
+
+// Per-client, per-layer tensors that were never stacked: ptrs[k * L + l] is tensor l of client k,
+// seg_off[l] .. seg_off[l+1] its span in the flat output.  Avoids a K x P gather copy in the
+// drop-in aggregator when the updates already live on the device as separate tensors.
+__global__ void __launch_bounds__(kThreads)
+fedavg_ptrs_kernel(const float* const* __restrict__ ptrs, const long long* __restrict__ seg_off,
+                   const float* __restrict__ w, float* __restrict__ out, int K, int L, long long P) {
+    extern __shared__ long long s_off[];
+    for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long p = (long long)blockIdx.x * kThreads + threadIdx.x; p < P; p += stride) {
+        int lo = 0, hi = L;                       // largest l with s_off[l] <= p
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
+        const long long j = p - s_off[lo];
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(&w[k]), __ldcs(&ptrs[(long long)k * L + lo][j])));
+        out[p] = acc;
+    }
+}
+
+// uint8 affine-quantised client rows (reference src/shared/compression.py:230-244 dequant rule
+// (float(q) - zp) * scale, per client and per layer), dequantised in registers and averaged in the
+// same pass: K bytes + 4 bytes of traffic per parameter instead of 4K + 4.
+__global__ void __launch_bounds__(kThreads)
+fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __restrict__ scale,
+                 const float* __restrict__ zp, const long long* __restrict__ seg_off,
+                 const float* __restrict__ w, float* __restrict__ out, int K, int L, long long P) {
+    extern __shared__ long long s_off[];
+    for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
+    __syncthreads();
+    const long long P4 = (P + 3) >> 2;
+    const long long stride = (long long)gridDim.x * kThreads;
+    const bool vec_ok = (ldq & 3) == 0;
+    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < P4; c += stride) {
+        const long long p = c << 2;
+        int lo = 0, hi = L;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
+        const bool whole = vec_ok && (p + 3 < P) && (p + 3 < s_off[lo + 1]);
+        if (whole) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int k = 0; k < K; ++k) {
+                const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(q + (long long)k * ldq + p));
+                const float s = __ldg(&scale[(long long)k * L + lo]), z = __ldg(&zp[(long long)k * L + lo]);
+                const float wk = __ldg(&w[k]);
+                a0 = __fadd_rn(a0, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.x, z), s)));
+                a1 = __fadd_rn(a1, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.y, z), s)));
+                a2 = __fadd_rn(a2, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.z, z), s)));
+                a3 = __fadd_rn(a3, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.w, z), s)));
+            }
+            out[p] = a0; out[p + 1] = a1; out[p + 2] = a2; out[p + 3] = a3;
+        } else {
+            for (long long e = p; e < min(p + 4, P); ++e) {
+                int l = lo;
+                while (e >= s_off[l + 1]) ++l;
+                float a = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float s = __ldg(&scale[(long long)k * L + l]), z = __ldg(&zp[(long long)k * L + l]);
+                    a = __fadd_rn(a, __fmul_rn(__ldg(&w[k]), __fmul_rn(__fsub_rn((float)q[(long long)k * ldq + e], z), s)));
+                }
+                out[e] = a;
+            }
+        }
+    }
+}
+
+int grid_for(long long work_items) {
+    const long long blocks = (work_items + kThreads - 1) / kThreads;
+    const long long cap = (long long)flb_num_sms() * 16;     // 16 resident CTAs of 256 threads per SM at most
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+extern "C" int flb_fedavg_weighted_sum(const float* theta, long long ld, const float* w, float* out,
+                                       int K, long long P, int accumulate, void* stream) {
+    FLB_CHECK_ARG(theta && w && out, "flb_fedavg_weighted_sum: null pointer");
+    FLB_CHECK_ARG(K >= 1 && P >= 0 && ld >= P, "flb_fedavg_weighted_sum: need K >= 1, P >= 0, ld >= P (K=%d P=%lld ld=%lld)", K, P, ld);
+    if (P == 0) return FLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = (ld % 4 == 0) && ((uintptr_t)theta % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    long long P4 = vec ? (P >> 2) : 0;
+    if (P4 > 0) {
+        fedavg_flat_vec4_kernel<<<grid_for(P4), kThreads, 0, st>>>(theta, ld, w, out, K, P4, accumulate);
+        FLB_LAUNCH_CHECK();
+    }
+    if ((P4 << 2) < P) {
+        fedavg_flat_scalar_kernel<<<grid_for(P - (P4 << 2)), kThreads, 0, st>>>(theta, ld, w, out, K, P4 << 2, P, accumulate);
+        FLB_LAUNCH_CHECK();
+    }
+    return FLB_OK;
+}
+
+extern "C" int flb_fedavg_weighted_sum_ptrs(const float* const* ptrs, const long long* seg_off, const float* w,
+                                            float* out, int K, int L, long long P, void* stream) {
+    FLB_CHECK_ARG(ptrs && seg_off && w && out, "flb_fedavg_weighted_sum_ptrs: null pointer");
+    FLB_CHECK_ARG(K >= 1 && L >= 1 && L <= 4096, "flb_fedavg_weighted_sum_ptrs: need K >= 1 and 1 <= L <= 4096");
+    if (P == 0) return FLB_OK;
+    fedavg_ptrs_kernel<<<grid_for(P), kThreads, (L + 1) * sizeof(long long), (cudaStream_t)stream>>>(ptrs, seg_off, w, out, K, L, P);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+extern "C" int flb_fedavg_weighted_sum_q8(const uint8_t* q, long long ldq, const float* scale, const float* zp,
+                                          const long long* seg_off, const float* w, float* out,
+                                          int K, int L, long long P, void* stream) {
+    FLB_CHECK_ARG(q && scale && zp && seg_off && w && out, "flb_fedavg_weighted_sum_q8: null pointer");
+    FLB_CHECK_ARG(K >= 1 && L >= 1 && L <= 4096 && ldq >= P, "flb_fedavg_weighted_sum_q8: bad K/L/ldq");
+    if (P == 0) return FLB_OK;
+    fedavg_q8_kernel<<<grid_for((P + 3) / 4), kThreads, (L + 1) * sizeof(long long), (cudaStream_t)stream>>>(
+        q, ldq, scale, zp, seg_off, w, out, K, L, P);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}

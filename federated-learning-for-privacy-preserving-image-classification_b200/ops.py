@@ -1,0 +1,171 @@
+"""Tensor-level wrappers over the C ABI (flat ``[K, ld]`` client-major buffers in HBM).
+
+Data layout: every client's model is one fp32 row of a ``[K, ld]`` matrix, ``ld`` = P rounded up to
+32 floats so rows start 128 B aligned; the layer -> (offset, shape) table is ``layout.ParamLayout``.
+All functions launch on the current torch stream and never synchronise."""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _row_stride(t: torch.Tensor) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise L.FlbError("expected a [K, ld] tensor with unit inner stride")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def as_weight_tensor(w, device) -> torch.Tensor:
+    """Host weights are Python float64 in the reference (fedavg.py:247-265) and become fp32 when they
+    multiply an fp32 tensor; the same single rounding happens here."""
+    if isinstance(w, torch.Tensor):
+        return w.to(device=device, dtype=torch.float32).contiguous()
+    return torch.tensor([float(x) for x in w], dtype=torch.float64).to(torch.float32).to(device)
+
+
+def fedavg_weighted_sum(theta: torch.Tensor, w, P: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                        accumulate: bool = False) -> torch.Tensor:
+    L.require_cuda_f32(theta, "theta")
+    L.ensure_device(theta.device)
+    K = theta.shape[0]
+    ld = _row_stride(theta)
+    P = theta.shape[1] if P is None else P
+    wt = as_weight_tensor(w, theta.device)
+    if wt.numel() != K:
+        raise L.FlbError(f"fedavg_weighted_sum: {wt.numel()} weights for {K} client rows")
+    if out is None:
+        out = torch.empty(P, dtype=torch.float32, device=theta.device)
+        accumulate = False
+    with torch.cuda.device(theta.device):
+        L.call("flb_fedavg_weighted_sum", L.ptr(theta), ld, L.ptr(wt), L.ptr(out), K, P, int(accumulate),
+               L.stream_ptr(theta.device))
+    return out
+
+
+def fedavg_weighted_sum_ptrs(ptr_table: torch.Tensor, seg_off: torch.Tensor, w, K: int, Lyr: int, P: int,
+                             device) -> torch.Tensor:
+    L.ensure_device(device)
+    wt = as_weight_tensor(w, device)
+    out = torch.empty(P, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L.call("flb_fedavg_weighted_sum_ptrs", L.ptr(ptr_table), L.ptr(seg_off), L.ptr(wt), L.ptr(out), K, Lyr, P,
+               L.stream_ptr(device))
+    return out
+
+
+def fedavg_weighted_sum_q8(q: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, seg_off: torch.Tensor, w,
+                           P: int) -> torch.Tensor:
+    if not (q.is_cuda and q.dtype == torch.uint8):
+        raise L.FlbError("fedavg_weighted_sum_q8: q must be a CUDA uint8 tensor")
+    L.ensure_device(q.device)
+    K, Lyr = q.shape[0], seg_off.numel() - 1
+    wt = as_weight_tensor(w, q.device)
+    out = torch.empty(P, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        L.call("flb_fedavg_weighted_sum_q8", L.ptr(q), _row_stride(q), L.ptr(scale), L.ptr(zp), L.ptr(seg_off),
+               L.ptr(wt), L.ptr(out), K, Lyr, P, L.stream_ptr(q.device))
+    return out
+
+
+def gaussian_sigma_unit(epsilon: float, delta: float) -> float:
+    """sigma / sensitivity of the reference's Gaussian mechanism (src/shared/privacy.py:202-209)."""
+    if epsilon <= 0:
+        raise ValueError("Epsilon must be positive")
+    if delta <= 0 or delta >= 1:
+        raise ValueError("Delta must be in (0, 1)")
+    return math.sqrt(2 * math.log(1.25 / delta)) / epsilon
+
+
+def dp_clip_noise(local: torch.Tensor, global_w: Optional[torch.Tensor], max_norm: float, sigma_unit: float,
+                  seed: int = 0, stream_base: int = 0, z: Optional[torch.Tensor] = None, P: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Batched update-level DP over K client rows.  Returns (upload rows [K, ld], ||delta_k|| [K])."""
+    L.require_cuda_f32(local, "local")
+    L.ensure_device(local.device)
+    K, ld = local.shape[0], _row_stride(local)
+    P = local.shape[1] if P is None else P
+    dev = local.device
+    if global_w is not None:
+        L.require_cuda_f32(global_w, "global_w")
+    if z is not None:
+        L.require_cuda_f32(z, "z")
+        if _row_stride(z) != ld:
+            raise L.FlbError("dp_clip_noise: z must share the row pitch of local")
+    if out is None:
+        out = torch.empty_like(local)
+    norm2 = torch.empty(K, dtype=torch.float64, device=dev)
+    norms = torch.empty(K, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = L.stream_ptr(dev)
+        L.call("flb_dp_sumsq", L.ptr(local), ld, L.ptr(global_w), L.ptr(norm2), K, P, st)
+        L.call("flb_dp_clip_noise", L.ptr(local), ld, L.ptr(global_w), L.ptr(z), L.ptr(norm2), L.ptr(out),
+               L.ptr(norms), float(max_norm), float(sigma_unit), int(seed) & (2**64 - 1),
+               int(stream_base) & (2**64 - 1), K, P, st)
+    return out, norms
+
+
+def dp_add_noise(x: torch.Tensor, sigma: float, seed: int = 0, stream_base: int = 0,
+                 z: Optional[torch.Tensor] = None, P: Optional[int] = None) -> torch.Tensor:
+    L.require_cuda_f32(x, "x")
+    L.ensure_device(x.device)
+    K, ld = x.shape[0], _row_stride(x)
+    P = x.shape[1] if P is None else P
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.call("flb_dp_add_noise", L.ptr(x), ld, L.ptr(z), L.ptr(out), float(sigma), int(seed) & (2**64 - 1),
+               int(stream_base) & (2**64 - 1), K, P, L.stream_ptr(x.device))
+    return out
+
+
+def philox_normal(n: int, seed: int, stream: int, device) -> torch.Tensor:
+    device = torch.device(device)
+    L.ensure_device(device)
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L.call("flb_philox_normal", L.ptr(out), n, seed, stream, L.stream_ptr(device))
+    return out
+
+
+def philox_raw(nblocks: int, seed: int, stream: int, first_block: int, device) -> torch.Tensor:
+    device = torch.device(device)
+    L.ensure_device(device)
+    out = torch.empty((nblocks, 4), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        L.call("flb_philox_raw", L.ptr(out), nblocks, seed, stream, first_block, L.stream_ptr(device))
+    return out
+
+
+def q8_quantize(x: torch.Tensor, seg_off: torch.Tensor, P: Optional[int] = None, bits: int = 8,
+                symmetric: bool = True):
+    """Per-(client, layer) affine quantisation of the K client rows.  Returns (q uint8 [K, ld], scale [K, L], zp [K, L])."""
+    L.require_cuda_f32(x, "x")
+    L.ensure_device(x.device)
+    K, ld = x.shape[0], _row_stride(x)
+    P = x.shape[1] if P is None else P
+    Lyr = seg_off.numel() - 1
+    dev = x.device
+    q = torch.empty((K, ld), dtype=torch.uint8, device=dev)
+    scale = torch.empty((K, Lyr), dtype=torch.float32, device=dev)
+    zp = torch.empty((K, Lyr), dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * K * Lyr, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.call("flb_q8_quantize", L.ptr(x), ld, L.ptr(seg_off), L.ptr(q), ld, L.ptr(scale), L.ptr(zp), L.ptr(scratch),
+               K, Lyr, P, bits, int(symmetric), L.stream_ptr(dev))
+    return q, scale, zp
+
+
+def q8_dequantize(q: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, seg_off: torch.Tensor,
+                  P: Optional[int] = None) -> torch.Tensor:
+    L.ensure_device(q.device)
+    K, ldq = q.shape[0], _row_stride(q)
+    P = q.shape[1] if P is None else P
+    Lyr = seg_off.numel() - 1
+    out = torch.zeros((K, ldq), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        L.call("flb_q8_dequantize", L.ptr(q), ldq, L.ptr(seg_off), L.ptr(scale), L.ptr(zp), L.ptr(out), ldq, K, Lyr, P,
+               L.stream_ptr(q.device))
+    return out

@@ -1,0 +1,145 @@
+"""GPU parity: csrc/privacy.cu through the C ABI / the drop-in engine vs the oracle and the reference's golden vectors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import philox as OP
+from oracle import privacy as OPV
+
+pytestmark = pytest.mark.gpu
+NAMES = ["a.weight", "a.bias", "b.weight", "b.bias"]
+
+
+class _InjectedNoise:
+    """Stand-in for engine.noise_generator (the reference's injection point): noise = sigma * z."""
+
+    def __init__(self, z):
+        self.z = z
+
+    def add_noise_to_gradients(self, g, sensitivity, epsilon, delta):
+        sigma = OPV.gaussian_sigma(sensitivity, epsilon, delta)
+        return {k: v + sigma * self.z[k].to(v.device) for k, v in g.items()}
+
+
+@pytest.mark.parametrize("tag", ["big", "small"])
+def test_clip_bit_exact_vs_reference_golden(cuda_device, tag):
+    from flb200.privacy import GradientClipper, create_privacy_engine
+    gold = load_golden("privacy_update_level.npz")
+    g = {k: torch.from_numpy(gold[f"{tag}/g/{k}"]) for k in NAMES}
+    clipped, norm = GradientClipper(1.0, cuda_device).clip_gradients(g)
+    assert abs(norm - float(gold[f"{tag}/norm"])) <= 1e-6 * max(1.0, float(gold[f"{tag}/norm"]))
+    for k in NAMES:
+        assert clipped[k].device.type == "cpu" and clipped[k] is not g[k]
+        np.testing.assert_allclose(clipped[k].numpy(), gold[f"{tag}/clipped/{k}"], rtol=2e-7, atol=0)
+    # engine.clip_gradients(g, max_norm) is the stand-alone clip (privacy.py:313-317)
+    c2 = create_privacy_engine(device=cuda_device).clip_gradients(g, 1.0)
+    for k in NAMES:
+        assert torch.equal(c2[k], clipped[k])
+
+
+@pytest.mark.parametrize("tag", ["big", "small"])
+def test_injected_noise_matches_reference_golden(cuda_device, tag):
+    """Identical injected noise tensor: fused kernel (z_in) and the stub-generator path both reproduce the
+    unmodified reference's add_noise output."""
+    from flb200 import ops
+    from flb200.layout import ParamLayout
+    from flb200.privacy import create_privacy_engine
+    gold = load_golden("privacy_update_level.npz")
+    g = {k: torch.from_numpy(gold[f"{tag}/g/{k}"]) for k in NAMES}
+    z = {k: torch.from_numpy(gold[f"{tag}/z/{k}"]) for k in NAMES}
+    lay = ParamLayout.from_weights(g)
+    rows, zrows = lay.new_rows(1, cuda_device), lay.new_rows(1, cuda_device)
+    lay.flatten_into(rows[0], g)
+    lay.flatten_into(zrows[0], z)
+    out, norms = ops.dp_clip_noise(rows, None, 1.0, ops.gaussian_sigma_unit(1.0, 1e-5), z=zrows, P=lay.P)
+    got = lay.unflatten(out[0], "cpu")
+    for k in NAMES:
+        np.testing.assert_allclose(got[k].numpy(), gold[f"{tag}/noisy/{k}"], rtol=0, atol=1e-6)
+    eng = create_privacy_engine(device=cuda_device)
+    eng.noise_generator = _InjectedNoise(z)
+    noisy = eng.add_noise(g, 1.0, 1e-5)
+    for k in NAMES:
+        np.testing.assert_allclose(noisy[k].numpy(), gold[f"{tag}/noisy/{k}"], rtol=0, atol=1e-6)
+    assert eng.budget_tracker.get_remaining_budget() == tuple(gold[f"{tag}/remaining"])       # budget consumed once
+    from flb200.privacy import PrivacyError
+    with pytest.raises(PrivacyError, match="Privacy budget exhausted"):
+        eng.add_noise(g, 1.0, 1e-5)
+    with pytest.raises(PrivacyError, match="Invalid privacy parameters"):
+        create_privacy_engine(device=cuda_device).add_noise(g, -1.0, 1e-5)
+
+
+def test_batched_client_glue_sigma0_and_injected(cuda_device):
+    """K clients at once, w_upload = global + noise(clip(local - global)) (federated_trainer.py:428-469):
+    sigma = 0 reproduces the clip exactly; injected z reproduces the oracle bit-for-bit when the coefficient agrees."""
+    from flb200 import ops
+    K, P = 5, 421642
+    ld = (P + 31) // 32 * 32
+    rng = np.random.default_rng(3)
+    wg = (rng.standard_normal(P) * 0.05).astype(np.float32)
+    scale = np.array([1e-5, 1e-3, 2e-3, 1e-2, 0.1], dtype=np.float32)         # norms straddle C = 1
+    wl = wg[None] + rng.standard_normal((K, P)).astype(np.float32) * scale[:, None]
+    z = rng.standard_normal((K, P)).astype(np.float32)
+    loc, zz = (torch.zeros((K, ld), device=cuda_device) for _ in range(2))
+    loc[:, :P] = torch.from_numpy(wl).to(cuda_device)
+    zz[:, :P] = torch.from_numpy(z).to(cuda_device)
+    glob = torch.zeros(ld, device=cuda_device)
+    glob[:P] = torch.from_numpy(wg).to(cuda_device)
+    out0, norms = ops.dp_clip_noise(loc, glob, 1.0, 0.0, P=P)
+    out1, _ = ops.dp_clip_noise(loc, glob, 1.0, ops.gaussian_sigma_unit(1.0, 1e-5), z=zz, P=P)
+    clipped_any = False
+    for k in range(K):
+        wlk, wgk = {"w": torch.from_numpy(wl[k])}, {"w": torch.from_numpy(wg)}
+        ref0, sens, _ = OPV.apply_update_dp(wlk, wgk, 1e9, 0.5, 1.0, {"w": torch.zeros(P)})
+        n_ref = OPV.global_norm({"w": wlk["w"] - wgk["w"]})
+        assert abs(norms[k].item() - n_ref) <= 2e-6 * n_ref
+        clipped_any |= n_ref > 1.0
+        np.testing.assert_allclose(out0[k, :P].cpu().numpy(), ref0["w"].numpy(), rtol=0, atol=1e-7)
+        ref1, _, sigma = OPV.apply_update_dp(wlk, wgk, 1.0, 1e-5, 1.0, {"w": torch.from_numpy(z[k])})
+        np.testing.assert_allclose(out1[k, :P].cpu().numpy(), ref1["w"].numpy(), rtol=0, atol=2e-6 * max(1.0, sigma))
+    assert clipped_any
+
+
+def test_philox_bit_exact_and_distribution(cuda_device):
+    from flb200 import ops
+    raw = ops.philox_raw(1000, 42, 3, 5, cuda_device).cpu().numpy().view(np.uint32)
+    assert np.array_equal(raw, OP.raw_blocks(1000, 42, 3, first_block=5))
+    for ctr, key, exp in OP.KAT[:1]:        # the all-zero Random123 vector is block 0 of (seed 0, stream 0)
+        assert ops.philox_raw(1, 0, 0, 0, cuda_device).cpu().numpy().view(np.uint32).tolist()[0] == list(exp)
+    n = 20_000_001
+    z = ops.philox_normal(n, 42, 3, cuda_device)
+    np.testing.assert_allclose(z[:4096].cpu().numpy(), OP.normals(4096, 42, 3), rtol=0, atol=2e-5)
+    zd = z.double()
+    m, s = zd.mean().item(), zd.std().item()
+    assert abs(m) < 1e-3 and abs(s - 1) < 1e-3
+    assert abs((zd ** 3).mean().item()) < 5e-3 and abs((zd ** 4).mean().item() - 3) < 1e-2
+    # KS distance against the normal CDF on a 1M subsample
+    sub = torch.sort(zd[:1_000_000]).values
+    cdf = 0.5 * (1 + torch.erf(sub / math.sqrt(2)))
+    emp = torch.arange(1, sub.numel() + 1, device=sub.device, dtype=torch.float64) / sub.numel()
+    assert (cdf - emp).abs().max().item() < 1.63 / math.sqrt(sub.numel())          # alpha = 0.01
+    # independent of launch shape: a different length / stream gives the same prefix / different values
+    assert torch.equal(ops.philox_normal(1003, 42, 3, cuda_device), z[:1003])
+    assert not torch.equal(ops.philox_normal(1003, 42, 4, cuda_device), z[:1003])
+
+
+def test_reference_statistical_window_and_budget(cuda_device):
+    """The reference's own checks: mean|noise|/sigma in [0.5, 2] (src/validation/privacy_validator.py:104-108) and
+    N calls at (0.1, 1e-6) consume exactly N x (0.1, 1e-6) (:166-212)."""
+    from flb200.privacy import create_privacy_engine
+    g = {"conv.weight": torch.zeros(64, 32, 3, 3), "fc.weight": torch.zeros(128, 3136), "fc.bias": None}
+    g["conv.weight"][0, 0, 0, 0] = 3.0                       # norm 3 > C -> sensitivity C = 1
+    eng = create_privacy_engine(epsilon=1.0, delta=1e-5, device=cuda_device)
+    for i in range(5):
+        noisy = eng.add_noise(g, 0.1, 1e-6)
+        assert noisy["fc.bias"] is None
+        sigma = OPV.gaussian_sigma(1.0, 0.1, 1e-6)
+        ratio = float(noisy["fc.weight"].abs().mean()) / sigma
+        assert 0.5 <= ratio <= 2.0 and abs(ratio - math.sqrt(2 / math.pi)) < 0.01
+        st = eng.budget_tracker.get_budget_status()
+        assert abs(st["consumed_epsilon"] - 0.1 * (i + 1)) < 1e-6 and abs(st["consumed_delta"] - 1e-6 * (i + 1)) < 1e-9
+    a = eng.add_noise(g, 0.1, 1e-6)["fc.weight"]
+    b = eng.add_noise(g, 0.1, 1e-6)["fc.weight"]
+    assert not torch.equal(a, b)                              # fresh stream per call
