@@ -40,6 +40,8 @@ def fedavg_weighted_sum(theta: torch.Tensor, w, P: Optional[int] = None, out: Op
     if out is None:
         out = torch.empty(P, dtype=torch.float32, device=theta.device)
         accumulate = False
+    if P == 0:
+        return out
     with torch.cuda.device(theta.device):
         L.call("flb_fedavg_weighted_sum", L.ptr(theta), ld, L.ptr(wt), L.ptr(out), K, P, int(accumulate),
                L.stream_ptr(theta.device))
