@@ -35,7 +35,31 @@ SIGNATURES = {
     "flb_philox_raw": [_vp, _ll, _ull, _ull, _ull, _vp],
     "flb_q8_quantize": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp],
     "flb_q8_dequantize": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
+    "flb_train_ws_bytes": [_i, _i, _i],
+    "flb_train_ws_offset": [_i, _i, _i, C.c_char_p],
+    "flb_train_begin_epoch": [_vp, _vp],
+    "flb_train_step": [_vp, _vp],
+    "flb_train_forward_backward": [_vp, _vp],
+    "flb_train_forward": [_vp, _vp],
+    "flb_train_advance": [_vp, _vp],
 }
+_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset"}
+
+
+
+class TrainArgs(C.Structure):
+    """``flb_train_args`` of include/flb.h, field for field."""
+    _fields_ = [
+        ("x", _vp), ("y", _vp), ("sample_off", _vp), ("nsamples", _vp), ("step_ctr", _vp),
+        ("W", _vp), ("G", _vp), ("M", _vp), ("V", _vp), ("tcount", _vp), ("ws", _vp),
+        ("loss_sum", _vp), ("correct", _vp), ("nbatch", _vp), ("nseen", _vp),
+        ("drop_keep", _vp), ("dp_z", _vp),
+        ("ld", _ll), ("seed", _ull), ("client_base", _ull),
+        ("lr", _d), ("beta1", _d), ("beta2", _d), ("eps", _d), ("weight_decay", _d), ("momentum", _d),
+        ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i),
+        ("drop_p", C.c_float), ("dp_clip", C.c_float), ("dp_sigma", C.c_float),
+    ]
+
 
 _lock = threading.Lock()
 _lib: Optional[C.CDLL] = None
@@ -56,7 +80,7 @@ def load() -> C.CDLL:
         lib.flb_last_error.argtypes = []
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here == header/library drift
-            fn.restype = C.c_int
+            fn.restype = C.c_longlong if name in _RESTYPE_LL else C.c_int
             fn.argtypes = argtypes
         _lib = lib
         return lib
@@ -80,6 +104,13 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise FlbError(f"{name}: {lib.flb_last_error().decode()} (code {rc})")
+
+
+def call_ll(name: str, *args) -> int:
+    v = getattr(load(), name)(*args)
+    if v < 0:
+        raise FlbError(f"{name}{args}: unsupported configuration")
+    return v
 
 
 def ptr(t: Optional[torch.Tensor]):

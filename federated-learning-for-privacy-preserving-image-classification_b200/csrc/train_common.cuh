@@ -1,0 +1,79 @@
+// Shared definitions for the batched-over-clients training kernels.
+//
+// Everything a step needs lives in HBM as client-major arrays: parameters / gradients / optimizer moments
+// [K, ld] (reference layer order and layouts, see layout.py), the clients' samples as one concatenated
+// [sum N_c, C*H*W] array, and an activation workspace carved by flb_train_ws_layout().  One launch of each
+// kernel serves ALL clients resident on the GPU (blockIdx.z / .y = client); per-step variation (which batch,
+// ragged last batch, finished clients) is derived on the device from *step_ctr, so a whole epoch is a fixed
+// launch sequence that can be captured in one CUDA graph.
+#pragma once
+#include "flb_common.cuh"
+#include "../../include/flb.h"
+
+// conv activations are stored NHWC on a zero-padded (Hp x Wp) grid per image so that a 3x3 tap is a constant
+// row shift of the flattened [pixels, C] matrix (implicit GEMM without im2col; TMA-friendly)
+struct ConvGeom {
+    int Cin, Cout, H, W, Hp, Wp;
+    __host__ __device__ int PP() const { return Hp * Wp; }
+};
+
+__device__ __forceinline__ int flb_bsz(const flb_train_args& a, int client) {
+    const int s = *a.step_ctr;
+    int r = a.nsamples[client] - s * a.B;
+    return r < 0 ? 0 : (r > a.B ? a.B : r);
+}
+
+// SimpleCNN parameter offsets in a row (reference named_parameters order, models_pytorch.py:69-80)
+struct SimpleCnnOff {
+    static constexpr int c1w = 0, c1b = 288, c2w = 320, c2b = 18752, f1w = 18816, f1b = 420224, f2w = 420352,
+                         f2b = 421632, P = 421642;
+};
+
+// workspace carve-up (element offsets are per client; total = K * per-client size)
+struct SimpleCnnWs {
+    float* a1p;      // [K][B][16*16][32]   conv1 output after ReLU+pool, padded NHWC (conv2 input)
+    uint8_t* idx1;   // [K][B][196][32]     pool-1 argmax (0..3)
+    float* z2;       // [K][B][16*16][64]   conv2 pre-activation (fp32 path) / dz2 in backward
+    float* a2;       // [K][B][3136]        conv2 output after ReLU+pool, NCHW-flattened (fc1 input)
+    uint8_t* idx2;   // [K][B][3136]
+    float* hpre;     // [K][B][128]         fc1 pre-activation without bias (split-K accumulated)
+    float* h;        // [K][B][128]         after bias, ReLU, dropout
+    float* logits;   // [K][B][10]
+    float* dlog;     // [K][B][10]
+    float* dh;       // [K][B][128]
+    float* da2;      // [K][B][3136]
+    float* da1p;     // [K][B][16*16][32]
+    float* norm2;    // [K][B]              per-sample squared gradient norms (dp_mode 1)
+    float* coef;     // [K][B]              per-sample clip coefficients
+    float* g1ps;     // [K][B][320]         per-sample conv1 weight+bias gradients (dp_mode 1)
+};
+
+static inline size_t flb_align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static inline size_t simplecnn_ws_carve(void* base, int K, int B, SimpleCnnWs* ws) {
+    size_t off = 0;
+    char* p = (char*)base;
+    const size_t KB = (size_t)K * B;
+#define CARVE(field, type, count)                                  \
+    do {                                                           \
+        if (ws) ws->field = (type*)(p + off);                      \
+        off = flb_align256(off + sizeof(type) * (size_t)(count));  \
+    } while (0)
+    CARVE(a1p, float, KB * 256 * 32);
+    CARVE(idx1, uint8_t, KB * 196 * 32);
+    CARVE(z2, float, KB * 256 * 64);
+    CARVE(a2, float, KB * 3136);
+    CARVE(idx2, uint8_t, KB * 3136);
+    CARVE(hpre, float, KB * 128);
+    CARVE(h, float, KB * 128);
+    CARVE(logits, float, KB * 10);
+    CARVE(dlog, float, KB * 10);
+    CARVE(dh, float, KB * 128);
+    CARVE(da2, float, KB * 3136);
+    CARVE(da1p, float, KB * 256 * 32);
+    CARVE(norm2, float, KB);
+    CARVE(coef, float, KB);
+    CARVE(g1ps, float, KB * 320);
+#undef CARVE
+    return off;
+}

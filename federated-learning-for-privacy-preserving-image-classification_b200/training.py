@@ -1,0 +1,478 @@
+"""Local client training behind the reference's ``LocalTrainer`` surface, plus the batched engine under it.
+
+``BatchedClientTrainer`` keeps K clients resident on one GPU as rows of ``[K, ld]`` parameter / gradient /
+optimizer-moment matrices and advances all of them one minibatch per launch sequence (``flb_train_step``);
+a whole epoch is captured once in a CUDA graph and replayed, and the loss / accuracy accumulators
+(``running_loss``, ``correct_predictions``, src/shared/training.py:200-203) stay on the device until the epoch ends --
+one host read per epoch instead of two syncs per step.
+
+``LocalTrainer`` mirrors src/shared/training.py:28-403 (constructor, ``train_local_model``, ``evaluate_model``,
+gradient hooks, checkpoints, ``TrainingError``) and is a K = 1 view of the same engine."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import logging
+import math
+import os
+import time
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from datetime import datetime
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .layout import ParamLayout
+from .models import TrainingMetrics
+from .models_pytorch import INPUT_SHAPES, MODEL_IDS, FederatedCNNBase, ModelFactory
+
+logger = logging.getLogger(__name__)
+
+OPTIMIZERS = {"adam": 0, "sgd": 1, "adamw": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1}
+MAX_BATCH = 32
+
+
+class TrainingError(Exception):
+    pass
+
+
+def model_layout(model_name: str, num_classes: int = 10) -> ParamLayout:
+    m = ModelFactory.create_model(model_name, num_classes=num_classes)
+    return ParamLayout(m.param_spec())
+
+
+def _cuda_device(device) -> torch.device:
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cuda")
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None and torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+class BatchedClientTrainer:
+    """K simulated clients training side by side on one GPU (the "batched across clients" engine)."""
+
+    def __init__(self, model_name: str, num_clients: int, device=None, batch_size: int = 32,
+                 dropout_rate: Optional[float] = None, precision: str = "fp32", seed: int = 42,
+                 client_base: int = 0, use_graph: bool = True):
+        if model_name not in MODEL_IDS:
+            raise ValueError(f"Unknown model: {model_name}. Available: {list(MODEL_IDS)}")
+        if model_name != "simple_cnn":
+            raise L.FlbError(f"BatchedClientTrainer: kernels for '{model_name}' are not built yet (simple_cnn only)")
+        if not (1 <= batch_size <= MAX_BATCH):
+            raise L.FlbError(f"batch_size must be in 1..{MAX_BATCH}, got {batch_size}")
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {list(PRECISIONS)}")
+        self.model_name = model_name
+        self.model_id = MODEL_IDS[model_name]
+        self.K = int(num_clients)
+        self.B = int(batch_size)
+        self.device = _cuda_device(device)
+        L.ensure_device(self.device)
+        self.precision = precision
+        self.seed = seed
+        self.client_base = client_base
+        self.use_graph = use_graph
+        self.dropout_rate = (0.25 if model_name == "simple_cnn" else 0.3) if dropout_rate is None else float(dropout_rate)
+        self.layout = model_layout(model_name)
+        self.sample_numel = math.prod(INPUT_SHAPES[model_name])
+        dev, K = self.device, self.K
+        lay = self.layout
+        self.W = lay.new_rows(K, dev)
+        self.G = lay.new_rows(K, dev)
+        self.M = lay.new_rows(K, dev)
+        self.V = lay.new_rows(K, dev)
+        self.tcount = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_sum = torch.zeros(K, dtype=torch.float32, device=dev)
+        self.correct = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.nbatch = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.nseen = torch.zeros(K, dtype=torch.int32, device=dev)
+        self.ws_bytes = L.call_ll("flb_train_ws_bytes", self.model_id, K, self.B)
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)      # pads of the NHWC grids stay zero forever
+        self.x = self.y = self.sample_off = self.nsamples = None
+        self.n_host: List[int] = []
+        self.drop_keep: Optional[torch.Tensor] = None
+        self.dp_z: Optional[torch.Tensor] = None
+        self.dp_mode, self.dp_clip, self.dp_sigma = 0, 1.0, 0.0
+        self._graph = None
+        self._graph_key = None
+        self._seen_key = None
+        self.args = L.TrainArgs()
+
+    # ---- state ---------------------------------------------------------------------------------------
+    def set_global_row(self, row: torch.Tensor) -> None:
+        """Every client starts the round from the same global model (src/client/federated_trainer.py:378)."""
+        self.W.copy_(row.to(self.device).view(1, -1).expand(self.K, -1))
+
+    def set_client_weights(self, k: int, weights: Dict[str, torch.Tensor]) -> None:
+        self.layout.flatten_into(self.W[k], weights)
+
+    def client_weights(self, k: int, device=None) -> Dict[str, torch.Tensor]:
+        return self.layout.unflatten(self.W[k], device)
+
+    def load_data(self, xs: Sequence[torch.Tensor], ys: Sequence[torch.Tensor]) -> None:
+        """xs[k]: [N_k, C, H, W] fp32, ys[k]: [N_k] integer labels (host or device); batches are consecutive slices
+        of ``batch_size`` samples, the last one ragged -- exactly what an unshuffled DataLoader yields."""
+        if len(xs) != self.K or len(ys) != self.K:
+            raise L.FlbError(f"load_data: expected {self.K} clients, got {len(xs)}")
+        ns = [int(x.shape[0]) for x in xs]
+        for x, y in zip(xs, ys):
+            if x[0].numel() != self.sample_numel if x.shape[0] else False:
+                raise L.FlbError(f"load_data: sample shape {tuple(x.shape[1:])} does not match {self.model_name}")
+            if y.shape[0] != x.shape[0]:
+                raise L.FlbError("load_data: data / target length mismatch")
+        dev = self.device
+        total = sum(ns)
+        self.x = torch.empty((max(total, 1), self.sample_numel), dtype=torch.float32, device=dev)
+        self.y = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        off = 0
+        offs = []
+        for x, y, n in zip(xs, ys, ns):
+            offs.append(off)
+            if n:
+                self.x[off:off + n].copy_(x.reshape(n, -1), non_blocking=True)
+                self.y[off:off + n].copy_(y.to(torch.int32), non_blocking=True)
+            off += n
+        self.sample_off = torch.tensor(offs, dtype=torch.int64).to(dev)
+        self.nsamples = torch.tensor(ns, dtype=torch.int32).to(dev)
+        self.n_host = ns
+        self.h2d_bytes = total * (self.sample_numel * 4 + 4)
+
+    def configure_dp(self, mode: str = "none", max_grad_norm: float = 1.0, sigma: float = 0.0,
+                     z: Optional[torch.Tensor] = None) -> None:
+        """mode 'none' (reference behaviour: plain minibatch descent) or 'per_sample' (north-star kernel 2):
+        g = (sum_i clip_C(g_i) + N(0, sigma^2)) / B inside every step.  ``z`` [K, ld] injects the standard normals."""
+        if mode not in ("none", "per_sample"):
+            raise ValueError("dp mode must be 'none' or 'per_sample'")
+        self.dp_mode = 0 if mode == "none" else 1
+        self.dp_clip, self.dp_sigma, self.dp_z = float(max_grad_norm), float(sigma), z
+        self._graph = None
+
+    # ---- launches --------------------------------------------------------------------------------------
+    def _fill_args(self, lr: float, optimizer_type: str, train: bool = True) -> None:
+        opt = optimizer_type.lower()
+        if opt not in OPTIMIZERS:
+            raise ValueError(f"Unknown optimizer type: {optimizer_type}")          # training.py:255
+        if self.x is None:
+            raise L.FlbError("no client data loaded")
+        a = self.args
+        p = lambda t: None if t is None else t.data_ptr()      # noqa: E731
+        a.x, a.y, a.sample_off, a.nsamples, a.step_ctr = p(self.x), p(self.y), p(self.sample_off), p(self.nsamples), p(self.step_ctr)
+        a.W, a.G, a.M, a.V, a.tcount, a.ws = p(self.W), p(self.G), p(self.M), p(self.V), p(self.tcount), p(self.ws)
+        a.loss_sum, a.correct, a.nbatch, a.nseen = p(self.loss_sum), p(self.correct), p(self.nbatch), p(self.nseen)
+        a.drop_keep, a.dp_z = p(self.drop_keep), p(self.dp_z)
+        a.ld, a.seed, a.client_base = self.layout.ld, self.seed, self.client_base
+        a.lr, a.beta1, a.beta2, a.eps = float(lr), 0.9, 0.999, 1e-8            # torch.optim.Adam / AdamW defaults
+        a.weight_decay = 0.01 if opt == "adamw" else 0.0
+        a.momentum = 0.9                                                          # training.py:251
+        a.model, a.K, a.B = self.model_id, self.K, self.B
+        a.precision, a.opt, a.dp_mode = PRECISIONS[self.precision], OPTIMIZERS[opt], self.dp_mode if train else 0
+        a.drop_p = self.dropout_rate if train else 0.0
+        a.dp_clip, a.dp_sigma = self.dp_clip, self.dp_sigma
+
+    def max_steps(self) -> int:
+        return (max(self.n_host) + self.B - 1) // self.B if self.n_host else 0
+
+    def _launch_epoch(self) -> None:
+        st = L.stream_ptr(self.device)
+        ap = C.byref(self.args)
+        L.call("flb_train_begin_epoch", ap, st)
+        for _ in range(self.max_steps()):
+            L.call("flb_train_step", ap, st)
+
+    def _run_epoch(self) -> None:
+        """Eager the first time a configuration is seen, captured into one CUDA graph (begin_epoch + every step of the
+        epoch) the second time, replayed afterwards.  All per-step variation is device-side, so the graph is static."""
+        with torch.cuda.device(self.device):
+            key = (bytes(self.args), self.max_steps())
+            if self.use_graph and self._graph is not None and self._graph_key == key:
+                self._graph.replay()
+                return
+            if self.use_graph and self._seen_key == key:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):            # capture only records; nothing executes here
+                    self._launch_epoch()
+                self._graph, self._graph_key = g, key
+                g.replay()
+                return
+            self._seen_key = key
+            self._launch_epoch()
+
+    def train(self, epochs: int, learning_rate: float = 0.001, optimizer_type: str = "adam"):
+        """One call = one ``train_local_model`` for every client: fresh optimizer state (training.py:89), ``epochs``
+        passes over each client's samples.  Returns per-client lists (loss, accuracy, samples_processed) where loss /
+        accuracy are those of the last epoch (training.py:143-144) and samples are summed over epochs (:105)."""
+        self._fill_args(learning_rate, optimizer_type, train=True)
+        self.M.zero_()
+        self.V.zero_()
+        self.tcount.zero_()
+        loss = acc = None
+        total = torch.zeros(self.K, dtype=torch.int64)
+        for _ in range(epochs):
+            self._run_epoch()
+            loss, acc, seen = self.epoch_metrics()
+            total += seen
+        if loss is None:
+            return [0.0] * self.K, [0.0] * self.K, [0] * self.K
+        return loss.tolist(), acc.tolist(), total.tolist()
+
+    def epoch_metrics(self):
+        """The one device->host read of an epoch: mean of batch-mean losses, accuracy, samples (training.py:209-212)."""
+        stats = torch.stack([self.loss_sum, self.correct.float(), self.nbatch.float(), self.nseen.float()]).cpu()
+        nb, ns = stats[2].clamp(min=1), stats[3].clamp(min=1)
+        return (stats[0] / nb).double(), (stats[1] / ns).double(), stats[3].long()
+
+    # ---- single-step entries used by tests / evaluation ---------------------------------------------------
+    def forward_backward(self, learning_rate: float = 0.001, optimizer_type: str = "adam") -> None:
+        self._fill_args(learning_rate, optimizer_type, train=True)
+        with torch.cuda.device(self.device):
+            st = L.stream_ptr(self.device)
+            L.call("flb_train_begin_epoch", C.byref(self.args), st)
+            L.call("flb_train_forward_backward", C.byref(self.args), st)
+
+    def ws_array(self, name: str, dtype, per_client: int) -> torch.Tensor:
+        off = L.call_ll("flb_train_ws_offset", self.model_id, self.K, self.B, name.encode())
+        nbytes = self.K * self.B * per_client * torch.empty(0, dtype=dtype).element_size()
+        return self.ws[off:off + nbytes].view(dtype).view(self.K, self.B, per_client)
+
+    def evaluate(self):
+        """Forward-only pass over the loaded samples (eval mode: no dropout).  Returns per-client
+        (mean batch loss, accuracy, samples) and the logits [sum N, classes] on the device."""
+        self._fill_args(0.0, "adam", train=False)
+        logits = torch.empty((self.x.shape[0], 10), dtype=torch.float32, device=self.device)
+        lg = self.ws_array("logits", torch.float32, 10)
+        with torch.cuda.device(self.device):
+            st = L.stream_ptr(self.device)
+            ap = C.byref(self.args)
+            L.call("flb_train_begin_epoch", ap, st)
+            offs = self.sample_off.tolist()
+            for s in range(self.max_steps()):
+                L.call("flb_train_forward", ap, st)
+                for k, n in enumerate(self.n_host):
+                    b = min(self.B, n - s * self.B)
+                    if b > 0:
+                        logits[offs[k] + s * self.B: offs[k] + s * self.B + b].copy_(lg[k, :b])
+                L.call("flb_train_advance", ap, st)
+        loss, acc, seen = self.epoch_metrics()
+        return loss.tolist(), acc.tolist(), seen.tolist(), logits
+
+
+# ----------------------------------------------------------------------------------------------------------
+def _collect_loader(loader: Iterable, max_batch: int = MAX_BATCH) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Drain one pass of a DataLoader-like iterable of (data, targets) into contiguous tensors.  The kernels consume
+    consecutive slices of a fixed batch size, so all batches but the last must have the same size."""
+    xs, ys, sizes = [], [], []
+    for data, targets in loader:
+        xs.append(data)
+        ys.append(targets)
+        sizes.append(int(targets.shape[0]))
+    if not xs:
+        raise ValueError("empty data loader")
+    bs = sizes[0]
+    if any(s != bs for s in sizes[:-1]) or sizes[-1] > bs:
+        raise ValueError(f"batches must share one size except a smaller last one, got sizes {sorted(set(sizes))}")
+    if bs > max_batch:
+        raise ValueError(f"batch size {bs} > {max_batch} is not supported by the batched kernels")
+    return torch.cat(xs), torch.cat(ys), bs
+
+
+def _engine_for(model: FederatedCNNBase, device, batch_size: int, precision: str) -> BatchedClientTrainer:
+    cache = model.__dict__.setdefault("_flb_engines", {})
+    key = (str(device), batch_size, precision)
+    if key not in cache:
+        cache[key] = BatchedClientTrainer(model.model_name, 1, device, batch_size, model.dropout_rate, precision)
+    return cache[key]
+
+
+def forward_logits(model: FederatedCNNBase, x: torch.Tensor, precision: str = "fp32") -> torch.Tensor:
+    """``model(x)`` through the CUDA forward kernels.  Dropout follows ``model.training`` like nn.Dropout."""
+    p = next(model.parameters())
+    if not p.is_cuda:
+        raise L.FlbError("model.forward: parameters are on the CPU; move the model to a CUDA device (no CPU path)")
+    eng = _engine_for(model, p.device, MAX_BATCH, precision)
+    eng.set_client_weights(0, {n: q.data for n, q in model.named_parameters()})
+    eng.load_data([x.detach().to(torch.float32)], [torch.zeros(x.shape[0], dtype=torch.int64)])
+    if model.training and model.dropout_rate > 0:
+        raise L.FlbError("model.forward in train mode with dropout is only available inside LocalTrainer")
+    return eng.evaluate()[3].to(x.device if x.is_cuda else p.device)
+
+
+class LocalTrainer:
+    """Drop-in for src/shared/training.py:28-403."""
+
+    def __init__(self, model: FederatedCNNBase, device: Optional[torch.device] = None,
+                 checkpoint_dir: Optional[str] = None, precision: str = "fp32"):
+        self.model = model
+        self.device = _cuda_device(device)
+        self.checkpoint_dir = checkpoint_dir
+        self.precision = precision
+        L.ensure_device(self.device)            # no CPU fallback: fail here, loudly
+        self.model.to(self.device)
+        self.current_epoch = 0
+        self.training_history: List[Dict[str, Any]] = []
+        self._last_grads: Dict[str, torch.Tensor] = {}
+        if self.checkpoint_dir:
+            os.makedirs(self.checkpoint_dir, exist_ok=True)
+
+    def _push(self, eng: BatchedClientTrainer) -> None:
+        eng.set_client_weights(0, {n: p.data for n, p in self.model.named_parameters()})
+
+    def _pull(self, eng: BatchedClientTrainer) -> None:
+        views = eng.layout.views(eng.W[0])
+        with torch.no_grad():
+            for n, p in self.model.named_parameters():
+                p.data.copy_(views[n])
+
+    def train_local_model(self, train_loader, epochs: int, learning_rate: float = 0.001,
+                          optimizer_type: str = "adam", loss_function: Optional[nn.Module] = None,
+                          validation_loader=None, save_checkpoints: bool = True,
+                          early_stopping_patience: Optional[int] = None) -> TrainingMetrics:
+        try:
+            start = time.time()
+            if loss_function is not None and not isinstance(loss_function, nn.CrossEntropyLoss):
+                raise ValueError("only nn.CrossEntropyLoss (the reference default) is implemented in the kernels")
+            if optimizer_type.lower() not in OPTIMIZERS:
+                raise ValueError(f"Unknown optimizer type: {optimizer_type}")
+            self.model.train()
+            eng = None
+            losses, accs = [], []
+            total_samples = 0
+            best_val, patience = float("inf"), 0
+            for epoch in range(epochs):
+                self.current_epoch = epoch
+                x, y, bs = _collect_loader(train_loader)          # one pass of the loader = one epoch (shuffling included)
+                if eng is None:
+                    eng = _engine_for(self.model, self.device, bs, self.precision)
+                    eng.dropout_rate = float(self.model.dropout_rate)
+                    self._push(eng)
+                    eng._fill_args(learning_rate, optimizer_type, train=True)
+                    eng.M.zero_(); eng.V.zero_(); eng.tcount.zero_()       # fresh optimizer (training.py:89)
+                elif eng.B != bs:
+                    raise ValueError("batch size changed between epochs")
+                eng.load_data([x], [y])
+                eng._fill_args(learning_rate, optimizer_type, train=True)
+                eng._run_epoch()
+                loss, acc, seen = eng.epoch_metrics()
+                losses.append(float(loss[0])); accs.append(float(acc[0]))
+                total_samples += int(seen[0])
+                self._pull(eng)
+                val_loss = None
+                if validation_loader:
+                    val_loss, _ = self._validate_epoch(validation_loader)
+                    self.model.train()
+                if save_checkpoints and self.checkpoint_dir:
+                    self._save_checkpoint(epoch, losses[-1], val_loss)
+                if early_stopping_patience and validation_loader:
+                    if val_loss < best_val:
+                        best_val, patience = val_loss, 0
+                    else:
+                        patience += 1
+                        if patience >= early_stopping_patience:
+                            break
+            if eng is not None:
+                self._last_grads = {n: v.clone() for n, v in eng.layout.views(eng.G[0]).items()}
+            metrics = TrainingMetrics(loss=losses[-1] if losses else 0.0, accuracy=accs[-1] if accs else 0.0,
+                                      epochs_completed=len(losses), training_time=time.time() - start,
+                                      samples_processed=total_samples)
+            self.training_history.append({"timestamp": datetime.now().isoformat(), "epochs": len(losses),
+                                          "final_loss": metrics.loss, "final_accuracy": metrics.accuracy,
+                                          "training_time": metrics.training_time, "samples_processed": total_samples})
+            return metrics
+        except Exception as e:
+            logger.error(f"Local training failed: {str(e)}")
+            raise TrainingError(f"Local training failed: {str(e)}")
+
+    def _validate_epoch(self, val_loader, criterion=None) -> Tuple[float, float]:
+        self.model.eval()
+        x, y, bs = _collect_loader(val_loader)
+        eng = _engine_for(self.model, self.device, bs, self.precision)
+        self._push(eng)
+        eng.load_data([x], [y])
+        loss, acc, _, _ = eng.evaluate()
+        return float(loss[0]), float(acc[0])
+
+    def evaluate_model(self, test_loader) -> Dict[str, float]:
+        try:
+            self.model.eval()
+            x, y, bs = _collect_loader(test_loader)
+            eng = _engine_for(self.model, self.device, bs, self.precision)
+            self._push(eng)
+            eng.load_data([x], [y])
+            _, _, _, logits = eng.evaluate()
+            pred = logits.argmax(1).cpu()
+            y = y.cpu().long()
+            hit = pred == y
+            out = {"overall_accuracy": hit.float().mean().item() if y.numel() else 0.0,
+                   "total_samples": int(y.numel()), "correct_predictions": int(hit.sum())}
+            for cls in torch.unique(y).tolist():
+                m = y == cls
+                out[f"class_{cls}_accuracy"] = int((hit & m).sum()) / int(m.sum())
+            return out
+        except Exception as e:
+            raise TrainingError(f"Model evaluation failed: {str(e)}")
+
+    def get_model_gradients(self) -> Dict[str, torch.Tensor]:
+        """Gradients of the last minibatch step (the kernels keep them in the flat G row, not in ``param.grad``)."""
+        return {n: g.clone() for n, g in self._last_grads.items()}
+
+    def set_model_gradients(self, gradients: Dict[str, torch.Tensor]):
+        for n, p in self.model.named_parameters():
+            if n in gradients:
+                p.grad = gradients[n].clone().to(p.device)
+
+    def _save_checkpoint(self, epoch: int, train_loss: float, val_loss: Optional[float] = None):
+        if not self.checkpoint_dir:
+            return
+        ckpt = {"epoch": epoch, "model_state_dict": self.model.state_dict(), "train_loss": train_loss,
+                "val_loss": val_loss, "timestamp": datetime.now().isoformat(), "model_info": self.model.get_model_info()}
+        torch.save(ckpt, os.path.join(self.checkpoint_dir, f"checkpoint_epoch_{epoch}.pt"))
+        torch.save(ckpt, os.path.join(self.checkpoint_dir, "latest_checkpoint.pt"))
+
+    def load_checkpoint(self, checkpoint_path: str) -> Dict[str, Any]:
+        try:
+            ckpt = torch.load(checkpoint_path, map_location=self.device)
+            self.model.load_state_dict(ckpt["model_state_dict"])
+            self.current_epoch = ckpt["epoch"]
+            return {"epoch": ckpt["epoch"], "train_loss": ckpt["train_loss"], "val_loss": ckpt.get("val_loss"),
+                    "timestamp": ckpt.get("timestamp")}
+        except Exception as e:
+            raise TrainingError(f"Failed to load checkpoint: {str(e)}")
+
+    def get_training_history(self) -> List[Dict[str, Any]]:
+        return self.training_history.copy()
+
+    def save_training_history(self, filepath: str):
+        try:
+            with open(filepath, "w") as f:
+                json.dump(self.training_history, f, indent=2)
+        except Exception as e:
+            logger.error(f"Failed to save training history: {str(e)}")
+
+    def reset_training_state(self):
+        self.current_epoch = 0
+        self.training_history = []
+
+
+@dataclass
+class FederatedTrainingConfig:
+    """src/shared/training.py:406-452 (same keyword order and defaults)."""
+    local_epochs: int = 5
+    batch_size: int = 32
+    learning_rate: float = 0.001
+    optimizer_type: str = "adam"
+    early_stopping_patience: Optional[int] = None
+    save_checkpoints: bool = True
+    validation_split: float = 0.1
+
+    def to_dict(self) -> Dict[str, Any]:
+        return dict(self.__dict__)
+
+    @classmethod
+    def from_dict(cls, config_dict: Dict[str, Any]) -> "FederatedTrainingConfig":
+        return cls(**config_dict)

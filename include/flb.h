@@ -62,6 +62,62 @@ int flb_q8_quantize(const float* x, long long ld, const long long* seg_off, uint
 int flb_q8_dequantize(const uint8_t* q, long long ldq, const long long* seg_off, const float* scale,
                       const float* zp, float* out, long long ld, int K, int L, long long P, void* stream);
 
+/* ---- batched local training: src/shared/training.py:60-212 (LocalTrainer._train_epoch), ------------------
+ *      models src/shared/models_pytorch.py:59-97 (SimpleCNN), optimizers training.py:244-255 ----------------
+ * One call advances EVERY resident client by one minibatch step (zero_grad -> forward -> mean cross-entropy ->
+ * backward -> optimizer step, training.py:189-197).  All pointers are device pointers; the struct itself is
+ * host memory and is read at call time only. */
+typedef struct flb_train_args {
+    /* data: the clients' samples concatenated; client k owns rows sample_off[k] .. sample_off[k]+nsamples[k] */
+    const float* x;               /* [sum N_c, C*H*W] fp32, NCHW per sample                          */
+    const int* y;                 /* [sum N_c] labels                                                */
+    const long long* sample_off;  /* [K]                                                             */
+    const int* nsamples;          /* [K]                                                             */
+    int* step_ctr;                /* [1] current minibatch index within the epoch (device-advanced)  */
+    /* state, client-major rows of pitch ld floats, reference layer order/layouts                    */
+    float* W;                     /* [K, ld] parameters                                              */
+    float* G;                     /* [K, ld] gradients (scratch)                                     */
+    float* M;                     /* [K, ld] Adam exp_avg / SGD momentum buffer                      */
+    float* V;                     /* [K, ld] Adam exp_avg_sq                                         */
+    int* tcount;                  /* [K] optimizer steps taken (device-advanced)                     */
+    void* ws;                     /* activation workspace, flb_train_ws_bytes() bytes, zeroed once   */
+    /* epoch accumulators (training.py:200-212): sum of batch-mean losses, argmax hits, batches, samples */
+    float* loss_sum;              /* [K] */
+    int* correct;                 /* [K] */
+    int* nbatch;                  /* [K] */
+    int* nseen;                   /* [K] */
+    const unsigned char* drop_keep; /* optional injected dropout keep-mask [K, B, 128] (NULL: Philox)  */
+    const float* dp_z;            /* optional injected standard normals [K, ld] for dp_mode 1 (NULL: Philox) */
+    long long ld;
+    unsigned long long seed;      /* Philox seed for dropout and per-sample-DP noise                 */
+    unsigned long long client_base; /* global index of local client 0 (Philox stream = client_base + k) */
+    double lr, beta1, beta2, eps, weight_decay, momentum;   /* torch.optim defaults are Python doubles */
+    int model;                    /* 0 = simple_cnn                                                  */
+    int K;                        /* resident clients                                                */
+    int B;                        /* batch size (<= 32)                                              */
+    int precision;                /* 0 = fp32 CUDA-core kernels, 1 = TF32 tcgen05 tensor-core kernels */
+    int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
+    int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise         */
+    float drop_p;                 /* dropout probability of SimpleCNN.dropout (0.25 upstream)        */
+    float dp_clip;                /* per-sample max_grad_norm C                                      */
+    float dp_sigma;               /* noise std of the summed clipped gradient (= C * sigma_unit)     */
+} flb_train_args;
+
+long long flb_train_ws_bytes(int model, int K, int B);
+/* pointers (as byte offsets into ws) of named workspace arrays, for tests: returns -1 if unknown */
+long long flb_train_ws_offset(int model, int K, int B, const char* name);
+/* zero the epoch accumulators and step counter (start of _train_epoch, training.py:178-182) */
+int flb_train_begin_epoch(const flb_train_args* a, void* stream);
+/* one minibatch step for all K clients; clients that have run out of samples are skipped */
+int flb_train_step(const flb_train_args* a, void* stream);
+/* forward + loss/accuracy accumulation only (LocalTrainer._validate_epoch / evaluate_model, training.py:214-242,
+ * 307-360; also model.forward): logits land in the workspace array "logits" */
+int flb_train_forward(const flb_train_args* a, void* stream);
+/* advance the device-side minibatch counter (and optimizer step counts) without a step */
+int flb_train_advance(const flb_train_args* a, void* stream);
+/* forward + loss/gradients only (no optimizer, no counter advance): fills G and the workspace, for parity tests */
+int flb_train_forward_backward(const flb_train_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "flb.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return re.findall(r"\b(?:int|const char\*)\s+(flb_\w+)\s*\(", src)
+    return re.findall(r"\b(?:int|long long|const char\*)\s+(flb_\w+)\s*\(", src)
 
 
 def test_library_exports_every_header_symbol():
@@ -32,7 +32,7 @@ def test_python_binding_matches_header():
 def test_header_argument_counts_match_binding():
     src = open(os.path.join(ROOT, "include", "flb.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    for name, args in re.findall(r"\bint\s+(flb_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for name, args in re.findall(r"\b(?:int|long long)\s+(flb_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         n = 0 if args.strip() in ("", "void") else len(args.split(","))
         assert n == len(_lib.SIGNATURES[name]), name
 
