@@ -224,9 +224,10 @@ class BatchedClientTrainer:
 
     def epoch_metrics(self):
         """The one device->host read of an epoch: mean of batch-mean losses, accuracy, samples (training.py:209-212)."""
-        stats = torch.stack([self.loss_sum, self.correct.float(), self.nbatch.float(), self.nseen.float()]).cpu()
+        stats = torch.stack([self.loss_sum.double(), self.correct.double(), self.nbatch.double(),
+                             self.nseen.double()]).cpu()
         nb, ns = stats[2].clamp(min=1), stats[3].clamp(min=1)
-        return (stats[0] / nb).double(), (stats[1] / ns).double(), stats[3].long()
+        return stats[0] / nb, stats[1] / ns, stats[3].long()
 
     # ---- single-step entries used by tests / evaluation ---------------------------------------------------
     def forward_backward(self, learning_rate: float = 0.001, optimizer_type: str = "adam") -> None:
@@ -351,7 +352,6 @@ class LocalTrainer:
                     eng = _engine_for(self.model, self.device, bs, self.precision)
                     eng.dropout_rate = float(self.model.dropout_rate)
                     self._push(eng)
-                    eng._fill_args(learning_rate, optimizer_type, train=True)
                     eng.M.zero_(); eng.V.zero_(); eng.tcount.zero_()       # fresh optimizer (training.py:89)
                 elif eng.B != bs:
                     raise ValueError("batch size changed between epochs")

@@ -38,3 +38,20 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def adam_trajectory_check(gold, prefix, weights, w0, lr, rel_l2=5e-3):
+    """Adam's update is ~lr*g/(|g|+eps): coordinates whose gradient is within rounding of zero take a different
+    +-lr step under ANY change of summation order, so trajectories are compared (SURVEY.md section 7 'hard parts') by
+    (a) |w - w_ref| <= 2*lr elementwise and (b) relative L2 error of the accumulated update, on the golden samples."""
+    import torch
+    num = den = 0.0
+    for k, t in weights.items():
+        a = t.detach().reshape(-1).to(torch.float32).cpu().numpy()
+        b0 = w0[k].detach().reshape(-1).cpu().numpy()
+        ref = gold[f"{prefix}/{k}/sample"]
+        got, start = (a[::STRIDE], b0[::STRIDE]) if a.size > 4096 else (a, b0)
+        assert np.abs(got - ref).max() <= 2 * lr, k
+        num += float(((got - ref).astype(np.float64) ** 2).sum())
+        den += float(((ref - start).astype(np.float64) ** 2).sum())
+    assert (num / den) ** 0.5 <= rel_l2, (num / den) ** 0.5

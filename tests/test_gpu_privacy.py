@@ -99,7 +99,8 @@ def test_batched_client_glue_sigma0_and_injected(cuda_device):
         clipped_any |= n_ref > 1.0
         np.testing.assert_allclose(out0[k, :P].cpu().numpy(), ref0["w"].numpy(), rtol=0, atol=1e-6)
         ref1, _, sigma = OPV.apply_update_dp(wlk, wgk, 1.0, 1e-5, 1.0, {"w": torch.from_numpy(z[k])})
-        np.testing.assert_allclose(out1[k, :P].cpu().numpy(), ref1["w"].numpy(), rtol=0, atol=2e-6 * max(1.0, sigma))
+        np.testing.assert_allclose(out1[k, :P].cpu().numpy(), ref1["w"].numpy(), rtol=0,
+                                   atol=5e-6 * sigma * float(np.abs(z[k]).max()) + 1e-6)   # sigma inherits the 5e-6 norm tolerance when unclipped
     assert clipped_any
 
 
