@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- one "step" = one full FedAvg round of the hot path on synthetic MNIST-shaped data:
+every resident client trains 1 local epoch of the SimpleCNN (batch 32, Adam 1e-3) from the global model, the
+update-level DP clip + Gaussian noise is applied to every client's delta, and the updates are FedAvg-aggregated
+(NCCL all-reduce across ranks when N > 1).  Workload at N = 1 = BASELINE.json configs[1] (10 clients, DP, 1 B200);
+weak scaling: 10 clients per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                  (this framework)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  (CPU restatement of the reference path)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL = "simple_cnn"
+CLIENTS_PER_GPU = 10
+FLOP_PER_SAMPLE = 25.0e6          # fwd + bwd, 2 * MAC
+METRIC = "DP-SGD client samples/s (one FedAvg round: local epoch + update-level DP + aggregation)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline_run(n_clients: int, threads: int, rounds: int = 1):
+    """The reference path restated on the CPU (oracle/round.py: LocalTrainer loop + update-level DP + FedAvg), on a
+    bounded sample of the same workload.  Returns (samples/s, sample description)."""
+    from oracle import models as OM
+    from oracle import round as OR
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    w0 = OM.init_weights(MODEL, 0)
+    data = [OR.synthetic_client_data(MODEL, c) for c in range(n_clients)]
+    OR.federated_round(MODEL, w0, 1, dp=True, data=data[:1], dropout_rate=0.0)          # untimed warm-up client (oneDNN init)
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(rounds):
+        _, info = OR.federated_round(MODEL, w0, n_clients, dp=True, data=data, dropout_rate=0.0)
+        n += sum(info["num_samples"])
+    dt = time.perf_counter() - t0
+    return n / dt, f"{rounds} round(s) x {n_clients} clients x 1 local epoch (batch 32, Adam) + update-level DP + FedAvg, {n} samples in {dt:.1f} s"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample = cpu_baseline_run(CLIENTS_PER_GPU, threads, 2)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: SimpleCNN MNIST-shaped, update-level DP, FedAvg; each step = 2 rounds of 10 clients",
+                       "clients_per_gpu": CLIENTS_PER_GPU},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("FLB_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--dp-mode", default="update", choices=["update", "per_sample", "none"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import flb200  # noqa: F401
+    from flb200.models_pytorch import ModelFactory
+    from flb200.simulation import FederatedRoundEngine, synthetic_client_data, synthetic_num_samples
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    n_clients = CLIENTS_PER_GPU * world
+
+    eng = FederatedRoundEngine(MODEL, n_clients, dev, rank=rank, world_size=world, process_group=pg, batch_size=32,
+                               local_epochs=1, learning_rate=1e-3, optimizer_type="adam", dp_mode=args.dp_mode,
+                               epsilon=1.0, delta=1e-5, max_grad_norm=1.0, dropout_rate=0.25, precision=args.precision)
+    torch.manual_seed(0)
+    w0 = ModelFactory.create_model(MODEL).get_model_weights()
+    eng.set_global_weights(w0)
+    host = [synthetic_client_data(MODEL, i) for i in eng.client_ids]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+    sizes_all = [synthetic_num_samples(MODEL, i) for i in range(n_clients)]
+    eng.load_data([h[0] for h in host], [h[1] for h in host], sizes_all)
+    samples_round_local = eng.samples_per_round()
+    samples_round = sum(sizes_all)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_rounds(n, e2e=False):
+        """device time (CUDA events on the launch stream) summed over n rounds, L2 flushed before each"""
+        total = 0.0
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                eng.load_data([h[0] for h in host], [h[1] for h in host], sizes_all)       # H2D from pinned memory
+                out = eng.run_round(read_metrics=True)                                      # D2H: losses / accuracies
+                gw = eng.global_row[:eng.layout.P].cpu()                                    # D2H: the aggregated model
+            else:
+                eng.run_round(read_metrics=False)
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    for _ in range(args.warmup):
+        eng.run_round(read_metrics=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed_rounds(args.steps)
+    barrier()
+    sampler.stop_flag = True
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    value = samples_round * args.steps / (ms / 1e3)
+
+    # end to end through the public API: host buffers in, aggregated model + metrics out, every step
+    timed_rounds(1, e2e=True)
+    barrier()
+    ms_e2e = timed_rounds(args.steps, e2e=True)
+    barrier()
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    h2d = eng.trainer.h2d_bytes
+    d2h = eng.layout.P * 4 + 4 * 8 * len(eng.client_ids)
+
+    # per-kernel breakdown of one step, CUDA events on the launch stream (eager, outside the timed region)
+    tr = eng.trainer
+    tr.set_global_row(eng.global_row)
+    tr._fill_args(eng.lr, eng.optimizer_type, train=True)
+    import ctypes as C
+    from flb200 import _lib as L
+    L.call("flb_train_begin_epoch", C.byref(tr.args), L.stream_ptr(dev))
+    tr.profile_step()
+    acc = {}
+    reps = 5
+    for _ in range(reps):
+        for k, v in tr.profile_step().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    step_ms = sum(acc.values())
+    top = max(acc, key=acc.get)
+    pk = peaks()
+    K_local, B = len(eng.client_ids), 32
+    # algorithmic FLOPs of the GEMM-shaped kernels per launch (all resident clients, full batch)
+    flops = {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288,
+             "fc1_fwd": 2 * 3136 * 128, "fc1_dgrad": 2 * 3136 * 128, "fc1_wgrad": 2 * 3136 * 128}
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    if top in flops:
+        ach = flops[top] * B * K_local / (acc[top] * 1e-3) / 1e12
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                "traffic": None, "peak_source": "0.5 x sustained bf16 of " + pk["source"] + " (TF32 = half bf16 rate)"}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+    roof["share_of_step"] = acc[top] / step_ms
+    roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in acc.items()}
+
+    launches_round = tr.launches_per_epoch() + (2 if args.dp_mode == "update" else 0) + 1
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: SimpleCNN MNIST-shaped 28x28, 10 clients/GPU x 1 local epoch (batch 32, Adam 1e-3, dropout 0.25), "
+                                   "update-level DP (eps=1, delta=1e-5, C=1), FedAvg" + (" + NCCL all-reduce" if world > 1 else ""),
+                       "clients": n_clients, "samples_per_round": samples_round, "dp_mode": args.dp_mode, "precision": args.precision,
+                       "l2": "flushed (256 MB write) before every timed round", "round_ms": ms / args.steps},
+            "e2e": {"value": samples_round * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_round * args.steps,
+            "roofline": roof, "clocks": sampler.summary()}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sample = cpu_baseline_run(CLIENTS_PER_GPU, threads, 4)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,7 @@ SIGNATURES = {
     "flb_fedavg_weighted_sum_ptrs": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_fedavg_weighted_sum_q8": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_dp_sumsq": [_vp, _ll, _vp, _vp, _i, _ll, _vp],
-    "flb_dp_clip_noise": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _i, _ll, _vp],
+    "flb_dp_clip_noise": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _ull, _i, _ll, _vp],
     "flb_dp_add_noise": [_vp, _ll, _vp, _vp, _d, _ull, _ull, _i, _ll, _vp],
     "flb_philox_normal": [_vp, _ll, _ull, _ull, _vp],
     "flb_philox_raw": [_vp, _ll, _ull, _ull, _ull, _vp],
@@ -42,6 +42,8 @@ SIGNATURES = {
     "flb_train_forward_backward": [_vp, _vp],
     "flb_train_forward": [_vp, _vp],
     "flb_train_advance": [_vp, _vp],
+    "flb_train_step_launches": [_vp],
+    "flb_train_step_profiled": [_vp, _vp, C.c_char_p, _i, _vp, _i],
 }
 _RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset"}
 
@@ -54,7 +56,7 @@ class TrainArgs(C.Structure):
         ("W", _vp), ("G", _vp), ("M", _vp), ("V", _vp), ("tcount", _vp), ("ws", _vp),
         ("loss_sum", _vp), ("correct", _vp), ("nbatch", _vp), ("nseen", _vp),
         ("drop_keep", _vp), ("dp_z", _vp),
-        ("ld", _ll), ("seed", _ull), ("client_base", _ull),
+        ("ld", _ll), ("seed", _ull), ("client_base", _ull), ("client_stride", _ull),
         ("lr", _d), ("beta1", _d), ("beta2", _d), ("eps", _d), ("weight_decay", _d), ("momentum", _d),
         ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i),
         ("drop_p", C.c_float), ("dp_clip", C.c_float), ("dp_sigma", C.c_float),

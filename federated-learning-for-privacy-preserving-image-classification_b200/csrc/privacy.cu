@@ -59,7 +59,7 @@ dp_clip_noise_kernel(const float* __restrict__ local, long long ld, const float*
                      const float* __restrict__ z_in, const double* __restrict__ norm2,
                      float* __restrict__ out, float* __restrict__ norms_out,
                      double max_norm, double sigma_unit, unsigned long long seed,
-                     unsigned long long stream_base, long long P) {
+                     unsigned long long stream_base, unsigned long long stream_stride, long long P) {
     const int k = blockIdx.y;
     const double n = sqrt(norm2[k]);
     const float coef = n > max_norm ? (float)(max_norm / n) : 1.0f;        // privacy.py:127-131
@@ -88,7 +88,7 @@ dp_clip_noise_kernel(const float* __restrict__ local, long long ld, const float*
             }
         }
         if (noisy && !zrow) {
-            const float4 zz = flb_normal4(seed, stream_base + (unsigned long long)k, (unsigned long long)c);
+            const float4 zz = flb_normal4(seed, stream_base + stream_stride * (unsigned long long)k, (unsigned long long)c);
             z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
         }
         float r[4];
@@ -170,7 +170,7 @@ extern "C" int flb_dp_sumsq(const float* local, long long ld, const float* globa
 extern "C" int flb_dp_clip_noise(const float* local, long long ld, const float* global_w, const float* z_in,
                                  const double* norm2, float* out, float* norms_out, double max_norm,
                                  double sigma_unit, unsigned long long seed, unsigned long long stream_base,
-                                 int K, long long P, void* stream) {
+                                 unsigned long long stream_stride, int K, long long P, void* stream) {
     FLB_CHECK_ARG(local && norm2 && out, "flb_dp_clip_noise: null pointer");
     FLB_CHECK_ARG(K >= 1 && K <= 65535 && P >= 0 && ld >= P, "flb_dp_clip_noise: need 1 <= K <= 65535, ld >= P");
     FLB_CHECK_ARG(max_norm > 0.0 && sigma_unit >= 0.0, "flb_dp_clip_noise: need max_norm > 0 and sigma_unit >= 0");
@@ -179,8 +179,8 @@ extern "C" int flb_dp_clip_noise(const float* local, long long ld, const float* 
     const bool vec = (ld % 4 == 0) && ((uintptr_t)local % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      (!global_w || (uintptr_t)global_w % 16 == 0) && (!z_in || (uintptr_t)z_in % 16 == 0);
     dim3 grid(blocks_per_client(P, K), K);
-    if (vec) dp_clip_noise_kernel<true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, P);
-    else dp_clip_noise_kernel<false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, P);
+    if (vec) dp_clip_noise_kernel<true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
+    else dp_clip_noise_kernel<false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

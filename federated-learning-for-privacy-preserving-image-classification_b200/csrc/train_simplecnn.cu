@@ -22,6 +22,22 @@
 
 namespace {
 
+// per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
+struct StepProfile {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[48];
+    const char* name[48];
+};
+StepProfile g_prof;
+#define MARK(label)                                                       \
+    do {                                                                  \
+        if (g_prof.on && g_prof.n < 48) {                                 \
+            cudaEventRecord(g_prof.ev[g_prof.n], st);                     \
+            g_prof.name[g_prof.n++] = label;                              \
+        }                                                                 \
+    } while (0)
+
 using Off = SimpleCnnOff;
 constexpr int PP2 = 256;     // conv2 runs on a 16x16 padded grid (14x14 real)
 constexpr int WP2 = 16;
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
             bool keep;
             if (a.drop_keep) keep = a.drop_keep[kb * 128 + e] != 0;
             else {
-                const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + k,
+                const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
                                                   ((unsigned long long)a.tcount[k] << 12) + (e >> 2));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
                 keep = flb_u01(rr[e & 3]) >= a.drop_p;
@@ -551,7 +567,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P)
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
-            const float4 zz = flb_normal4(a.seed, a.client_base + k, ((unsigned long long)t << 32) + c4);
+            const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
             z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
         }
 #pragma unroll
@@ -612,17 +628,23 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     const int K = a.K, B = a.B;
     const dim3 per_sample(B, K);
     FLB_CUDA(cudaMemsetAsync(ws.hpre, 0, sizeof(float) * (size_t)K * B * 128, st));
+    MARK("begin");
     conv1_fwd_pool_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    MARK("conv1_fwd_pool");
     {
         ConvFwdProb p{}; p.a = a; p.g = kConv2; p.xin_all = ws.a1p; p.z_all = ws.z2; p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, B * PP2, 64, 1, K, st);
     }
+    MARK("conv2_fwd");
     pool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    MARK("pool2");
     {
         LinFwdProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.act_all = ws.a2; p.out_all = ws.hpre;
         simt::launch(p, B, 128, 14, K, st);
     }
+    MARK("fc1_fwd");
     head_fwd_bwd_kernel<<<K, 256, 0, st>>>(a, ws);
+    MARK("head_fwd_bwd");
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -642,11 +664,14 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         LinDgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.dout_all = ws.dh; p.dact_all = ws.da2;
         simt::launch(p, B, 3136, 1, K, st);
     }
+    MARK("fc1_dgrad");
     unpool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    MARK("unpool2");
     {
         ConvDgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.dx_all = ws.da1p; p.woff = Off::c2w;
         simt::launch(p, B * PP2, 32, 1, K, st);
     }
+    MARK("conv2_dgrad");
 
     // ---- per-sample clip coefficients (dp_mode 1) ----
     const float* coef = nullptr;
@@ -659,22 +684,27 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         conv1_bwd_kernel<<<per_sample, 256, 0, st>>>(a, ws, 1);
         clip_coef_kernel<<<flb_cdiv(K * B, 256), 256, 0, st>>>(a, ws);
         coef = ws.coef;
+        MARK("per_sample_norms");
     }
 
     // ---- weight gradients ----
     head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws, a.dp_mode == 1);
+    MARK("head_wgrad");
     {
         LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
         p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
         simt::launch(p, 128, 3137, 1, K, st);
     }
+    MARK("fc1_wgrad");
     {
         ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
         p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, 64, 289, 16, K, st);
     }
+    MARK("conv2_wgrad");
     if (a.dp_mode == 1) conv1_ps_reduce_kernel<<<K, 320, 0, st>>>(a, ws);
     else conv1_bwd_kernel<<<per_sample, 256, 0, st>>>(a, ws, 0);
+    MARK("conv1_wgrad");
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -729,7 +759,47 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     if (int rc = forward_backward(*a, st)) return rc;
     const int blocks = max(1, min(flb_cdiv(Off::P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
     optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, Off::P);
+    MARK("optimizer");
     advance_kernel<<<1, 1024, 0, st>>>(*a);
+    MARK("advance");
     FLB_LAUNCH_CHECK();
     return FLB_OK;
+}
+
+// number of kernel launches (memsets excluded) one flb_train_step issues for these args
+extern "C" int flb_train_step_launches(const flb_train_args* a) {
+    if (!a) return -1;
+    return a->dp_mode == 1 ? 18 : 14;
+}
+
+// One step with a CUDA event after every kernel.  Synchronises the stream (profiling aid, not the product path).
+// names_out receives '\n'-separated labels; ms_out[i] = device time of labelled segment i.  Returns the segment count.
+extern "C" int flb_train_step_profiled(const flb_train_args* a, void* stream, char* names_out, int names_cap,
+                                       float* ms_out, int max_n) {
+    if (int rc = check_args(a)) return rc;
+    FLB_CHECK_ARG(names_out && ms_out && names_cap > 0 && max_n > 0, "flb_train_step_profiled: bad output buffers");
+    for (int i = 0; i < 48; ++i) FLB_CUDA(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.n = 0;
+    g_prof.on = true;
+    const int rc = flb_train_step(a, stream);
+    g_prof.on = false;
+    int n = 0;
+    if (rc == FLB_OK && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess) {
+        names_out[0] = 0;
+        size_t used = 0;
+        for (int i = 1; i < g_prof.n && n < max_n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_prof.ev[i - 1], g_prof.ev[i]);
+            ms_out[n++] = ms;
+            const size_t len = strlen(g_prof.name[i]);
+            if (used + len + 2 < (size_t)names_cap) {
+                memcpy(names_out + used, g_prof.name[i], len);
+                used += len;
+                names_out[used++] = '\n';
+                names_out[used] = 0;
+            }
+        }
+    }
+    for (int i = 0; i < 48; ++i) cudaEventDestroy(g_prof.ev[i]);
+    return rc == FLB_OK ? n : rc;
 }

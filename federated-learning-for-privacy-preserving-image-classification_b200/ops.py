@@ -84,7 +84,7 @@ def gaussian_sigma_unit(epsilon: float, delta: float) -> float:
 
 def dp_clip_noise(local: torch.Tensor, global_w: Optional[torch.Tensor], max_norm: float, sigma_unit: float,
                   seed: int = 0, stream_base: int = 0, z: Optional[torch.Tensor] = None, P: Optional[int] = None,
-                  out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  out: Optional[torch.Tensor] = None, stream_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
     """Batched update-level DP over K client rows.  Returns (upload rows [K, ld], ||delta_k|| [K])."""
     L.require_cuda_f32(local, "local")
     L.ensure_device(local.device)
@@ -106,7 +106,7 @@ def dp_clip_noise(local: torch.Tensor, global_w: Optional[torch.Tensor], max_nor
         L.call("flb_dp_sumsq", L.ptr(local), ld, L.ptr(global_w), L.ptr(norm2), K, P, st)
         L.call("flb_dp_clip_noise", L.ptr(local), ld, L.ptr(global_w), L.ptr(z), L.ptr(norm2), L.ptr(out),
                L.ptr(norms), float(max_norm), float(sigma_unit), int(seed) & (2**64 - 1),
-               int(stream_base) & (2**64 - 1), K, P, st)
+               int(stream_base) & (2**64 - 1), int(stream_stride), K, P, st)
     return out, norms
 
 

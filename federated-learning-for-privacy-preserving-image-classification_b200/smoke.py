@@ -1,0 +1,35 @@
+"""__graft_entry__.smoke(): one small federated round on cuda:0 checked against the CPU oracle.
+(The only product-tree file allowed to import ``oracle`` -- it is the checker here, not the path.)"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def run(device: torch.device) -> None:
+    from oracle import models as OM
+    from oracle import round as OR
+    from .simulation import FederatedRoundEngine
+
+    model, K, sizes = "simple_cnn", 3, [40, 33, 64]
+    w0 = OM.init_weights(model, 13)
+    data = [OR.synthetic_client_data(model, c, n=sizes[c]) for c in range(K)]
+    gen = torch.Generator().manual_seed(61)
+    spec = OM.model_spec(model)
+    zs = [{k: torch.randn(spec[k], generator=gen) * 1e-3 for k in spec} for _ in range(K)]
+    ref, info = OR.federated_round(model, w0, K, dp=True, zs=zs, data=data, batch_size=8, lr=1e-2, optimizer="sgd")
+
+    eng = FederatedRoundEngine(model, K, device, batch_size=8, learning_rate=1e-2, optimizer_type="sgd",
+                               dp_mode="update", dropout_rate=0.0, precision="fp32")
+    eng.set_global_weights(w0)
+    eng.load_data([d[0] for d in data], [d[1] for d in data], sizes)
+    zrows = eng.layout.new_rows(K, eng.device)
+    for k in range(K):
+        eng.layout.flatten_into(zrows[k], zs[k])
+    eng.dp_z = zrows
+    out = eng.run_round()
+    got = eng.global_weights("cpu")
+    for name in ref:
+        np.testing.assert_allclose(got[name].numpy(), ref[name].numpy(), rtol=2e-4, atol=2e-6, err_msg=name)
+    assert out["samples"] == sizes
+    print(f"smoke ok: round of {K} clients matches the oracle; losses {['%.4f' % l for l in out['losses']]}")

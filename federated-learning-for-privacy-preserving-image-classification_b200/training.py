@@ -59,7 +59,7 @@ class BatchedClientTrainer:
 
     def __init__(self, model_name: str, num_clients: int, device=None, batch_size: int = 32,
                  dropout_rate: Optional[float] = None, precision: str = "fp32", seed: int = 42,
-                 client_base: int = 0, use_graph: bool = True):
+                 client_base: int = 0, client_stride: int = 1, use_graph: bool = True):
         if model_name not in MODEL_IDS:
             raise ValueError(f"Unknown model: {model_name}. Available: {list(MODEL_IDS)}")
         if model_name != "simple_cnn":
@@ -77,6 +77,7 @@ class BatchedClientTrainer:
         self.precision = precision
         self.seed = seed
         self.client_base = client_base
+        self.client_stride = client_stride
         self.use_graph = use_graph
         self.dropout_rate = (0.25 if model_name == "simple_cnn" else 0.3) if dropout_rate is None else float(dropout_rate)
         self.layout = model_layout(model_name)
@@ -167,7 +168,7 @@ class BatchedClientTrainer:
         a.W, a.G, a.M, a.V, a.tcount, a.ws = p(self.W), p(self.G), p(self.M), p(self.V), p(self.tcount), p(self.ws)
         a.loss_sum, a.correct, a.nbatch, a.nseen = p(self.loss_sum), p(self.correct), p(self.nbatch), p(self.nseen)
         a.drop_keep, a.dp_z = p(self.drop_keep), p(self.dp_z)
-        a.ld, a.seed, a.client_base = self.layout.ld, self.seed, self.client_base
+        a.ld, a.seed, a.client_base, a.client_stride = self.layout.ld, self.seed, self.client_base, self.client_stride
         a.lr, a.beta1, a.beta2, a.eps = float(lr), 0.9, 0.999, 1e-8            # torch.optim.Adam / AdamW defaults
         a.weight_decay = 0.01 if opt == "adamw" else 0.0
         a.momentum = 0.9                                                          # training.py:251
@@ -203,6 +204,24 @@ class BatchedClientTrainer:
                 return
             self._seen_key = key
             self._launch_epoch()
+
+    def profile_step(self) -> "OrderedDict[str, float]":
+        """Per-kernel device milliseconds of ONE step (CUDA events after every kernel; synchronises).  The step is a
+        real one: it advances the epoch's minibatch counter."""
+        buf = C.create_string_buffer(4096)
+        ms = (C.c_float * 48)()
+        with torch.cuda.device(self.device):
+            n = L.load().flb_train_step_profiled(C.byref(self.args), L.stream_ptr(self.device), buf, 4096, ms, 48)
+        if n < 0:
+            raise L.FlbError(L.load().flb_last_error().decode())
+        names = buf.value.decode().split("\n")[:n]
+        out: "OrderedDict[str, float]" = OrderedDict()
+        for nm, v in zip(names, ms):
+            out[nm] = out.get(nm, 0.0) + float(v)
+        return out
+
+    def launches_per_epoch(self) -> int:
+        return 1 + self.max_steps() * int(L.load().flb_train_step_launches(C.byref(self.args)))
 
     def train(self, epochs: int, learning_rate: float = 0.001, optimizer_type: str = "adam"):
         """One call = one ``train_local_model`` for every client: fresh optimizer state (training.py:89), ``epochs``

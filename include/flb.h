@@ -41,11 +41,11 @@ int flb_dp_sumsq(const float* local, long long ld, const float* global_w, double
                  int K, long long P, void* stream);
 /* out[k] = global + clip(local[k]-global)*1 + sigma_k*z ; sigma_k = min(||delta_k||, max_norm)*sigma_unit,
  * sigma_unit = sqrt(2 ln(1.25/delta))/epsilon (0 disables noise).  z_in (may be NULL) injects the standard
- * normals; otherwise z = Philox4x32-10(seed, stream_base + k, element).  norms_out[k] (may be NULL) = ||delta_k||. */
+ * normals; otherwise z = Philox4x32-10(seed, stream_base + k*stream_stride, element).  norms_out[k] (may be NULL) = ||delta_k||. */
 int flb_dp_clip_noise(const float* local, long long ld, const float* global_w, const float* z_in,
                       const double* norm2, float* out, float* norms_out, double max_norm,
                       double sigma_unit, unsigned long long seed, unsigned long long stream_base,
-                      int K, long long P, void* stream);
+                      unsigned long long stream_stride, int K, long long P, void* stream);
 /* out[k] = x[k] + sigma * z  (GaussianNoiseGenerator.add_noise_to_gradients alone, privacy.py:221-254) */
 int flb_dp_add_noise(const float* x, long long ld, const float* z_in, float* out, double sigma,
                      unsigned long long seed, unsigned long long stream_base, int K, long long P, void* stream);
@@ -90,7 +90,8 @@ typedef struct flb_train_args {
     const float* dp_z;            /* optional injected standard normals [K, ld] for dp_mode 1 (NULL: Philox) */
     long long ld;
     unsigned long long seed;      /* Philox seed for dropout and per-sample-DP noise                 */
-    unsigned long long client_base; /* global index of local client 0 (Philox stream = client_base + k) */
+    unsigned long long client_base; /* global index of local client 0 (Philox stream = client_base + k*client_stride) */
+    unsigned long long client_stride; /* global-index distance between consecutive local clients (= world size) */
     double lr, beta1, beta2, eps, weight_decay, momentum;   /* torch.optim defaults are Python doubles */
     int model;                    /* 0 = simple_cnn                                                  */
     int K;                        /* resident clients                                                */
@@ -110,6 +111,12 @@ long long flb_train_ws_offset(int model, int K, int B, const char* name);
 int flb_train_begin_epoch(const flb_train_args* a, void* stream);
 /* one minibatch step for all K clients; clients that have run out of samples are skipped */
 int flb_train_step(const flb_train_args* a, void* stream);
+/* kernels launched by one flb_train_step with these args (for launch accounting under CUDA-graph replay) */
+int flb_train_step_launches(const flb_train_args* a);
+/* profiling aid: one step with a CUDA event after every kernel; synchronises.  names_out: newline-separated labels,
+ * ms_out[i]: device milliseconds of segment i.  Returns the number of segments (>= 0) or an error code. */
+int flb_train_step_profiled(const flb_train_args* a, void* stream, char* names_out, int names_cap,
+                            float* ms_out, int max_n);
 /* forward + loss/accuracy accumulation only (LocalTrainer._validate_epoch / evaluate_model, training.py:214-242,
  * 307-360; also model.forward): logits land in the workspace array "logits" */
 int flb_train_forward(const flb_train_args* a, void* stream);
