@@ -40,7 +40,7 @@ def test_round_matches_reference_golden(cuda_device):
         g_loss, g_acc, g_n = gold[f"client{c}/metrics"]
         assert out["samples"][c] == int(g_n) and abs(out["losses"][c] - g_loss) < 1e-4 and abs(out["accuracies"][c] - g_acc) < 1e-9
         sens, sigma = gold[f"client{c}/sens_sigma"]
-        assert abs(eng.norms[c].item() - sens) < 2e-3 * sens        # ||delta|| after 2-4 Adam steps (sign-sensitive coordinates)
+        assert abs(min(eng.norms[c].item(), 1.0) - sens) < 2e-3 * sens     # sensitivity = min(||delta||, C)
     # global model: Adam steps of +-lr on near-zero-gradient coordinates differ (see conftest.adam_trajectory_check);
     # the aggregated update is compared on its own scale
     got = eng.global_weights("cpu")
