@@ -58,7 +58,7 @@ class TrainArgs(C.Structure):
         ("drop_keep", _vp), ("dp_z", _vp),
         ("ld", _ll), ("seed", _ull), ("client_base", _ull), ("client_stride", _ull),
         ("lr", _d), ("beta1", _d), ("beta2", _d), ("eps", _d), ("weight_decay", _d), ("momentum", _d),
-        ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i),
+        ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i), ("tc_mask", _i),
         ("drop_p", C.c_float), ("dp_clip", C.c_float), ("dp_sigma", C.c_float),
     ]
 

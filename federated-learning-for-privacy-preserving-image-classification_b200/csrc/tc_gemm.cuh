@@ -1,0 +1,185 @@
+// tcgen05 / TMEM / TMA building blocks and the warp-specialised grouped-GEMM skeleton (sm_100a only).
+//
+// One CTA computes one 128-row accumulator tile (or several 128-row tiles sharing the streamed operand) for one
+// client: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one elected lane issues
+// tcgen05.mma kind::tf32, fp32 accumulate in TMEM), warps 2-5 = epilogue (tcgen05.ld 32x32b, one TMEM lane per
+// thread).  Operands are staged in shared memory in the canonical 128-byte-swizzled layouts: TMA boxes with a
+// 128-byte inner extent land directly in that layout; small weight operands that need a permutation are written by
+// all threads ("resident" operand) before the pipeline starts.  The problem-specific parts (which boxes to load per
+// k-block, which MMAs to issue, what the epilogue does with the accumulator) come from a Traits class.
+#pragma once
+#include <cuda.h>
+#include "train_common.cuh"
+
+namespace tc {
+
+constexpr int THREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;      // bounded waits: a broken pipeline traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {       // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {           // the allocating warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).  lbo / sbo in bytes.
+//   K-major : rows of 128 B (32 fp32 along K); 8-row groups `sbo` apart (1024 when rows are dense); lbo unused.
+//   MN-major: rows of 128 B (32 fp32 along M/N), consecutive K indices 128 B apart; 8-K groups `sbo` apart,
+//             32-element M/N chunks `lbo` apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor: D = fp32, A = B = tf32, dense; a_mn / b_mn select MN-major operands
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row, k) inside a K-major SW128 tile whose rows are 128 B (32 fp32) and dense
+__device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)row * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
+}
+
+// Traits interface:
+//   struct Params;                                   kernel parameter block (holds CUtensorMaps by value)
+//   static constexpr int STAGES, STAGE_BYTES, RESIDENT_BYTES, TMEM_COLS;
+//   __device__ bool setup(const Params&, int& num_kb)          CTA-uniform; false -> nothing to do
+//   __device__ void stage_resident(uint8_t* res, int tid)      all threads (generic-proxy writes)
+//   __device__ void load(int kb, uint8_t* stage, uint64_t* bar) producer lane: expect_tx + TMA boxes
+//   __device__ void mma(int kb, uint32_t stage_addr, uint32_t res_addr, uint32_t tmem)   MMA lane
+//   __device__ void epilogue(uint32_t tmem, int quarter, int lane)   epilogue warps, quarter = warp % 4
+template <class T>
+__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ typename T::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], accum_bar;
+    __shared__ uint32_t tmem_base;
+    uint8_t* stages = smem;
+    uint8_t* resident = smem + (size_t)T::STAGES * T::STAGE_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T t;
+    int num_kb = 0;
+    if (!t.setup(p, num_kb)) return;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        fence_barrier_init();
+        t.prefetch(p);
+    }
+    if (warp == 1) tmem_alloc<T::TMEM_COLS>(&tmem_base);
+    if (T::RESIDENT_BYTES > 0) {
+        t.stage_resident(p, resident, threadIdx.x);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % T::STAGES, it = kb / T::STAGES;
+                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+                t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % T::STAGES, it = kb / T::STAGES;
+                mbar_wait(&full_bar[s], it & 1);
+                tc_fence_after();
+                t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), smem_u32(resident), tmem);
+                mma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+            }
+            mma_commit(&accum_bar);                 // accumulator complete
+        }
+    } else {
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        t.epilogue(p, tmem, warp & 3, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<T::TMEM_COLS>(tmem);
+}
+
+}  // namespace tc

@@ -20,7 +20,25 @@
 #include "philox.cuh"
 #include <string.h>
 
+namespace tc {
+int conv_fwd_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, int woff, int boff, cudaStream_t st);
+int conv_dgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, int woff, cudaStream_t st);
+int conv_wgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int woff, int splits, cudaStream_t st);
+int fc_fwd_3136_128(const flb_train_args& a, const float* act, float* out, int woff, int splits, cudaStream_t st);
+int fc_dgrad_3136_128(const flb_train_args& a, const float* dout, float* dact, int woff, cudaStream_t st);
+int fc_wgrad_3136_128(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st);
+}  // namespace tc
+
 namespace {
+
+enum : int { TC_CONV2_FWD = 1, TC_FC1_FWD = 2, TC_FC1_DGRAD = 4, TC_CONV2_DGRAD = 8, TC_FC1_WGRAD = 16, TC_CONV2_WGRAD = 32 };
+
+// which GEMMs run on the tensor cores for these args
+int tc_mask_of(const flb_train_args& a) {
+    int m = a.precision == 1 ? (a.tc_mask ? a.tc_mask : 63) : 0;
+    if (a.B % 8) m &= ~TC_FC1_WGRAD;        // its K extent is the batch: whole 8-row MMA steps only
+    return m;
+}
 
 // per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
 struct StepProfile {
@@ -289,7 +307,7 @@ struct LinDgradProb {       // dact[b][n] = sum_k dout[b][k] * W[k][n]
     __device__ void finish() {}
 };
 
-struct LinWgradProb {       // dW[m][n] = sum_b dout[b][m] * act[b][n];  column n == In is the bias gradient
+struct LinWgradProb {       // dW[m][n] = sum_b dout[b][m] * act[b][n]   (bias gradient: head_wgrad_kernel)
     static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
     flb_train_args a; int In, Out, woff, boff; const float* dout_all; const float* act_all; const float* coef_all;
     const float* dout; const float* act; const float* coef; float* gw; float* gb;
@@ -301,14 +319,12 @@ struct LinWgradProb {       // dW[m][n] = sum_b dout[b][m] * act[b][n];  column 
         coef = coef_all ? coef_all + (long long)client * a.B : nullptr;
         gw = a.G + (long long)client * a.ld + woff;
         gb = a.G + (long long)client * a.ld + boff;
-        M = Out; N = In + 1; Kd = bsz;
+        M = Out; N = In; Kd = bsz;
         return true;
     }
     __device__ float loadA(int m, int k) const { const float v = dout[k * Out + m]; return coef ? v * coef[k] : v; }
-    __device__ float loadB(int n, int k) const { return n == In ? 1.f : act[(long long)k * In + n]; }
-    __device__ void store(int m, int n, float acc) {
-        if (n == In) gb[m] = acc; else gw[(long long)m * In + n] = acc;
-    }
+    __device__ float loadB(int n, int k) const { return act[(long long)k * In + n]; }
+    __device__ void store(int m, int n, float acc) { gw[(long long)m * In + n] = acc; }
     __device__ void finish() {}
 };
 
@@ -394,6 +410,8 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
         for (int c = 0; c < 10; ++c) acc = fmaf(sdl[b][c], sw2[c][j], acc);
         ws.dh[kb * 128 + e] = acc * ws.dh[kb * 128 + e];
     }
+    // rows bsz..B-1 of dh feed the tensor-core fc1 wgrad as zeros (its K extent is the whole batch)
+    for (int e = bsz * 128 + tid; e < a.B * 128; e += 256) ws.dh[kb * 128 + e] = 0.f;
 }
 
 // fc2 weight/bias gradients (tiny): one CTA per client
@@ -422,6 +440,45 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(flb_train_args a, Simpl
         float acc = 0.f;
         for (int b = 0; b < bsz; ++b) acc += sdl[b][tid];
         G[Off::f2b + tid] = acc;
+    }
+    if (tid >= 128) {                           // fc1 bias gradient = column sums of dh
+        const int j = tid - 128;
+        float acc = 0.f;
+        for (int b = 0; b < bsz; ++b) acc = fmaf(ws.dh[kb * 128 + b * 128 + j], use_coef ? ws.coef[kb + b] : 1.f, acc);
+        G[Off::f1b + j] = acc;
+    }
+}
+
+// conv2 bias gradient (tensor-core path; the fp32 path gets it as an extra GEMM column): per-sample column sums of dz
+__global__ void __launch_bounds__(256) conv2_bias_grad_kernel(flb_train_args a, SimpleCnnWs ws, int use_coef) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const float* dz = ws.z2 + kb * (PP2 * 64);
+    const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+    float acc = 0.f;
+    for (int px = part; px < PP2; px += 4) acc += dz[px * 64 + c];
+    __shared__ float red[4][64];
+    red[part][c] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const float v = (red[0][c] + red[1][c] + red[2][c] + red[3][c]) * (use_coef ? ws.coef[kb] : 1.f);
+        atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], v);
+    }
+}
+
+// dp_mode 1, tensor-core wgrads: TMA cannot scale an operand in flight, so the activation gradients are scaled by
+// their sample's clip coefficient in place (after the norms have been taken)
+__global__ void __launch_bounds__(256) scale_rows_kernel(flb_train_args a, float* buf, const float* coef, int per_sample) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const float c = coef[kb];
+    float4* p = reinterpret_cast<float4*>(buf + kb * per_sample);
+    for (int e = threadIdx.x; e < per_sample / 4; e += 256) {
+        float4 v = p[e];
+        v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+        p[e] = v;
     }
 }
 
@@ -631,14 +688,19 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     MARK("begin");
     conv1_fwd_pool_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("conv1_fwd_pool");
-    {
+    const int tcm = tc_mask_of(a);
+    if (tcm & TC_CONV2_FWD) {
+        if (int rc = tc::conv_fwd_32_64(a, kConv2, ws.a1p, ws.z2, Off::c2w, Off::c2b, st)) return rc;
+    } else {
         ConvFwdProb p{}; p.a = a; p.g = kConv2; p.xin_all = ws.a1p; p.z_all = ws.z2; p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, B * PP2, 64, 1, K, st);
     }
     MARK("conv2_fwd");
     pool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("pool2");
-    {
+    if (tcm & TC_FC1_FWD) {
+        if (int rc = tc::fc_fwd_3136_128(a, ws.a2, ws.hpre, Off::f1w, 7, st)) return rc;
+    } else {
         LinFwdProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.act_all = ws.a2; p.out_all = ws.hpre;
         simt::launch(p, B, 128, 14, K, st);
     }
@@ -660,14 +722,19 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     if (int rc = forward(a, ws, st)) return rc;
 
     // ---- activation gradients ----
-    {
+    const int tcm = tc_mask_of(a);
+    if (tcm & TC_FC1_DGRAD) {
+        if (int rc = tc::fc_dgrad_3136_128(a, ws.dh, ws.da2, Off::f1w, st)) return rc;
+    } else {
         LinDgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.dout_all = ws.dh; p.dact_all = ws.da2;
         simt::launch(p, B, 3136, 1, K, st);
     }
     MARK("fc1_dgrad");
     unpool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("unpool2");
-    {
+    if (tcm & TC_CONV2_DGRAD) {
+        if (int rc = tc::conv_dgrad_32_64(a, kConv2, ws.z2, ws.da1p, Off::c2w, st)) return rc;
+    } else {
         ConvDgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.dx_all = ws.da1p; p.woff = Off::c2w;
         simt::launch(p, B * PP2, 32, 1, K, st);
     }
@@ -690,13 +757,20 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     // ---- weight gradients ----
     head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws, a.dp_mode == 1);
     MARK("head_wgrad");
-    {
+    if (tcm & TC_FC1_WGRAD) {
+        if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.dh, coef, 128);
+        if (int rc = tc::fc_wgrad_3136_128(a, ws.dh, ws.a2, Off::f1w, st)) return rc;
+    } else {
         LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
         p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
-        simt::launch(p, 128, 3137, 1, K, st);
+        simt::launch(p, 128, 3136, 1, K, st);
     }
     MARK("fc1_wgrad");
-    {
+    if (tcm & TC_CONV2_WGRAD) {
+        conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, coef != nullptr);
+        if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
+        if (int rc = tc::conv_wgrad_32_64(a, kConv2, ws.a1p, ws.z2, Off::c2w, 16, st)) return rc;
+    } else {
         ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
         p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, 64, 289, 16, K, st);

@@ -101,6 +101,7 @@ class BatchedClientTrainer:
         self.drop_keep: Optional[torch.Tensor] = None
         self.dp_z: Optional[torch.Tensor] = None
         self.dp_mode, self.dp_clip, self.dp_sigma = 0, 1.0, 0.0
+        self.tc_mask = 0                      # 0 = every GEMM on tensor cores when precision == 'tf32' (see flb.h)
         self._graph = None
         self._graph_key = None
         self._seen_key = None
@@ -174,6 +175,7 @@ class BatchedClientTrainer:
         a.momentum = 0.9                                                          # training.py:251
         a.model, a.K, a.B = self.model_id, self.K, self.B
         a.precision, a.opt, a.dp_mode = PRECISIONS[self.precision], OPTIMIZERS[opt], self.dp_mode if train else 0
+        a.tc_mask = self.tc_mask
         a.drop_p = self.dropout_rate if train else 0.0
         a.dp_clip, a.dp_sigma = self.dp_clip, self.dp_sigma
 
