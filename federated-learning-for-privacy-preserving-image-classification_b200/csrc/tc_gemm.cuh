@@ -68,14 +68,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {           // the a
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
 
-// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell).  lbo / sbo in bytes.
-//   K-major : rows of 128 B (32 fp32 along K); 8-row groups `sbo` apart (1024 when rows are dense); lbo unused.
-//   MN-major: rows of 128 B (32 fp32 along M/N), consecutive K indices 128 B apart; 8-K groups `sbo` apart,
-//             32-element M/N chunks `lbo` apart.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+// shared-memory matrix descriptors, version 1 (Blackwell).  lbo / sbo in bytes.
+//   K-major, SWIZZLE_128B (layout type 2): rows of 128 B (32 fp32 along K), 16-byte chunks XOR-ed with (row % 8);
+//       8-row groups `sbo` apart (1024 when rows are dense); lbo unused.  Matches TMA CU_TENSOR_MAP_SWIZZLE_128B.
+//   MN-major tf32, SWIZZLE_128B with 32-byte atoms (layout type 1, the only MN-major layout the tf32 MMA accepts):
+//       rows of 128 B (32 fp32 along M/N), consecutive K indices 128 B apart, 32-byte chunks XOR-ed with (row % 4);
+//       4-K groups `sbo` apart (512 when dense), 32-element M/N chunks `lbo` apart.
+//       Matches TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t smem_desc_raw(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout_type) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout_type << 61);
 }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) { return smem_desc_raw(addr, lbo, sbo, 2); }
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) { return smem_desc_raw(addr, lbo, sbo, 1); }
 
 // instruction descriptor: D = fp32, A = B = tf32, dense; a_mn / b_mn select MN-major operands
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {

@@ -33,23 +33,25 @@ static EncodeTiledFn encode_fn() {
 
 // fp32 tensor of `rank` dims (dims[0] innermost, strides in bytes for dims 1..), box with a 32-float (128 B) inner extent
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, bool mn_major) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { flb_set_error("cuTensorMapEncodeTiled is not available from the driver"); return FLB_ERR_CUDA; }
     cuuint64_t gd[3]; cuuint64_t gs[2]; cuuint32_t bx[3]; cuuint32_t es[3] = {1, 1, 1};
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { flb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FLB_ERR_CUDA; }
     return FLB_OK;
 }
 
-static int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// mn_major: the box feeds an MN-major tf32 operand (rows = K indices), which needs the 32-byte-atom swizzle
+static int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool mn_major = false) {
     const uint64_t dims[2] = {cols, rows}, strides[1] = {cols * sizeof(float)};
     const uint32_t box[2] = {32, box_rows};
-    return make_map(m, base, 2, dims, strides, box);
+    return make_map(m, base, 2, dims, strides, box, mn_major);
 }
 
 __device__ __forceinline__ int tap_shift(int tap, int Wp) { return (tap / 3 - 1) * Wp + (tap % 3 - 1); }
@@ -198,8 +200,8 @@ struct ConvWgradTC {
         for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-                mma_tf32(tmem + mt * COUT, smem_desc(stage + mt * 4 * 4096 + k * 1024, 4096, 1024),
-                         smem_desc(stage + A_BYTES + k * 1024, 4096, 1024), id, kb > 0 || k > 0);
+                mma_tf32(tmem + mt * COUT, smem_desc_mn(stage + mt * 4 * 4096 + k * 1024, 4096, 512),
+                         smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         float* gw = p.a.G + (long long)client * p.a.ld + p.woff;
@@ -289,7 +291,7 @@ struct FcDgradTC {
         constexpr uint32_t id = idesc_tf32(128, 32, true, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 1024, 4096, 1024), smem_desc(stage + 4 * 4096 + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc(stage + 4 * 4096 + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -331,7 +333,7 @@ struct FcWgradTC {
     __device__ void mma(int, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, 256, true, true);
         for (int k = 0; k < ksteps; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 1024, 4096, 1024), smem_desc(stage + 4 * 4096 + k * 1024, 4096, 1024), id, k > 0);
+            mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int j = quarter * 32 + lane;
@@ -381,19 +383,19 @@ int conv_dgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* dz
 int conv_wgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int woff, int splits, cudaStream_t st) {
     using T = ConvWgradTC<32, 64>;
     T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32)) return rc;
-    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32)) return rc;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32, true)) return rc;
     p.a = a; p.g = g; p.woff = woff;
     const int total = a.B * g.PP() / 32;
     p.kb_per_split = (total + splits - 1) / splits;
     return launch<T>(p, dim3(splits, a.K), st);
 }
 
-static int make_w_map(CUtensorMap* m, const flb_train_args& a, int woff, int in, int out, uint32_t box_rows) {
+static int make_w_map(CUtensorMap* m, const flb_train_args& a, int woff, int in, int out, uint32_t box_rows, bool mn_major = false) {
     const uint64_t dims[3] = {(uint64_t)in, (uint64_t)out, (uint64_t)a.K};
     const uint64_t strides[2] = {(uint64_t)in * sizeof(float), (uint64_t)a.ld * sizeof(float)};
     const uint32_t box[3] = {32, box_rows, 1};
-    return make_map(m, a.W + woff, 3, dims, strides, box);
+    return make_map(m, a.W + woff, 3, dims, strides, box, mn_major);
 }
 
 int fc_fwd_3136_128(const flb_train_args& a, const float* act, float* out, int woff, int splits, cudaStream_t st) {
@@ -409,7 +411,7 @@ int fc_fwd_3136_128(const flb_train_args& a, const float* act, float* out, int w
 int fc_dgrad_3136_128(const flb_train_args& a, const float* dout, float* dact, int woff, cudaStream_t st) {
     using T = FcDgradTC<3136, 128>;
     T::Params p;
-    if (int rc = make_w_map(&p.map_w, a, woff, 3136, 128, 32)) return rc;
+    if (int rc = make_w_map(&p.map_w, a, woff, 3136, 128, 32, true)) return rc;
     if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32)) return rc;
     p.a = a; p.dact_all = dact;
     return launch<T>(p, dim3((3136 + 127) / 128, a.K), st);
@@ -418,8 +420,8 @@ int fc_dgrad_3136_128(const flb_train_args& a, const float* dout, float* dact, i
 int fc_wgrad_3136_128(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
     using T = FcWgradTC<3136, 128>;
     T::Params p;
-    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32)) return rc;
-    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, 3136, 32)) return rc;
+    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, 3136, 32, true)) return rc;
     p.a = a; p.woff = woff;
     return launch<T>(p, dim3((3136 + 255) / 256, a.K), st);
 }
