@@ -116,7 +116,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("FLB_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("FLB_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--dp-mode", default="update", choices=["update", "per_sample", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
