@@ -37,6 +37,7 @@ SIGNATURES = {
     "flb_q8_dequantize": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
     "flb_train_ws_bytes": [_i, _i, _i],
     "flb_train_ws_offset": [_i, _i, _i, C.c_char_p],
+    "flb_train_bn_floats": [_i],
     "flb_train_begin_epoch": [_vp, _vp],
     "flb_train_step": [_vp, _vp],
     "flb_train_forward_backward": [_vp, _vp],
@@ -45,7 +46,7 @@ SIGNATURES = {
     "flb_train_step_launches": [_vp],
     "flb_train_step_profiled": [_vp, _vp, C.c_char_p, _i, _vp, _i],
 }
-_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset"}
+_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset", "flb_train_bn_floats"}
 
 
 
@@ -55,10 +56,10 @@ class TrainArgs(C.Structure):
         ("x", _vp), ("y", _vp), ("sample_off", _vp), ("nsamples", _vp), ("step_ctr", _vp),
         ("W", _vp), ("G", _vp), ("M", _vp), ("V", _vp), ("tcount", _vp), ("ws", _vp),
         ("loss_sum", _vp), ("correct", _vp), ("nbatch", _vp), ("nseen", _vp),
-        ("drop_keep", _vp), ("dp_z", _vp),
+        ("drop_keep", _vp), ("dp_z", _vp), ("bn_running", _vp),
         ("ld", _ll), ("seed", _ull), ("client_base", _ull), ("client_stride", _ull),
         ("lr", _d), ("beta1", _d), ("beta2", _d), ("eps", _d), ("weight_decay", _d), ("momentum", _d),
-        ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i), ("tc_mask", _i),
+        ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i), ("eval_mode", _i), ("tc_mask", _i),
         ("drop_p", C.c_float), ("dp_clip", C.c_float), ("dp_sigma", C.c_float),
     ]
 

@@ -1,0 +1,191 @@
+// C-ABI entry points of the batched local-training path (include/flb.h, "batched local training") and the
+// model-independent kernels: optimizer step over [K, ld], epoch bookkeeping.  Model-specific launch sequences live in
+// train_simplecnn.cu (model 0) and train_cifar.cu (model 1).
+#include "train_common.cuh"
+#include "philox.cuh"
+#include <string.h>
+
+StepProfile g_prof;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// optimizer over [K, ld]; torch.optim semantics (training.py:244-255): Adam(lr) | SGD(lr, momentum=0.9) | AdamW(lr)
+__global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P) {
+    const int k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    const int t = a.tcount[k] + 1;
+    float* W = a.W + (long long)k * a.ld;
+    float* G = a.G + (long long)k * a.ld;
+    float* M = a.M + (long long)k * a.ld;
+    float* V = a.V + (long long)k * a.ld;
+    // scalars are formed in double and rounded to fp32 once, like Python floats entering fp32 tensor ops
+    const double bc1d = 1.0 - pow(a.beta1, (double)t), bc2d = 1.0 - pow(a.beta2, (double)t);
+    const float step_size = (float)(a.lr / bc1d), bc2_sqrt = (float)sqrt(bc2d);
+    const float lr = (float)a.lr, omb1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, omb2 = (float)(1.0 - a.beta2);
+    const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
+    const float inv_b = 1.f / (float)bsz;
+    const float* zrow = a.dp_z ? a.dp_z + (long long)k * a.ld : nullptr;
+    const int P4 = (P + 3) >> 2;
+    for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
+            const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
+            z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int p = c4 * 4 + e;
+            if (p >= P) break;
+            float g = G[p];
+            if (a.dp_mode == 1) g = (g + a.dp_sigma * (zrow ? zrow[p] : z[e])) * inv_b;   // (sum clipped + N(0, sigma^2)) / B
+            float w = W[p];
+            if (a.opt == 1) {                               // SGD with momentum, dampening 0
+                const float buf = t == 1 ? g : fmaf(mu, M[p], g);
+                M[p] = buf;
+                w = w - lr * buf;
+            } else {
+                if (a.opt == 2) w = w * decay;      // AdamW decoupled decay
+                float m = M[p], v = V[p];
+                m = m + (g - m) * omb1;                           // exp_avg.lerp_(grad, 1 - beta1)
+                v = v * b2 + omb2 * g * g;                  // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+                M[p] = m; V[p] = v;
+                const float denom = sqrtf(v) / bc2_sqrt + eps;
+                w = w - step_size * (m / denom);                             // param.addcdiv_(m, denom, -step_size)
+            }
+            W[p] = w;
+        }
+    }
+}
+
+__global__ void advance_kernel(flb_train_args a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < a.K && flb_bsz(a, k) > 0) a.tcount[k] += 1;
+    __syncthreads();            // single block: every tcount update read the old step first
+    if (k == 0) *a.step_ctr += 1;
+}
+
+__global__ void begin_epoch_kernel(flb_train_args a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < a.K) { a.loss_sum[k] = 0.f; a.correct[k] = 0; a.nbatch[k] = 0; a.nseen[k] = 0; }
+    if (k == 0) *a.step_ctr = 0;
+}
+
+int check_args(const flb_train_args* a) {
+    FLB_CHECK_ARG(a != nullptr, "flb_train: null args");
+    FLB_CHECK_ARG(a->model == 0 || a->model == 1, "flb_train: model %d not supported (0 = simple_cnn, 1 = cifar10_cnn)", a->model);
+    FLB_CHECK_ARG(a->K >= 1 && a->K <= 1024 && a->B >= 1 && a->B <= 32, "flb_train: need 1 <= K <= 1024 and 1 <= B <= 32 (K=%d B=%d)", a->K, a->B);
+    const int P = a->model == 0 ? simplecnn::num_params() : cifar::num_params();
+    FLB_CHECK_ARG(a->ld >= P, "flb_train: ld %lld < %d parameters", a->ld, P);
+    FLB_CHECK_ARG(a->x && a->y && a->sample_off && a->nsamples && a->step_ctr && a->W && a->G && a->M && a->V &&
+                  a->tcount && a->ws && a->loss_sum && a->correct && a->nbatch && a->nseen, "flb_train: null device pointer in args");
+    FLB_CHECK_ARG(a->opt >= 0 && a->opt <= 2, "flb_train: Unknown optimizer type: %d", a->opt);
+    FLB_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f, "flb_train: dropout probability must be in [0, 1)");
+    FLB_CHECK_ARG(a->precision == 0 || a->precision == 1, "flb_train: precision must be 0 (fp32) or 1 (tf32 tensor cores)");
+    FLB_CHECK_ARG(a->dp_mode == 0 || a->dp_mode == 1, "flb_train: dp_mode must be 0 or 1");
+    if (a->model == 1) {
+        FLB_CHECK_ARG(a->bn_running != nullptr, "flb_train: cifar10_cnn needs the bn_running buffer");
+        if (a->dp_mode == 1) {
+            flb_set_error("flb_train: per-sample DP is undefined for cifar10_cnn (BatchNorm couples the samples of a batch)");
+            return FLB_ERR_UNSUPPORTED;
+        }
+    }
+    return FLB_OK;
+}
+
+int num_params(const flb_train_args& a) { return a.model == 0 ? simplecnn::num_params() : cifar::num_params(); }
+
+}  // namespace
+
+extern "C" long long flb_train_ws_bytes(int model, int K, int B) {
+    if (K < 1 || B < 1) return -1;
+    return model == 0 ? simplecnn::ws_bytes(K, B) : model == 1 ? cifar::ws_bytes(K, B) : -1;
+}
+
+extern "C" long long flb_train_ws_offset(int model, int K, int B, const char* name) {
+    if (K < 1 || B < 1 || !name) return -1;
+    return model == 0 ? simplecnn::ws_offset(K, B, name) : model == 1 ? cifar::ws_offset(K, B, name) : -1;
+}
+
+extern "C" long long flb_train_bn_floats(int model) { return model == 1 ? cifar::bn_floats() : 0; }
+
+extern "C" int flb_train_begin_epoch(const flb_train_args* a, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    begin_epoch_kernel<<<flb_cdiv(a->K, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+extern "C" int flb_train_forward(const flb_train_args* a, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    return a->model == 0 ? simplecnn::forward(*a, (cudaStream_t)stream) : cifar::forward(*a, (cudaStream_t)stream);
+}
+
+extern "C" int flb_train_advance(const flb_train_args* a, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    advance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*a);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+static int fwd_bwd(const flb_train_args& a, cudaStream_t st) {
+    return a.model == 0 ? simplecnn::forward_backward(a, st) : cifar::forward_backward(a, st);
+}
+
+extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    return fwd_bwd(*a, (cudaStream_t)stream);
+}
+
+extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = fwd_bwd(*a, st)) return rc;
+    const int P = num_params(*a);
+    const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
+    optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P);
+    MARK("optimizer");
+    advance_kernel<<<1, 1024, 0, st>>>(*a);
+    MARK("advance");
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+// number of kernel launches (memsets excluded) one flb_train_step issues for these args
+extern "C" int flb_train_step_launches(const flb_train_args* a) {
+    if (!a) return -1;
+    return 2 + (a->model == 0 ? simplecnn::step_launches(*a) : cifar::step_launches(*a));
+}
+
+// One step with a CUDA event after every kernel.  Synchronises the stream (profiling aid, not the product path).
+// names_out receives '\n'-separated labels; ms_out[i] = device time of labelled segment i.  Returns the segment count.
+extern "C" int flb_train_step_profiled(const flb_train_args* a, void* stream, char* names_out, int names_cap,
+                                       float* ms_out, int max_n) {
+    if (int rc = check_args(a)) return rc;
+    FLB_CHECK_ARG(names_out && ms_out && names_cap > 0 && max_n > 0, "flb_train_step_profiled: bad output buffers");
+    for (int i = 0; i < 96; ++i) FLB_CUDA(cudaEventCreate(&g_prof.ev[i]));
+    g_prof.n = 0;
+    g_prof.on = true;
+    const int rc = flb_train_step(a, stream);
+    g_prof.on = false;
+    int n = 0;
+    if (rc == FLB_OK && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess) {
+        names_out[0] = 0;
+        size_t used = 0;
+        for (int i = 1; i < g_prof.n && n < max_n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, g_prof.ev[i - 1], g_prof.ev[i]);
+            ms_out[n++] = ms;
+            const size_t len = strlen(g_prof.name[i]);
+            if (used + len + 2 < (size_t)names_cap) {
+                memcpy(names_out + used, g_prof.name[i], len);
+                used += len;
+                names_out[used++] = '\n';
+                names_out[used] = 0;
+            }
+        }
+    }
+    for (int i = 0; i < 96; ++i) cudaEventDestroy(g_prof.ev[i]);
+    return rc == FLB_OK ? n : rc;
+}

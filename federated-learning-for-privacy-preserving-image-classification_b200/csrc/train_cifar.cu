@@ -1,0 +1,733 @@
+// CIFAR10CNN (reference src/shared/models_pytorch.py:100-165) local-training step, batched over all resident clients:
+//   3 x [conv3x3+bias -> BatchNorm2d (batch statistics) -> ReLU, conv3x3+bias -> BN -> ReLU, maxpool2, dropout]
+//   -> flatten 2048 -> fc 512 + ReLU + dropout -> fc 256 + ReLU + dropout -> fc 10,
+// mean cross-entropy (src/shared/training.py:90,193), backward, optimizer step (training.py:244-255; train_api.cu).
+//
+// Activations live NHWC on per-image padded grids (train_common.cuh ConvGeom): 32x32 -> 33-wide rows, 1096 rows per
+// image; 16x16 -> 17 / 296; 8x8 -> 9 / 88 (multiples of 8 so that the tensor-core wgrad can walk pixels 8 at a time).
+// A conv writes its pre-BN output z on the whole grid (pad positions hold don't-care values); the BN consumers reduce /
+// apply over REAL pixels only and write zeros at the pads, so every conv input has zero pads.
+//
+// BatchNorm per client and layer (BatchNorm2d defaults eps 1e-5, momentum 0.1): the per-channel sums are reduced in
+// fp32 per thread and accumulated across CTAs in double (acc[k][0..3][448] = sum z, sum z^2, sum dy*xhat, sum dy), so
+// mean / biased variance / dgamma / dbeta are formed once, in double, by every consumer.  Running statistics are
+// client-local buffers (never federated, models_pytorch.py:25-27) and are only used in eval mode.
+#include "gemm_probs.cuh"
+#include "philox.cuh"
+#include <string.h>
+
+namespace {
+
+constexpr int NCONV = 6;
+constexpr int BN_CH = 448;                       // 32 + 32 + 64 + 64 + 128 + 128
+constexpr float BN_EPS = 1e-5f, BN_MOM = 0.1f;
+constexpr int DROP_PER_SAMPLE = 8192 + 4096 + 2048 + 512 + 256;     // injected keep-mask floats per sample (NCHW order)
+
+struct Net {
+    int cin[NCONV], cout[NCONV], cw[NCONV], cb[NCONV], bw[NCONV], bb[NCONV], coff[NCONV];
+    int f1w, f1b, f2w, f2b, f3w, f3b, P;
+};
+constexpr Net make_net() {
+    Net n{};
+    const int ci[NCONV] = {3, 32, 32, 64, 64, 128}, co[NCONV] = {32, 32, 64, 64, 128, 128};
+    int off = 0, c = 0;
+    for (int i = 0; i < NCONV; ++i) {
+        n.cin[i] = ci[i]; n.cout[i] = co[i];
+        n.cw[i] = off; off += co[i] * ci[i] * 9;
+        n.cb[i] = off; off += co[i];
+        n.bw[i] = off; off += co[i];
+        n.bb[i] = off; off += co[i];
+        n.coff[i] = c; c += co[i];
+    }
+    n.f1w = off; off += 512 * 2048;
+    n.f1b = off; off += 512;
+    n.f2w = off; off += 256 * 512;
+    n.f2b = off; off += 256;
+    n.f3w = off; off += 10 * 256;
+    n.f3b = off; off += 10;
+    n.P = off;
+    return n;
+}
+constexpr Net kNet = make_net();
+static_assert(kNet.P == 1470890, "CIFAR10CNN parameter count (SURVEY.md section 2a)");
+
+// geometry of the three resolutions; Cin / Cout are filled per layer
+constexpr ConvGeom geom(int level, int cin, int cout) {
+    return level == 0 ? ConvGeom{cin, cout, 32, 32, 34, 33, 1096}
+         : level == 1 ? ConvGeom{cin, cout, 16, 16, 18, 17, 296}
+                      : ConvGeom{cin, cout, 8, 8, 10, 9, 88};
+}
+constexpr int PP32 = 1096, PP16 = 296, PP8 = 88;
+
+struct CifarWs {
+    float *z1, *y1, *z2, *p1;          // grid 32: conv1 out, bn1+relu, conv2 out; grid 16: pooled+dropped (conv3 input)
+    float *z3, *y3, *z4, *p2;          // grid 16 ...; grid 8: p2
+    float *z5, *y5, *z6, *a;           // grid 8 ...; a: [2048] NCHW-flattened fc1 input
+    uint8_t *i1, *i2, *i3;             // pool argmax (bits 0-1) | dropped (bit 2)
+    float *hpre1, *h1, *m1, *hpre2, *h, *logits, *dlog, *dh2, *dh1, *da;
+    float *d32a, *d32b, *d16p, *d16a, *d16b, *d8p, *d8a, *d8b;
+    double* acc;                       // [K][4][448]
+};
+
+size_t carve(void* base, int K, int B, CifarWs* ws) {
+    size_t off = 0;
+    char* p = (char*)base;
+    const size_t KB = (size_t)K * B;
+#define CARVE(field, type, count)                                  \
+    do {                                                           \
+        if (ws) ws->field = (type*)(p + off);                      \
+        off = flb_align256(off + sizeof(type) * (size_t)(count));  \
+    } while (0)
+    CARVE(z1, float, KB * PP32 * 32); CARVE(y1, float, KB * PP32 * 32); CARVE(z2, float, KB * PP32 * 32);
+    CARVE(p1, float, KB * PP16 * 32);
+    CARVE(z3, float, KB * PP16 * 64); CARVE(y3, float, KB * PP16 * 64); CARVE(z4, float, KB * PP16 * 64);
+    CARVE(p2, float, KB * PP8 * 64);
+    CARVE(z5, float, KB * PP8 * 128); CARVE(y5, float, KB * PP8 * 128); CARVE(z6, float, KB * PP8 * 128);
+    CARVE(a, float, KB * 2048);
+    CARVE(i1, uint8_t, KB * 8192); CARVE(i2, uint8_t, KB * 4096); CARVE(i3, uint8_t, KB * 2048);
+    CARVE(hpre1, float, KB * 512); CARVE(h1, float, KB * 512); CARVE(m1, float, KB * 512);
+    CARVE(hpre2, float, KB * 256); CARVE(h, float, KB * 256);
+    CARVE(logits, float, KB * 10); CARVE(dlog, float, KB * 10);
+    CARVE(dh2, float, KB * 256); CARVE(dh1, float, KB * 512); CARVE(da, float, KB * 2048);
+    CARVE(d32a, float, KB * PP32 * 32); CARVE(d32b, float, KB * PP32 * 32);
+    CARVE(d16p, float, KB * PP16 * 32); CARVE(d16a, float, KB * PP16 * 64); CARVE(d16b, float, KB * PP16 * 64);
+    CARVE(d8p, float, KB * PP8 * 64); CARVE(d8a, float, KB * PP8 * 128); CARVE(d8b, float, KB * PP8 * 128);
+    CARVE(acc, double, (size_t)K * 4 * BN_CH);
+#undef CARVE
+    return off;
+}
+
+// ---- conv1 (Cin = 3): the input is the raw NCHW sample; K = 27 is too thin for a tensor-core tile -----------------
+struct Conv1FwdProb {
+    static constexpr bool A_MCONTIG = false, B_NCONTIG = false;
+    flb_train_args a; ConvGeom g; float* z_all; int woff, boff;
+    const float* x; float* z; const float* w; const float* bias;
+    __device__ bool setup(int client, int& M, int& N, int& Kd) {
+        const int bsz = flb_bsz(a, client);
+        if (bsz == 0) return false;
+        x = a.x + (a.sample_off[client] + (long long)(*a.step_ctr) * a.B) * (3 * g.H * g.W);
+        z = z_all + (long long)client * a.B * g.PP() * g.Cout;
+        w = a.W + (long long)client * a.ld + woff;
+        bias = a.W + (long long)client * a.ld + boff;
+        M = bsz * g.PP(); N = g.Cout; Kd = 27;
+        return true;
+    }
+    __device__ float patch(int m, int k) const {             // k = ci * 9 + tap (the order of W[co][ci][3][3])
+        const int b = m / g.PP(), r = m - b * g.PP();
+        const int h = r / g.Wp, w_ = r - h * g.Wp;
+        if (h >= g.H || w_ >= g.W) return 0.f;
+        const int ci = k / 9, tap = k - ci * 9;
+        const int hh = h + tap / 3 - 1, ww = w_ + tap % 3 - 1;
+        if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) return 0.f;
+        return x[((long long)(b * 3 + ci) * g.H + hh) * g.W + ww];
+    }
+    __device__ float loadA(int m, int k) const { return patch(m, k); }
+    __device__ float loadB(int n, int k) const { return __ldg(&w[n * 27 + k]); }
+    __device__ void store(int m, int n, float acc) { z[(long long)m * g.Cout + n] = acc + bias[n]; }
+    __device__ void finish() {}
+};
+
+struct Conv1WgradProb {       // dW[co][k] = sum_rows dz[row][co] * patch(row, k); column 27 = bias gradient
+    static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
+    flb_train_args a; ConvGeom g; const float* dz_all; int woff, boff;
+    Conv1FwdProb f; const float* dz; float* gw; float* gb;
+    __device__ bool setup(int client, int& M, int& N, int& Kd) {
+        const int bsz = flb_bsz(a, client);
+        if (bsz == 0) return false;
+        f.a = a; f.g = g;
+        f.x = a.x + (a.sample_off[client] + (long long)(*a.step_ctr) * a.B) * (3 * g.H * g.W);
+        dz = dz_all + (long long)client * a.B * g.PP() * g.Cout;
+        gw = a.G + (long long)client * a.ld + woff;
+        gb = a.G + (long long)client * a.ld + boff;
+        M = g.Cout; N = 28; Kd = bsz * g.PP();
+        return true;
+    }
+    __device__ float loadA(int m, int k) const { return dz[(long long)k * g.Cout + m]; }
+    __device__ float loadB(int n, int k) const { return n == 27 ? 1.f : f.patch(k, n); }
+    __device__ void store(int m, int n, float acc) { atomicAdd(n == 27 ? &gb[m] : &gw[m * 27 + n], acc); }
+    __device__ void finish() {}
+};
+
+// ---- BatchNorm ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool real_px(const ConvGeom& g, int r) {       // r = row within the client's [B * PP] rows
+    const int rr = r % g.PP();
+    const int h = rr / g.Wp;
+    return h < g.H && (rr - h * g.Wp) < g.W;
+}
+
+// per-channel mean / invstd of client k for this step (train) or from the running buffers (eval)
+__device__ __forceinline__ void bn_moments(const flb_train_args& a, const double* acc, int k, int ch, int n_real,
+                                           float& mean, float& invstd, float& var_b) {
+    if (a.eval_mode) {
+        const float* run = a.bn_running + (long long)k * 2 * BN_CH;
+        mean = run[ch];
+        var_b = run[BN_CH + ch];
+    } else {
+        const double* A = acc + (long long)k * 4 * BN_CH;
+        const double m = A[ch] / n_real;
+        double v = A[BN_CH + ch] / n_real - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m;
+        var_b = (float)v;
+    }
+    invstd = 1.0f / sqrtf(var_b + BN_EPS);
+}
+
+// column sums over the real pixels of client k: MODE 0: (sum z, sum z^2) -> acc[0], acc[1];
+// MODE 1: g = relu-masked upstream gradient; (sum g * xhat, sum g) -> acc[2], acc[3]
+template <int C, int MODE>
+__global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* dy_all,
+                                                        const float* y_all, double* acc, int coff) {
+    const int k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    constexpr int RL = 256 / C;
+    const int tid = threadIdx.x, c = tid % C, rl = tid / C;
+    const int PP = g.PP(), rows = bsz * PP;
+    const int per = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+    const long long base = (long long)k * a.B * PP * C;
+    const float* z = z_all + base;
+    float mean = 0.f, invstd = 0.f, vb;
+    if (MODE == 1) bn_moments(a, acc, k, coff + c, bsz * g.H * g.W, mean, invstd, vb);
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = r0 + rl; r < r1; r += RL) {
+        if (!real_px(g, r)) continue;
+        const long long e = (long long)r * C + c;
+        if (MODE == 0) {
+            const float v = z[e];
+            s0 += v;
+            s1 = fmaf(v, v, s1);
+        } else {
+            float gv = dy_all[base + e];
+            if (y_all && !(y_all[base + e] > 0.f)) gv = 0.f;
+            s0 = fmaf(gv, (z[e] - mean) * invstd, s0);
+            s1 += gv;
+        }
+    }
+    __shared__ float red[2][256];
+    red[0][tid] = s0; red[1][tid] = s1;
+    __syncthreads();
+    if (tid < C) {
+        for (int i = 1; i < RL; ++i) { s0 += red[0][tid + i * C]; s1 += red[1][tid + i * C]; }
+        double* A = acc + (long long)k * 4 * BN_CH + (MODE == 0 ? 0 : 2 * BN_CH) + coff + c;
+        atomicAdd(A, (double)s0);
+        atomicAdd(A + BN_CH, (double)s1);
+    }
+}
+
+// y = relu(bn(z)) on the real pixels, 0 on the pads; CTA (0, k) also updates the client's running statistics
+template <int C>
+__global__ void __launch_bounds__(256) bn_relu_apply_kernel(flb_train_args a, ConvGeom g, const float* z_all, float* y_all,
+                                                            const double* acc, int coff, int gwoff, int gboff) {
+    const int k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    __shared__ float s_scale[C], s_beta[C];
+    const int tid = threadIdx.x;
+    const int n_real = bsz * g.H * g.W;
+    const float* W = a.W + (long long)k * a.ld;
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, n_real, mean, invstd, vb);
+        // ATen's CPU kernel (batch_norm_cpu_transform_input): alpha = invstd * weight, beta = bias - mean * alpha,
+        // out = in * alpha + beta -- same association here so that near-ties in the following max-pool break alike
+        s_scale[tid] = invstd * W[gwoff + tid];
+        s_beta[tid] = W[gboff + tid] - mean * s_scale[tid];
+        if (blockIdx.x == 0 && !a.eval_mode) {
+            float* run = a.bn_running + (long long)k * 2 * BN_CH + coff + tid;
+            run[0] = (1.f - BN_MOM) * run[0] + BN_MOM * mean;
+            const float unb = n_real > 1 ? vb * ((float)n_real / (float)(n_real - 1)) : vb;
+            run[BN_CH] = (1.f - BN_MOM) * run[BN_CH] + BN_MOM * unb;
+        }
+    }
+    __syncthreads();
+    const int PP = g.PP(), rows = bsz * PP;
+    const long long base = (long long)k * a.B * PP * C;
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
+    float4* y4 = reinterpret_cast<float4*>(y_all + base);
+    constexpr int C4 = C / 4;
+    const long long total = (long long)rows * C4;
+    for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
+        const int r = (int)(e / C4), c = (int)(e % C4) * 4;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (real_px(g, r)) {
+            const float4 v = z4[e];
+            o.x = fmaxf(__fadd_rn(__fmul_rn(v.x, s_scale[c]), s_beta[c]), 0.f);
+            o.y = fmaxf(__fadd_rn(__fmul_rn(v.y, s_scale[c + 1]), s_beta[c + 1]), 0.f);
+            o.z = fmaxf(__fadd_rn(__fmul_rn(v.z, s_scale[c + 2]), s_beta[c + 2]), 0.f);
+            o.w = fmaxf(__fadd_rn(__fmul_rn(v.w, s_scale[c + 3]), s_beta[c + 3]), 0.f);
+        }
+        y4[e] = o;
+    }
+}
+
+// dropout decision of element e of drop layer `layer` (0..4) for local client k, sample b
+__device__ __forceinline__ bool drop_keep(const flb_train_args& a, int k, int b, int layer, int layer_off, int per_sample, int e_nchw) {
+    if (a.drop_keep) return a.drop_keep[((long long)k * a.B + b) * DROP_PER_SAMPLE + layer_off + e_nchw] != 0;
+    const unsigned long long e = (unsigned long long)b * per_sample + e_nchw;
+    const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
+                                      ((unsigned long long)a.tcount[k] << 24) + ((unsigned long long)layer << 20) + (e >> 2));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    return flb_u01(rr[e & 3]) >= a.drop_p;
+}
+
+// relu(bn(z)) -> 2x2 max-pool (+argmax) -> dropout.  One CTA per (sample, client).  FLAT: the output is fc1's
+// NCHW-flattened input [C * Ho * Wo]; otherwise the next resolution's padded NHWC grid.  Also updates running stats.
+template <int C, bool FLAT>
+__global__ void __launch_bounds__(256) bn_relu_pool_drop_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* z_all,
+                                                                float* out_all, uint8_t* idx_all, const double* acc, int coff,
+                                                                int gwoff, int gboff, int drop_layer, int drop_off) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (b >= bsz) return;
+    __shared__ float s_scale[C], s_beta[C];
+    const int tid = threadIdx.x;
+    const int n_real = bsz * g.H * g.W;
+    const float* W = a.W + (long long)k * a.ld;
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, n_real, mean, invstd, vb);
+        s_scale[tid] = invstd * W[gwoff + tid];
+        s_beta[tid] = W[gboff + tid] - mean * s_scale[tid];
+        if (b == 0 && !a.eval_mode) {
+            float* run = a.bn_running + (long long)k * 2 * BN_CH + coff + tid;
+            run[0] = (1.f - BN_MOM) * run[0] + BN_MOM * mean;
+            const float unb = n_real > 1 ? vb * ((float)n_real / (float)(n_real - 1)) : vb;
+            run[BN_CH] = (1.f - BN_MOM) * run[BN_CH] + BN_MOM * unb;
+        }
+    }
+    __syncthreads();
+    const long long kb = (long long)k * a.B + b;
+    const float* z = z_all + kb * g.PP() * C;
+    const int Ho = g.H / 2, Wo = g.W / 2, npool = Ho * Wo;
+    float* out = out_all + kb * (FLAT ? C * npool : go.PP() * C);
+    uint8_t* idx = idx_all + kb * npool * C;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    for (int e = tid; e < npool * C; e += 256) {
+        const int c = e % C, pp = e / C, ph = pp / Wo, pw = pp - ph * Wo;
+        float best = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float v = __fadd_rn(__fmul_rn(z[((2 * ph + i) * g.Wp + 2 * pw + j) * C + c], s_scale[c]), s_beta[c]);
+                if (v > best) { best = v; bi = i * 2 + j; }
+            }
+        float v = fmaxf(best, 0.f);
+        if (a.drop_p > 0.f) {
+            if (drop_keep(a, k, b, drop_layer, drop_off, npool * C, c * npool + pp)) v *= keep_scale;
+            else { v = 0.f; bi |= 4; }
+        }
+        if (FLAT) { out[c * npool + pp] = v; idx[c * npool + pp] = (uint8_t)bi; }
+        else { out[(ph * go.Wp + pw) * C + c] = v; idx[e] = (uint8_t)bi; }
+    }
+}
+
+// backward of the kernel above up to (and including) the ReLU: dy on the fine grid (zeros on pads and non-argmax
+// positions).  dpool: gradient w.r.t. the pooled+dropped output (FLAT: [C*Ho*Wo], else the coarse padded grid).
+template <int C, bool FLAT>
+__global__ void __launch_bounds__(256) unpool_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
+                                                     const float* pooled_all, const uint8_t* idx_all, float* dy_all) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const int Ho = g.H / 2, Wo = g.W / 2, npool = Ho * Wo;
+    const float* dpool = dpool_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const float* pooled = pooled_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const uint8_t* idx = idx_all + kb * npool * C;
+    float* dy = dy_all + kb * g.PP() * C;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const int total = g.PP() * C;
+    for (int e = threadIdx.x; e < total; e += 256) {
+        const int c = e % C, r = e / C, h = r / g.Wp, w = r - h * g.Wp;
+        float v = 0.f;
+        if (h < g.H && w < g.W) {
+            const int pp = (h >> 1) * Wo + (w >> 1);
+            const int src = FLAT ? c * npool + pp : ((h >> 1) * go.Wp + (w >> 1)) * C + c;
+            const int code = idx[FLAT ? c * npool + pp : pp * C + c];
+            if (code == ((h & 1) * 2 + (w & 1)) && pooled[src] > 0.f) v = dpool[src] * keep_scale;   // bit 2 set = dropped
+        }
+        dy[e] = v;
+    }
+}
+
+// dz = gamma * invstd * (g - dbeta/N - xhat * dgamma/N) in place over dy (zeros on pads); g = dy masked by y > 0 when
+// y_all is given.  CTA (0, k) writes dgamma / dbeta into G.
+template <int C>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* y_all,
+                                                           float* dy_all, const double* acc, int coff, int gwoff, int gboff) {
+    const int k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    __shared__ float s_mean[C], s_invstd[C], s_c0[C], s_c1[C], s_c2[C];
+    const int tid = threadIdx.x;
+    const int n_real = bsz * g.H * g.W;
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, n_real, mean, invstd, vb);
+        const double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
+        const float dgamma = (float)A[0], dbeta = (float)A[BN_CH];
+        const float gamma = a.W[(long long)k * a.ld + gwoff + tid];
+        s_mean[tid] = mean; s_invstd[tid] = invstd;
+        s_c0[tid] = gamma * invstd;
+        s_c1[tid] = dbeta / (float)n_real;
+        s_c2[tid] = dgamma / (float)n_real;
+        if (blockIdx.x == 0) {
+            float* G = a.G + (long long)k * a.ld;
+            G[gwoff + tid] = dgamma;
+            G[gboff + tid] = dbeta;
+        }
+    }
+    __syncthreads();
+    const int PP = g.PP(), rows = bsz * PP;
+    const long long base = (long long)k * a.B * PP * C;
+    const long long total = (long long)rows * C;
+    for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
+        const int r = (int)(e / C), c = (int)(e % C);
+        float o = 0.f;
+        if (real_px(g, r)) {
+            float gv = dy_all[base + e];
+            if (y_all && !(y_all[base + e] > 0.f)) gv = 0.f;
+            const float xhat = (z_all[base + e] - s_mean[c]) * s_invstd[c];
+            o = s_c0[c] * (gv - s_c1[c] - xhat * s_c2[c]);
+        }
+        dy_all[base + e] = o;
+    }
+}
+
+// ---- classifier ------------------------------------------------------------------------------------------------------
+// h1 = dropout(relu(hpre1 + b)); the multiplier (0 where ReLU is inactive or the unit is dropped, else 1/(1-p)) is kept
+// in m1 for the backward pass
+__global__ void __launch_bounds__(256) fc_bias_relu_drop_kernel(flb_train_args a, const float* pre_all, float* h_all, float* m_all,
+                                                                int n, int boff, int drop_layer, int drop_off) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const float* W = a.W + (long long)k * a.ld;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    for (int j = threadIdx.x; j < n; j += 256) {
+        const float pre = pre_all[kb * n + j] + W[boff + j];
+        float mult = pre > 0.f ? 1.f : 0.f;
+        if (a.drop_p > 0.f) mult = drop_keep(a, k, b, drop_layer, drop_off, n, j) ? mult * keep_scale : 0.f;
+        h_all[kb * n + j] = pre * mult;
+        m_all[kb * n + j] = mult;
+    }
+}
+
+// last two layers: h = dropout(relu(hpre2 + b2)), logits = fc3(h), softmax cross-entropy, dlogits, d(hpre2).
+// One CTA per client (same structure as SimpleCNN's head kernel, 256 inputs).
+__global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, CifarWs ws) {
+    constexpr int IN = 256;
+    const int k = blockIdx.x;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    extern __shared__ float smem[];
+    float (*sh)[IN + 1] = reinterpret_cast<float (*)[IN + 1]>(smem);                          // [32][257]
+    float (*sw)[IN + 1] = reinterpret_cast<float (*)[IN + 1]>(smem + 32 * (IN + 1));          // [10][257]
+    float (*slog)[10] = reinterpret_cast<float (*)[10]>(smem + 42 * (IN + 1));                // [32][10]
+    float (*sdl)[10] = reinterpret_cast<float (*)[10]>(smem + 42 * (IN + 1) + 320);           // [32][10]
+    float* red = smem + 42 * (IN + 1) + 640;
+    const int tid = threadIdx.x;
+    const float* W = a.W + (long long)k * a.ld;
+    const long long kb = (long long)k * a.B;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    const int step = *a.step_ctr;
+    for (int e = tid; e < bsz * IN; e += 256) {
+        const int b = e / IN, j = e % IN;
+        const float pre = ws.hpre2[kb * IN + e] + W[kNet.f2b + j];
+        float mult = pre > 0.f ? 1.f : 0.f;
+        if (a.drop_p > 0.f) mult = drop_keep(a, k, b, 4, 8192 + 4096 + 2048 + 512, IN, j) ? mult * keep_scale : 0.f;
+        const float hv = pre * mult;
+        sh[b][j] = hv;
+        ws.h[kb * IN + e] = hv;
+        ws.dh2[kb * IN + e] = mult;
+    }
+    for (int e = tid; e < 10 * IN; e += 256) sw[e / IN][e % IN] = W[kNet.f3w + e];
+    if (tid < 2) red[tid] = 0.f;
+    __syncthreads();
+    for (int e = tid; e < bsz * 10; e += 256) {
+        const int b = e / 10, j = e % 10;
+        float acc = W[kNet.f3b + j];
+#pragma unroll 8
+        for (int i = 0; i < IN; ++i) acc = fmaf(sh[b][i], sw[j][i], acc);
+        slog[b][j] = acc;
+        ws.logits[kb * 10 + e] = acc;
+    }
+    __syncthreads();
+    if (tid < bsz) {
+        const int y = a.y[a.sample_off[k] + (long long)step * a.B + tid];
+        float mx = slog[tid][0];
+        int am = 0;
+        for (int j = 1; j < 10; ++j) if (slog[tid][j] > mx) { mx = slog[tid][j]; am = j; }
+        float se = 0.f;
+        for (int j = 0; j < 10; ++j) se += expf(slog[tid][j] - mx);
+        const float lse = logf(se) + mx;
+        const float gs = 1.f / (float)bsz;                                  // mean reduction (training.py:90)
+        for (int j = 0; j < 10; ++j) {
+            const float p = expf(slog[tid][j] - lse);
+            const float d = (p - (j == y ? 1.f : 0.f)) * gs;
+            sdl[tid][j] = d;
+            ws.dlog[kb * 10 + tid * 10 + j] = d;
+        }
+        atomicAdd(&red[0], lse - slog[tid][y]);
+        atomicAdd(&red[1], am == y ? 1.f : 0.f);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.loss_sum[k] += red[0] / (float)bsz;          // running_loss += loss.item()   (training.py:200)
+        a.correct[k] += (int)(red[1] + 0.5f);          // correct += (pred == y).sum()  (training.py:201-203)
+        a.nbatch[k] += 1;
+        a.nseen[k] += bsz;
+    }
+    for (int e = tid; e < bsz * IN; e += 256) {
+        const int b = e / IN, j = e % IN;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) acc = fmaf(sdl[b][c], sw[c][j], acc);
+        ws.dh2[kb * IN + e] = acc * ws.dh2[kb * IN + e];
+    }
+    for (int e = bsz * IN + tid; e < a.B * IN; e += 256) ws.dh2[kb * IN + e] = 0.f;      // zero rows feed the TC wgrad
+}
+constexpr size_t kHeadSmem = (42 * 257 + 640 + 2) * sizeof(float);
+
+// fc3 weight / bias gradients and fc2's bias gradient: one CTA per client
+__global__ void __launch_bounds__(256) head_wgrad_kernel(flb_train_args a, CifarWs ws) {
+    constexpr int IN = 256;
+    const int k = blockIdx.x;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    __shared__ float sdl[32][10];
+    const int tid = threadIdx.x;
+    const long long kb = (long long)k * a.B;
+    float* G = a.G + (long long)k * a.ld;
+    for (int e = tid; e < bsz * 10; e += 256) sdl[e / 10][e % 10] = ws.dlog[kb * 10 + e];
+    __syncthreads();
+    for (int e = tid; e < 10 * IN; e += 256) {
+        const int j = e / IN, i = e % IN;
+        float acc = 0.f;
+        for (int b = 0; b < bsz; ++b) acc = fmaf(sdl[b][j], ws.h[(kb + b) * IN + i], acc);
+        G[kNet.f3w + e] = acc;
+    }
+    if (tid < 10) {
+        float acc = 0.f;
+        for (int b = 0; b < bsz; ++b) acc += sdl[b][tid];
+        G[kNet.f3b + tid] = acc;
+    }
+    {
+        float acc = 0.f;
+        for (int b = 0; b < bsz; ++b) acc += ws.dh2[(kb + b) * IN + tid];
+        G[kNet.f2b + tid] = acc;
+    }
+}
+
+// d(hpre1) = dh1 * m1 in place (zero for the rows past the batch), and fc1's bias gradient.  One CTA per client.
+__global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, CifarWs ws) {
+    const int k = blockIdx.x;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    const int j = threadIdx.x;
+    const long long kb = (long long)k * a.B;
+    float acc = 0.f;
+    for (int b = 0; b < a.B; ++b) {
+        const long long e = (kb + b) * 512 + j;
+        const float v = b < bsz ? ws.dh1[e] * ws.m1[e] : 0.f;
+        ws.dh1[e] = v;
+        acc += v;
+    }
+    a.G[(long long)k * a.ld + kNet.f1b + j] = acc;
+}
+
+// ---- orchestration ------------------------------------------------------------------------------------------------------
+template <int C>
+void bn_stats(const flb_train_args& a, const ConvGeom& g, const float* z, double* acc, int coff, cudaStream_t st) {
+    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    bn_reduce_kernel<C, 0><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, nullptr, nullptr, acc, coff);
+}
+template <int C>
+void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, const float* y, float* dy, double* acc, int layer, cudaStream_t st) {
+    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, y, acc, kNet.coff[layer]);
+    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
+}
+template <int C>
+void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float* y, const double* acc, int layer, cudaStream_t st) {
+    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    bn_relu_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
+}
+
+void conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, int layer, cudaStream_t st) {
+    ConvFwdProb p{}; p.a = a; p.g = g; p.xin_all = xin; p.z_all = z; p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
+    simt::launch(p, a.B * g.PP(), g.Cout, 1, a.K, st);
+}
+void conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, int layer, cudaStream_t st) {
+    ConvDgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.dx_all = dx; p.woff = kNet.cw[layer];
+    simt::launch(p, a.B * g.PP(), g.Cin, 1, a.K, st);
+}
+void conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int layer, cudaStream_t st) {
+    ConvWgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.xin_all = xin; p.coef_all = nullptr;
+    p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
+    const int tiles = ((g.Cout + 63) / 64) * ((9 * g.Cin + 1 + 63) / 64);
+    const int splits = max(1, min(64, flb_num_sms() * 2 / (tiles * a.K)));
+    simt::launch(p, g.Cout, 9 * g.Cin + 1, splits, a.K, st);
+}
+void lin_fwd(const flb_train_args& a, const float* act, float* out, int In, int Out, int woff, int splits, cudaStream_t st) {
+    LinFwdProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.act_all = act; p.out_all = out;
+    simt::launch(p, a.B, Out, splits, a.K, st);
+}
+void lin_dgrad(const flb_train_args& a, const float* dout, float* dact, int In, int Out, int woff, cudaStream_t st) {
+    LinDgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.dout_all = dout; p.dact_all = dact;
+    simt::launch(p, a.B, In, 1, a.K, st);
+}
+void lin_wgrad(const flb_train_args& a, const float* dout, const float* act, int In, int Out, int woff, cudaStream_t st) {
+    LinWgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.boff = 0; p.dout_all = dout; p.act_all = act; p.coef_all = nullptr;
+    simt::launch(p, Out, In, 1, a.K, st);
+}
+
+constexpr ConvGeom G1 = geom(0, 3, 32), G2 = geom(0, 32, 32), G3 = geom(1, 32, 64), G4 = geom(1, 64, 64),
+                   G5 = geom(2, 64, 128), G6 = geom(2, 128, 128);
+
+int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
+    const int K = a.K, B = a.B;
+    const dim3 per_sample(B, K);
+    const size_t KB = (size_t)K * B;
+    FLB_CUDA(cudaMemsetAsync(ws.acc, 0, sizeof(double) * (size_t)K * 4 * BN_CH, st));
+    FLB_CUDA(cudaMemsetAsync(ws.hpre1, 0, sizeof(float) * KB * 512, st));
+    FLB_CUDA(cudaMemsetAsync(ws.hpre2, 0, sizeof(float) * KB * 256, st));
+    MARK("begin");
+    const bool stats = !a.eval_mode;
+    {
+        Conv1FwdProb p{}; p.a = a; p.g = G1; p.z_all = ws.z1; p.woff = kNet.cw[0]; p.boff = kNet.cb[0];
+        simt::launch(p, B * PP32, 32, 1, K, st);
+    }
+    MARK("conv1_fwd");
+    if (stats) bn_stats<32>(a, G1, ws.z1, ws.acc, kNet.coff[0], st);
+    bn_apply<32>(a, G1, ws.z1, ws.y1, ws.acc, 0, st);
+    MARK("bn1");
+    conv_fwd(a, G2, ws.y1, ws.z2, 1, st);
+    MARK("conv2_fwd");
+    if (stats) bn_stats<32>(a, G2, ws.z2, ws.acc, kNet.coff[1], st);
+    bn_relu_pool_drop_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.z2, ws.p1, ws.i1, ws.acc, kNet.coff[1], kNet.bw[1], kNet.bb[1], 0, 0);
+    MARK("bn2_pool");
+    conv_fwd(a, G3, ws.p1, ws.z3, 2, st);
+    MARK("conv3_fwd");
+    if (stats) bn_stats<64>(a, G3, ws.z3, ws.acc, kNet.coff[2], st);
+    bn_apply<64>(a, G3, ws.z3, ws.y3, ws.acc, 2, st);
+    MARK("bn3");
+    conv_fwd(a, G4, ws.y3, ws.z4, 3, st);
+    MARK("conv4_fwd");
+    if (stats) bn_stats<64>(a, G4, ws.z4, ws.acc, kNet.coff[3], st);
+    bn_relu_pool_drop_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.z4, ws.p2, ws.i2, ws.acc, kNet.coff[3], kNet.bw[3], kNet.bb[3], 1, 8192);
+    MARK("bn4_pool");
+    conv_fwd(a, G5, ws.p2, ws.z5, 4, st);
+    MARK("conv5_fwd");
+    if (stats) bn_stats<128>(a, G5, ws.z5, ws.acc, kNet.coff[4], st);
+    bn_apply<128>(a, G5, ws.z5, ws.y5, ws.acc, 4, st);
+    MARK("bn5");
+    conv_fwd(a, G6, ws.y5, ws.z6, 5, st);
+    MARK("conv6_fwd");
+    if (stats) bn_stats<128>(a, G6, ws.z6, ws.acc, kNet.coff[5], st);
+    bn_relu_pool_drop_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.z6, ws.a, ws.i3, ws.acc, kNet.coff[5], kNet.bw[5], kNet.bb[5], 2, 8192 + 4096);
+    MARK("bn6_pool");
+    lin_fwd(a, ws.a, ws.hpre1, 2048, 512, kNet.f1w, 8, st);
+    MARK("fc1_fwd");
+    fc_bias_relu_drop_kernel<<<per_sample, 256, 0, st>>>(a, ws.hpre1, ws.h1, ws.m1, 512, kNet.f1b, 3, 8192 + 4096 + 2048);
+    lin_fwd(a, ws.h1, ws.hpre2, 512, 256, kNet.f2w, 4, st);
+    MARK("fc2_fwd");
+    static bool configured = false;
+    if (!configured) {
+        FLB_CUDA(cudaFuncSetAttribute(head_fwd_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+        configured = true;
+    }
+    head_fwd_bwd_kernel<<<K, 256, kHeadSmem, st>>>(a, ws);
+    MARK("head_fwd_bwd");
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
+    CifarWs ws;
+    carve(a.ws, a.K, a.B, &ws);
+    const int K = a.K, B = a.B;
+    const dim3 per_sample(B, K);
+    // gradients accumulated with atomics (conv weights / biases) start from zero; everything else is stored
+    FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, kNet.f1w * sizeof(float), K, st));
+    if (int rc = forward_impl(a, ws, st)) return rc;
+
+    head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws);
+    lin_wgrad(a, ws.dh2, ws.h1, 512, 256, kNet.f2w, st);
+    lin_dgrad(a, ws.dh2, ws.dh1, 512, 256, kNet.f2w, st);
+    fc1_mask_bias_kernel<<<K, 512, 0, st>>>(a, ws);
+    MARK("fc23_bwd");
+    lin_wgrad(a, ws.dh1, ws.a, 2048, 512, kNet.f1w, st);
+    lin_dgrad(a, ws.dh1, ws.da, 2048, 512, kNet.f1w, st);
+    MARK("fc1_bwd");
+
+    // block 3 (8x8, 128 channels)
+    unpool_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.da, ws.a, ws.i3, ws.d8a);
+    bn_bwd<128>(a, G6, ws.z6, nullptr, ws.d8a, ws.acc, 5, st);
+    MARK("bn6_bwd");
+    conv_wgrad(a, G6, ws.y5, ws.d8a, 5, st);
+    conv_dgrad(a, G6, ws.d8a, ws.d8b, 5, st);
+    MARK("conv6_bwd");
+    bn_bwd<128>(a, G5, ws.z5, ws.y5, ws.d8b, ws.acc, 4, st);
+    MARK("bn5_bwd");
+    conv_wgrad(a, G5, ws.p2, ws.d8b, 4, st);
+    conv_dgrad(a, G5, ws.d8b, ws.d8p, 4, st);
+    MARK("conv5_bwd");
+
+    // block 2 (16x16, 64 channels)
+    unpool_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.d16a);
+    bn_bwd<64>(a, G4, ws.z4, nullptr, ws.d16a, ws.acc, 3, st);
+    MARK("bn4_bwd");
+    conv_wgrad(a, G4, ws.y3, ws.d16a, 3, st);
+    conv_dgrad(a, G4, ws.d16a, ws.d16b, 3, st);
+    MARK("conv4_bwd");
+    bn_bwd<64>(a, G3, ws.z3, ws.y3, ws.d16b, ws.acc, 2, st);
+    MARK("bn3_bwd");
+    conv_wgrad(a, G3, ws.p1, ws.d16b, 2, st);
+    conv_dgrad(a, G3, ws.d16b, ws.d16p, 2, st);
+    MARK("conv3_bwd");
+
+    // block 1 (32x32, 32 channels)
+    unpool_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.d32a);
+    bn_bwd<32>(a, G2, ws.z2, nullptr, ws.d32a, ws.acc, 1, st);
+    MARK("bn2_bwd");
+    conv_wgrad(a, G2, ws.y1, ws.d32a, 1, st);
+    conv_dgrad(a, G2, ws.d32a, ws.d32b, 1, st);
+    MARK("conv2_bwd");
+    bn_bwd<32>(a, G1, ws.z1, ws.y1, ws.d32b, ws.acc, 0, st);
+    MARK("bn1_bwd");
+    {
+        Conv1WgradProb p{}; p.a = a; p.g = G1; p.dz_all = ws.d32b; p.woff = kNet.cw[0]; p.boff = kNet.cb[0];
+        const int splits = max(1, min(64, flb_num_sms() * 2 / K));
+        simt::launch(p, 32, 28, splits, K, st);
+    }
+    MARK("conv1_wgrad");
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+}  // namespace
+
+namespace cifar {
+int num_params() { return kNet.P; }
+long long bn_floats() { return 2 * BN_CH; }
+long long ws_bytes(int K, int B) { return (long long)carve(nullptr, K, B, nullptr); }
+long long ws_offset(int K, int B, const char* name) {
+    CifarWs ws;
+    carve((void*)0, K, B, &ws);
+#define FIELD(f) if (!strcmp(name, #f)) return (long long)(uintptr_t)ws.f;
+    FIELD(z1) FIELD(y1) FIELD(z2) FIELD(p1) FIELD(z3) FIELD(y3) FIELD(z4) FIELD(p2) FIELD(z5) FIELD(y5) FIELD(z6) FIELD(a)
+    FIELD(hpre1) FIELD(h1) FIELD(hpre2) FIELD(h) FIELD(logits) FIELD(dlog) FIELD(dh2) FIELD(dh1) FIELD(da) FIELD(acc) FIELD(d32a) FIELD(d32b) FIELD(d16p) FIELD(d16a) FIELD(d16b) FIELD(d8p) FIELD(d8a) FIELD(d8b)
+#undef FIELD
+    return -1;
+}
+int forward(const flb_train_args& a, cudaStream_t st) {
+    CifarWs ws;
+    carve(a.ws, a.K, a.B, &ws);
+    return forward_impl(a, ws, st);
+}
+int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
+int step_launches(const flb_train_args&) { return 22 + 32; }
+}  // namespace cifar

@@ -12,9 +12,12 @@
 
 // conv activations are stored NHWC on a zero-padded (Hp x Wp) grid per image so that a 3x3 tap is a constant
 // row shift of the flattened [pixels, C] matrix (implicit GEMM without im2col; TMA-friendly)
+// Only the right column(s) and bottom row(s) need to be pad: the left / top neighbours of an image's first column /
+// row are the previous row's / previous image's pad positions.  PPv (rows per image, >= (H+1)*Wp + 1) overrides Hp*Wp.
 struct ConvGeom {
     int Cin, Cout, H, W, Hp, Wp;
-    __host__ __device__ int PP() const { return Hp * Wp; }
+    int PPv = 0;
+    __host__ __device__ int PP() const { return PPv ? PPv : Hp * Wp; }
 };
 
 __device__ __forceinline__ int flb_bsz(const flb_train_args& a, int client) {
@@ -47,6 +50,41 @@ struct SimpleCnnWs {
     float* coef;     // [K][B]              per-sample clip coefficients
     float* g1ps;     // [K][B][320]         per-sample conv1 weight+bias gradients (dp_mode 1)
 };
+
+// per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
+struct StepProfile {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[96];
+    const char* name[96];
+};
+extern StepProfile g_prof;
+#define MARK(label)                                                       \
+    do {                                                                  \
+        if (g_prof.on && g_prof.n < 96) {                                 \
+            cudaEventRecord(g_prof.ev[g_prof.n], st);                     \
+            g_prof.name[g_prof.n++] = label;                              \
+        }                                                                 \
+    } while (0)
+
+// model-specific launch sequences (train_simplecnn.cu, train_cifar.cu), dispatched by train_api.cu
+namespace simplecnn {
+int num_params();
+long long ws_bytes(int K, int B);
+long long ws_offset(int K, int B, const char* name);
+int forward(const flb_train_args& a, cudaStream_t st);
+int forward_backward(const flb_train_args& a, cudaStream_t st);
+int step_launches(const flb_train_args& a);
+}
+namespace cifar {
+int num_params();
+long long bn_floats();
+long long ws_bytes(int K, int B);
+long long ws_offset(int K, int B, const char* name);
+int forward(const flb_train_args& a, cudaStream_t st);
+int forward_backward(const flb_train_args& a, cudaStream_t st);
+int step_launches(const flb_train_args& a);
+}
 
 static inline size_t flb_align256(size_t v) { return (v + 255) & ~(size_t)255; }
 

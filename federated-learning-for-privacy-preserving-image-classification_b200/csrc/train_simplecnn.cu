@@ -17,6 +17,7 @@
 //   optimizer           Adam / SGD-momentum / AdamW over [K, ld]; dp_mode 1 adds Philox noise and the 1/B here
 #include "train_common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_probs.cuh"
 #include "philox.cuh"
 #include <string.h>
 
@@ -39,22 +40,6 @@ int tc_mask_of(const flb_train_args& a) {
     if (a.B % 8) m &= ~TC_FC1_WGRAD;        // its K extent is the batch: whole 8-row MMA steps only
     return m;
 }
-
-// per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
-struct StepProfile {
-    bool on = false;
-    int n = 0;
-    cudaEvent_t ev[48];
-    const char* name[48];
-};
-StepProfile g_prof;
-#define MARK(label)                                                       \
-    do {                                                                  \
-        if (g_prof.on && g_prof.n < 48) {                                 \
-            cudaEventRecord(g_prof.ev[g_prof.n], st);                     \
-            g_prof.name[g_prof.n++] = label;                              \
-        }                                                                 \
-    } while (0)
 
 using Off = SimpleCnnOff;
 constexpr int PP2 = 256;     // conv2 runs on a 16x16 padded grid (14x14 real)
@@ -136,197 +121,6 @@ __global__ void __launch_bounds__(256) pool2_kernel(flb_train_args a, SimpleCnnW
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// implicit-GEMM problem functors on the padded NHWC grid
-struct ConvFwdProb {
-    static constexpr bool A_MCONTIG = false, B_NCONTIG = false;
-    flb_train_args a; ConvGeom g;
-    const float* xin_all; float* z_all; int woff, boff;
-    const float* xin; float* z; const float* w; const float* bias; int Mtot;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        const long long kb = (long long)client * a.B;
-        xin = xin_all + kb * g.PP() * g.Cin;
-        z = z_all + kb * g.PP() * g.Cout;
-        w = a.W + (long long)client * a.ld + woff;
-        bias = a.W + (long long)client * a.ld + boff;
-        Mtot = a.B * g.PP();
-        M = bsz * g.PP(); N = g.Cout; Kd = 9 * g.Cin;
-        return true;
-    }
-    __device__ float loadA(int m, int k) const {
-        const int tap = k / g.Cin, ci = k - tap * g.Cin;
-        const int row = m + (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
-        return (row >= 0 && row < Mtot) ? xin[(long long)row * g.Cin + ci] : 0.f;
-    }
-    __device__ float loadB(int n, int k) const {
-        const int tap = k / g.Cin, ci = k - tap * g.Cin;
-        return __ldg(&w[(n * g.Cin + ci) * 9 + tap]);
-    }
-    __device__ void store(int m, int n, float acc) { z[(long long)m * g.Cout + n] = acc + bias[n]; }
-    __device__ void finish() {}
-};
-
-struct ConvDgradProb {      // dx[m][ci] = sum_{tap,co} dz[m - shift(tap)][co] * W[co][ci][tap]
-    static constexpr bool A_MCONTIG = false, B_NCONTIG = false;
-    flb_train_args a; ConvGeom g;
-    const float* dz_all; float* dx_all; int woff;
-    const float* dz; float* dx; const float* w; int Mtot;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        const long long kb = (long long)client * a.B;
-        dz = dz_all + kb * g.PP() * g.Cout;
-        dx = dx_all + kb * g.PP() * g.Cin;
-        w = a.W + (long long)client * a.ld + woff;
-        Mtot = a.B * g.PP();
-        M = bsz * g.PP(); N = g.Cin; Kd = 9 * g.Cout;
-        return true;
-    }
-    __device__ float loadA(int m, int k) const {
-        const int tap = k / g.Cout, co = k - tap * g.Cout;
-        const int row = m - ((tap / 3 - 1) * g.Wp + (tap % 3 - 1));
-        return (row >= 0 && row < Mtot) ? dz[(long long)row * g.Cout + co] : 0.f;
-    }
-    __device__ float loadB(int n, int k) const {
-        const int tap = k / g.Cout, co = k - tap * g.Cout;
-        return __ldg(&w[(co * g.Cin + n) * 9 + tap]);
-    }
-    __device__ void store(int m, int n, float acc) { dx[(long long)m * g.Cin + n] = acc; }
-    __device__ void finish() {}
-};
-
-// dW[co][ci][tap] = sum_px dz[px][co] * x[px + shift(tap)][ci];  column n == 9*Cin is the bias gradient.
-// In dp_mode 1 each pixel row is scaled by its sample's clip coefficient.
-struct ConvWgradProb {
-    static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
-    flb_train_args a; ConvGeom g;
-    const float* dz_all; const float* xin_all; const float* coef_all; int woff, boff;
-    const float* dz; const float* xin; const float* coef; float* gw; float* gb; int Mtot;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        const long long kb = (long long)client * a.B;
-        dz = dz_all + kb * g.PP() * g.Cout;
-        xin = xin_all + kb * g.PP() * g.Cin;
-        coef = coef_all ? coef_all + kb : nullptr;
-        gw = a.G + (long long)client * a.ld + woff;
-        gb = a.G + (long long)client * a.ld + boff;
-        Mtot = a.B * g.PP();
-        M = g.Cout; N = 9 * g.Cin + 1; Kd = bsz * g.PP();
-        return true;
-    }
-    __device__ float loadA(int m, int k) const {
-        const float v = dz[(long long)k * g.Cout + m];
-        return coef ? v * coef[k / g.PP()] : v;
-    }
-    __device__ float loadB(int n, int k) const {
-        if (n == 9 * g.Cin) return 1.f;
-        const int tap = n / g.Cin, ci = n - tap * g.Cin;
-        const int row = k + (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
-        return (row >= 0 && row < Mtot) ? xin[(long long)row * g.Cin + ci] : 0.f;
-    }
-    __device__ void store(int m, int n, float acc) {
-        if (n == 9 * g.Cin) { atomicAdd(&gb[m], acc); return; }
-        const int tap = n / g.Cin, ci = n - tap * g.Cin;
-        atomicAdd(&gw[(m * g.Cin + ci) * 9 + tap], acc);
-    }
-    __device__ void finish() {}
-};
-
-// per-sample conv weight-gradient norm (dp_mode 1): group = (client, sample); the [Cout, 9*Cin+1] per-sample
-// gradient tile lives in registers only -- squared, reduced with warp shuffles, one atomic per CTA.
-struct ConvWgradNormProb {
-    static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
-    flb_train_args a; ConvGeom g;
-    const float* dz_all; const float* xin_all; float* norm2_all;
-    const float* dz; const float* xin; float* dst; float sq; int lo, hi;
-    __device__ bool setup(int group, int& M, int& N, int& Kd) {
-        const int client = group / a.B, b = group % a.B;
-        sq = 0.f;
-        if (b >= flb_bsz(a, client)) return false;
-        const long long kb = (long long)client * a.B;
-        dz = dz_all + (kb + b) * g.PP() * g.Cout;
-        xin = xin_all + kb * g.PP() * g.Cin;
-        lo = -b * g.PP(); hi = (a.B - b) * g.PP();       // row bounds relative to this sample's first pixel
-        xin += (long long)b * g.PP() * g.Cin;
-        dst = norm2_all + kb + b;
-        M = g.Cout; N = 9 * g.Cin + 1; Kd = g.PP();
-        return true;
-    }
-    __device__ float loadA(int m, int k) const { return dz[(long long)k * g.Cout + m]; }
-    __device__ float loadB(int n, int k) const {
-        if (n == 9 * g.Cin) return 1.f;
-        const int tap = n / g.Cin, ci = n - tap * g.Cin;
-        const int row = k + (tap / 3 - 1) * g.Wp + (tap % 3 - 1);
-        return (row >= lo && row < hi) ? xin[(long long)row * g.Cin + ci] : 0.f;
-    }
-    __device__ void store(int, int, float acc) { sq = fmaf(acc, acc, sq); }
-    __device__ void finish() {
-        const float v = flb_warp_sum(sq);
-        if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(dst, v);
-    }
-};
-
-struct LinFwdProb {         // out[b][n] += sum_k act[b][k] * W[n][k]     (bias added by the consumer)
-    static constexpr bool A_MCONTIG = false, B_NCONTIG = false;
-    flb_train_args a; int In, Out, woff; const float* act_all; float* out_all;
-    const float* act; float* out; const float* w;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        act = act_all + (long long)client * a.B * In;
-        out = out_all + (long long)client * a.B * Out;
-        w = a.W + (long long)client * a.ld + woff;
-        M = bsz; N = Out; Kd = In;
-        return true;
-    }
-    __device__ float loadA(int m, int k) const { return act[(long long)m * In + k]; }
-    __device__ float loadB(int n, int k) const { return __ldg(&w[(long long)n * In + k]); }
-    __device__ void store(int m, int n, float acc) { atomicAdd(&out[m * Out + n], acc); }
-    __device__ void finish() {}
-};
-
-struct LinDgradProb {       // dact[b][n] = sum_k dout[b][k] * W[k][n]
-    static constexpr bool A_MCONTIG = false, B_NCONTIG = true;
-    flb_train_args a; int In, Out, woff; const float* dout_all; float* dact_all;
-    const float* dout; float* dact; const float* w;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        dout = dout_all + (long long)client * a.B * Out;
-        dact = dact_all + (long long)client * a.B * In;
-        w = a.W + (long long)client * a.ld + woff;
-        M = bsz; N = In; Kd = Out;
-        return true;
-    }
-    __device__ float loadA(int m, int k) const { return dout[m * Out + k]; }
-    __device__ float loadB(int n, int k) const { return __ldg(&w[(long long)k * In + n]); }
-    __device__ void store(int m, int n, float acc) { dact[(long long)m * In + n] = acc; }
-    __device__ void finish() {}
-};
-
-struct LinWgradProb {       // dW[m][n] = sum_b dout[b][m] * act[b][n]   (bias gradient: head_wgrad_kernel)
-    static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
-    flb_train_args a; int In, Out, woff, boff; const float* dout_all; const float* act_all; const float* coef_all;
-    const float* dout; const float* act; const float* coef; float* gw; float* gb;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        dout = dout_all + (long long)client * a.B * Out;
-        act = act_all + (long long)client * a.B * In;
-        coef = coef_all ? coef_all + (long long)client * a.B : nullptr;
-        gw = a.G + (long long)client * a.ld + woff;
-        gb = a.G + (long long)client * a.ld + boff;
-        M = Out; N = In; Kd = bsz;
-        return true;
-    }
-    __device__ float loadA(int m, int k) const { const float v = dout[k * Out + m]; return coef ? v * coef[k] : v; }
-    __device__ float loadB(int n, int k) const { return act[(long long)k * In + n]; }
-    __device__ void store(int m, int n, float acc) { gw[(long long)m * In + n] = acc; }
-    __device__ void finish() {}
-};
 
 // ------------------------------------------------------------------------------------------------
 // classifier head: fc1 bias + ReLU + dropout, fc2, softmax cross-entropy, dlogits, dh.  One CTA per client.
@@ -602,83 +396,6 @@ __global__ void clip_coef_kernel(flb_train_args a, SimpleCnnWs ws) {
     ws.coef[i] = n > a.dp_clip ? a.dp_clip / n : 1.f;         // clip rule of privacy.py:127-138, per sample
 }
 
-// ------------------------------------------------------------------------------------------------
-// optimizer over [K, ld]; torch.optim semantics (training.py:244-255): Adam(lr) | SGD(lr, momentum=0.9) | AdamW(lr)
-__global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P) {
-    const int k = blockIdx.y;
-    const int bsz = flb_bsz(a, k);
-    if (bsz == 0) return;
-    const int t = a.tcount[k] + 1;
-    float* W = a.W + (long long)k * a.ld;
-    float* G = a.G + (long long)k * a.ld;
-    float* M = a.M + (long long)k * a.ld;
-    float* V = a.V + (long long)k * a.ld;
-    // scalars are formed in double and rounded to fp32 once, like Python floats entering fp32 tensor ops
-    const double bc1d = 1.0 - pow(a.beta1, (double)t), bc2d = 1.0 - pow(a.beta2, (double)t);
-    const float step_size = (float)(a.lr / bc1d), bc2_sqrt = (float)sqrt(bc2d);
-    const float lr = (float)a.lr, omb1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, omb2 = (float)(1.0 - a.beta2);
-    const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
-    const float inv_b = 1.f / (float)bsz;
-    const float* zrow = a.dp_z ? a.dp_z + (long long)k * a.ld : nullptr;
-    const int P4 = (P + 3) >> 2;
-    for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
-            const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
-            z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int p = c4 * 4 + e;
-            if (p >= P) break;
-            float g = G[p];
-            if (a.dp_mode == 1) g = (g + a.dp_sigma * (zrow ? zrow[p] : z[e])) * inv_b;   // (sum clipped + N(0, sigma^2)) / B
-            float w = W[p];
-            if (a.opt == 1) {                               // SGD with momentum, dampening 0
-                const float buf = t == 1 ? g : fmaf(mu, M[p], g);
-                M[p] = buf;
-                w = w - lr * buf;
-            } else {
-                if (a.opt == 2) w = w * decay;      // AdamW decoupled decay
-                float m = M[p], v = V[p];
-                m = m + (g - m) * omb1;                           // exp_avg.lerp_(grad, 1 - beta1)
-                v = v * b2 + omb2 * g * g;                  // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-                M[p] = m; V[p] = v;
-                const float denom = sqrtf(v) / bc2_sqrt + eps;
-                w = w - step_size * (m / denom);                             // param.addcdiv_(m, denom, -step_size)
-            }
-            W[p] = w;
-        }
-    }
-}
-
-__global__ void advance_kernel(flb_train_args a) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < a.K && flb_bsz(a, k) > 0) a.tcount[k] += 1;
-    __syncthreads();            // single block: every tcount update read the old step first
-    if (k == 0) *a.step_ctr += 1;
-}
-
-__global__ void begin_epoch_kernel(flb_train_args a) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < a.K) { a.loss_sum[k] = 0.f; a.correct[k] = 0; a.nbatch[k] = 0; a.nseen[k] = 0; }
-    if (k == 0) *a.step_ctr = 0;
-}
-
-int check_args(const flb_train_args* a) {
-    FLB_CHECK_ARG(a != nullptr, "flb_train: null args");
-    FLB_CHECK_ARG(a->model == 0, "flb_train: model %d not supported by this entry (0 = simple_cnn)", a->model);
-    FLB_CHECK_ARG(a->K >= 1 && a->K <= 1024 && a->B >= 1 && a->B <= 32, "flb_train: need 1 <= K <= 1024 and 1 <= B <= 32 (K=%d B=%d)", a->K, a->B);
-    FLB_CHECK_ARG(a->ld >= Off::P, "flb_train: ld %lld < %d parameters", a->ld, Off::P);
-    FLB_CHECK_ARG(a->x && a->y && a->sample_off && a->nsamples && a->step_ctr && a->W && a->G && a->M && a->V &&
-                  a->tcount && a->ws && a->loss_sum && a->correct && a->nbatch && a->nseen, "flb_train: null device pointer in args");
-    FLB_CHECK_ARG(a->opt >= 0 && a->opt <= 2, "flb_train: Unknown optimizer type: %d", a->opt);
-    FLB_CHECK_ARG(a->drop_p >= 0.f && a->drop_p < 1.f, "flb_train: dropout probability must be in [0, 1)");
-    FLB_CHECK_ARG(a->precision == 0 || a->precision == 1, "flb_train: precision must be 0 (fp32) or 1 (tf32 tensor cores)");
-    FLB_CHECK_ARG(a->dp_mode == 0 || a->dp_mode == 1, "flb_train: dp_mode must be 0 or 1");
-    return FLB_OK;
-}
-
 const ConvGeom kConv2{32, 64, 14, 14, 16, 16};
 
 int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
@@ -785,13 +502,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
 
 }  // namespace
 
-extern "C" long long flb_train_ws_bytes(int model, int K, int B) {
-    if (model != 0 || K < 1 || B < 1) return -1;
-    return (long long)simplecnn_ws_carve(nullptr, K, B, nullptr);
-}
-
-extern "C" long long flb_train_ws_offset(int model, int K, int B, const char* name) {
-    if (model != 0 || K < 1 || B < 1 || !name) return -1;
+namespace simplecnn {
+int num_params() { return Off::P; }
+long long ws_bytes(int K, int B) { return (long long)simplecnn_ws_carve(nullptr, K, B, nullptr); }
+long long ws_offset(int K, int B, const char* name) {
     SimpleCnnWs ws;
     simplecnn_ws_carve((void*)0, K, B, &ws);
 #define FIELD(f) if (!strcmp(name, #f)) return (long long)(uintptr_t)ws.f;
@@ -800,80 +514,11 @@ extern "C" long long flb_train_ws_offset(int model, int K, int B, const char* na
 #undef FIELD
     return -1;
 }
-
-extern "C" int flb_train_begin_epoch(const flb_train_args* a, void* stream) {
-    if (int rc = check_args(a)) return rc;
-    begin_epoch_kernel<<<flb_cdiv(a->K, 256), 256, 0, (cudaStream_t)stream>>>(*a);
-    FLB_LAUNCH_CHECK();
-    return FLB_OK;
-}
-
-extern "C" int flb_train_forward(const flb_train_args* a, void* stream) {
-    if (int rc = check_args(a)) return rc;
+int forward(const flb_train_args& a, cudaStream_t st) {
     SimpleCnnWs ws;
-    simplecnn_ws_carve(a->ws, a->K, a->B, &ws);
-    return forward(*a, ws, (cudaStream_t)stream);
+    simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
+    return ::forward(a, ws, st);
 }
-
-extern "C" int flb_train_advance(const flb_train_args* a, void* stream) {
-    if (int rc = check_args(a)) return rc;
-    advance_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*a);
-    FLB_LAUNCH_CHECK();
-    return FLB_OK;
-}
-
-extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {
-    if (int rc = check_args(a)) return rc;
-    return forward_backward(*a, (cudaStream_t)stream);
-}
-
-extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
-    if (int rc = check_args(a)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = forward_backward(*a, st)) return rc;
-    const int blocks = max(1, min(flb_cdiv(Off::P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
-    optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, Off::P);
-    MARK("optimizer");
-    advance_kernel<<<1, 1024, 0, st>>>(*a);
-    MARK("advance");
-    FLB_LAUNCH_CHECK();
-    return FLB_OK;
-}
-
-// number of kernel launches (memsets excluded) one flb_train_step issues for these args
-extern "C" int flb_train_step_launches(const flb_train_args* a) {
-    if (!a) return -1;
-    return a->dp_mode == 1 ? 18 : 14;
-}
-
-// One step with a CUDA event after every kernel.  Synchronises the stream (profiling aid, not the product path).
-// names_out receives '\n'-separated labels; ms_out[i] = device time of labelled segment i.  Returns the segment count.
-extern "C" int flb_train_step_profiled(const flb_train_args* a, void* stream, char* names_out, int names_cap,
-                                       float* ms_out, int max_n) {
-    if (int rc = check_args(a)) return rc;
-    FLB_CHECK_ARG(names_out && ms_out && names_cap > 0 && max_n > 0, "flb_train_step_profiled: bad output buffers");
-    for (int i = 0; i < 48; ++i) FLB_CUDA(cudaEventCreate(&g_prof.ev[i]));
-    g_prof.n = 0;
-    g_prof.on = true;
-    const int rc = flb_train_step(a, stream);
-    g_prof.on = false;
-    int n = 0;
-    if (rc == FLB_OK && cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess) {
-        names_out[0] = 0;
-        size_t used = 0;
-        for (int i = 1; i < g_prof.n && n < max_n; ++i) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, g_prof.ev[i - 1], g_prof.ev[i]);
-            ms_out[n++] = ms;
-            const size_t len = strlen(g_prof.name[i]);
-            if (used + len + 2 < (size_t)names_cap) {
-                memcpy(names_out + used, g_prof.name[i], len);
-                used += len;
-                names_out[used++] = '\n';
-                names_out[used] = 0;
-            }
-        }
-    }
-    for (int i = 0; i < 48; ++i) cudaEventDestroy(g_prof.ev[i]);
-    return rc == FLB_OK ? n : rc;
-}
+int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
+int step_launches(const flb_train_args& a) { return a.dp_mode == 1 ? 16 : 12; }
+}  // namespace simplecnn

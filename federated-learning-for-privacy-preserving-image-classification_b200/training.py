@@ -62,8 +62,6 @@ class BatchedClientTrainer:
                  client_base: int = 0, client_stride: int = 1, use_graph: bool = True):
         if model_name not in MODEL_IDS:
             raise ValueError(f"Unknown model: {model_name}. Available: {list(MODEL_IDS)}")
-        if model_name != "simple_cnn":
-            raise L.FlbError(f"BatchedClientTrainer: kernels for '{model_name}' are not built yet (simple_cnn only)")
         if not (1 <= batch_size <= MAX_BATCH):
             raise L.FlbError(f"batch_size must be in 1..{MAX_BATCH}, got {batch_size}")
         if precision not in PRECISIONS:
@@ -96,6 +94,11 @@ class BatchedClientTrainer:
         self.nseen = torch.zeros(K, dtype=torch.int32, device=dev)
         self.ws_bytes = L.call_ll("flb_train_ws_bytes", self.model_id, K, self.B)
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)      # pads of the NHWC grids stay zero forever
+        nbn = L.call_ll("flb_train_bn_floats", self.model_id)
+        self.bn_running = None                # cifar10_cnn: client-local running_mean | running_var, [K, 2 * 448]
+        if nbn:
+            self.bn_running = torch.zeros((K, nbn), dtype=torch.float32, device=dev)
+            self.bn_running[:, nbn // 2:] = 1.0
         self.x = self.y = self.sample_off = self.nsamples = None
         self.n_host: List[int] = []
         self.drop_keep: Optional[torch.Tensor] = None
@@ -168,7 +171,8 @@ class BatchedClientTrainer:
         a.x, a.y, a.sample_off, a.nsamples, a.step_ctr = p(self.x), p(self.y), p(self.sample_off), p(self.nsamples), p(self.step_ctr)
         a.W, a.G, a.M, a.V, a.tcount, a.ws = p(self.W), p(self.G), p(self.M), p(self.V), p(self.tcount), p(self.ws)
         a.loss_sum, a.correct, a.nbatch, a.nseen = p(self.loss_sum), p(self.correct), p(self.nbatch), p(self.nseen)
-        a.drop_keep, a.dp_z = p(self.drop_keep), p(self.dp_z)
+        a.drop_keep, a.dp_z, a.bn_running = p(self.drop_keep), p(self.dp_z), p(self.bn_running)
+        a.eval_mode = 0 if train else 1
         a.ld, a.seed, a.client_base, a.client_stride = self.layout.ld, self.seed, self.client_base, self.client_stride
         a.lr, a.beta1, a.beta2, a.eps = float(lr), 0.9, 0.999, 1e-8            # torch.optim.Adam / AdamW defaults
         a.weight_decay = 0.01 if opt == "adamw" else 0.0
@@ -318,11 +322,25 @@ def forward_logits(model: FederatedCNNBase, x: torch.Tensor, precision: str = "f
     if not p.is_cuda:
         raise L.FlbError("model.forward: parameters are on the CPU; move the model to a CUDA device (no CPU path)")
     eng = _engine_for(model, p.device, MAX_BATCH, precision)
-    eng.set_client_weights(0, {n: q.data for n, q in model.named_parameters()})
+    _push_model(model, eng)
     eng.load_data([x.detach().to(torch.float32)], [torch.zeros(x.shape[0], dtype=torch.int64)])
     if model.training and model.dropout_rate > 0:
         raise L.FlbError("model.forward in train mode with dropout is only available inside LocalTrainer")
     return eng.evaluate()[3].to(x.device if x.is_cuda else p.device)
+
+
+def _push_model(model: FederatedCNNBase, eng: BatchedClientTrainer) -> None:
+    """Module parameters (+ client-local BatchNorm buffers, which are never federated) -> row 0 of the engine."""
+    eng.set_client_weights(0, {n: p.data for n, p in model.named_parameters()})
+    if eng.bn_running is not None:
+        half = eng.bn_running.shape[1] // 2
+        off = 0
+        for m in model.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                c = m.num_features
+                eng.bn_running[0, off:off + c].copy_(m.running_mean)
+                eng.bn_running[0, half + off:half + off + c].copy_(m.running_var)
+                off += c
 
 
 class LocalTrainer:
@@ -342,14 +360,26 @@ class LocalTrainer:
         if self.checkpoint_dir:
             os.makedirs(self.checkpoint_dir, exist_ok=True)
 
-    def _push(self, eng: BatchedClientTrainer) -> None:
-        eng.set_client_weights(0, {n: p.data for n, p in self.model.named_parameters()})
+    def _bn_modules(self):
+        return [m for m in self.model.modules() if isinstance(m, nn.BatchNorm2d)]
 
-    def _pull(self, eng: BatchedClientTrainer) -> None:
+    def _push(self, eng: BatchedClientTrainer) -> None:
+        _push_model(self.model, eng)
+
+    def _pull(self, eng: BatchedClientTrainer, steps: int = 0) -> None:
         views = eng.layout.views(eng.W[0])
         with torch.no_grad():
             for n, p in self.model.named_parameters():
                 p.data.copy_(views[n])
+            if eng.bn_running is not None:
+                half = eng.bn_running.shape[1] // 2
+                off = 0
+                for m in self._bn_modules():
+                    c = m.num_features
+                    m.running_mean.copy_(eng.bn_running[0, off:off + c])
+                    m.running_var.copy_(eng.bn_running[0, half + off:half + off + c])
+                    m.num_batches_tracked += steps
+                    off += c
 
     def train_local_model(self, train_loader, epochs: int, learning_rate: float = 0.001,
                           optimizer_type: str = "adam", loss_function: Optional[nn.Module] = None,
@@ -382,7 +412,7 @@ class LocalTrainer:
                 loss, acc, seen = eng.epoch_metrics()
                 losses.append(float(loss[0])); accs.append(float(acc[0]))
                 total_samples += int(seen[0])
-                self._pull(eng)
+                self._pull(eng, steps=eng.max_steps())
                 val_loss = None
                 if validation_loader:
                     val_loss, _ = self._validate_epoch(validation_loader)

@@ -88,17 +88,21 @@ typedef struct flb_train_args {
     int* nseen;                   /* [K] */
     const unsigned char* drop_keep; /* optional injected dropout keep-mask [K, B, 128] (NULL: Philox)  */
     const float* dp_z;            /* optional injected standard normals [K, ld] for dp_mode 1 (NULL: Philox) */
+    float* bn_running;            /* cifar10_cnn: client-local BatchNorm buffers [K, flb_train_bn_floats()] =
+                                     running_mean of bn1..bn6 then running_var of bn1..bn6 (never federated,
+                                     models_pytorch.py:25-27); NULL for simple_cnn                            */
     long long ld;
     unsigned long long seed;      /* Philox seed for dropout and per-sample-DP noise                 */
     unsigned long long client_base; /* global index of local client 0 (Philox stream = client_base + k*client_stride) */
     unsigned long long client_stride; /* global-index distance between consecutive local clients (= world size) */
     double lr, beta1, beta2, eps, weight_decay, momentum;   /* torch.optim defaults are Python doubles */
-    int model;                    /* 0 = simple_cnn                                                  */
+    int model;                    /* 0 = simple_cnn, 1 = cifar10_cnn (models_pytorch.py:59-97, :100-165) */
     int K;                        /* resident clients                                                */
     int B;                        /* batch size (<= 32)                                              */
     int precision;                /* 0 = fp32 CUDA-core kernels, 1 = TF32 tcgen05 tensor-core kernels */
     int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
     int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise         */
+    int eval_mode;                /* 1: model.eval() semantics -- no dropout, BatchNorm uses the running statistics */
     int tc_mask;                  /* precision 1 only: bit set = that GEMM on tensor cores (0 = all): 1 conv2 fwd,
                                      2 fc1 fwd, 4 fc1 dgrad, 8 conv2 dgrad, 16 fc1 wgrad, 32 conv2 wgrad (test aid) */
     float drop_p;                 /* dropout probability of SimpleCNN.dropout (0.25 upstream)        */
@@ -107,6 +111,8 @@ typedef struct flb_train_args {
 } flb_train_args;
 
 long long flb_train_ws_bytes(int model, int K, int B);
+/* floats per client of the bn_running buffer (0 for simple_cnn) */
+long long flb_train_bn_floats(int model);
 /* pointers (as byte offsets into ws) of named workspace arrays, for tests: returns -1 if unknown */
 long long flb_train_ws_offset(int model, int K, int B, const char* name);
 /* zero the epoch accumulators and step counter (start of _train_epoch, training.py:178-182) */

@@ -1,0 +1,216 @@
+"""GPU parity: the batched CIFAR10CNN training kernels (through the C ABI) vs the oracle (oracle/training.py) and vs
+golden vectors produced by the unmodified reference (models_pytorch.CIFAR10CNN + LocalTrainer)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import adam_trajectory_check, digest_check, load_golden
+from oracle import models as OM
+from oracle import training as OT
+
+pytestmark = pytest.mark.gpu
+MODEL = "cifar10_cnn"
+CH = [32, 32, 64, 64, 128, 128]
+MASK_SHAPES = [(32, 16, 16), (64, 8, 8), (128, 4, 4), (512,), (256,)]
+
+
+def _data(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((n,) + OM.input_shape(MODEL), generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    return x, y
+
+
+def _engine(cuda_device, K, B, **kw):
+    from flb200.training import BatchedClientTrainer
+    kw.setdefault("dropout_rate", 0.0)
+    kw.setdefault("precision", "fp32")
+    return BatchedClientTrainer(MODEL, K, cuda_device, batch_size=B, **kw)
+
+
+def _bn_buffers(eng, k=0):
+    run = eng.bn_running[k].cpu()
+    half = run.numel() // 2
+    out, off = {}, 0
+    for i, c in enumerate(CH, start=1):
+        out[f"bn{i}.running_mean"] = run[off:off + c]
+        out[f"bn{i}.running_var"] = run[half + off:half + off + c]
+        off += c
+    return out
+
+
+def _close(a, ref, tag, rel_l2=5e-3, frac=0.9):
+    """A max-pool window whose two largest entries agree to ~1e-7 picks a different argmax under ANY change of
+    summation order; one such flip moves one gradient entry to its neighbour and perturbs every upstream gradient
+    by ~1e-3 of its norm (measured: fp64 oracle vs reference fp32 shows the same).  So tensors are compared by
+    relative L2 error, and elementwise for the large majority of entries."""
+    a, ref = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(ref, dtype=np.float64).reshape(-1)
+    assert np.linalg.norm(a - ref) <= rel_l2 * np.linalg.norm(ref) + 1e-12, (tag, np.linalg.norm(a - ref) / np.linalg.norm(ref))
+    ok = np.abs(a - ref) <= 1e-2 * np.abs(ref) + 1e-4 * max(1e-3, np.abs(ref).max())
+    assert ok.mean() >= frac, (tag, ok.mean())
+
+
+def _grad_check(got, grads, tag):
+    for name, g in grads.items():
+        ref = g.numpy()
+        if name.startswith("conv") and name.endswith(".bias"):
+            # a conv bias feeding BatchNorm has an exactly-zero gradient; both sides hold rounding noise
+            assert np.abs(got[name].cpu().numpy()).max() < 1e-5 and np.abs(ref).max() < 1e-5, name
+            continue
+        _close(got[name].cpu().numpy(), ref, f"{tag}/{name}")
+
+
+def test_forward_and_grads_match_reference_golden(cuda_device):
+    gold = load_golden("forward_cifar10_cnn.npz")
+    w = OM.init_weights(MODEL, 11)
+    x, y = _data(21, 6)
+    assert abs(float(x.double().sum()) - float(gold["x_sum"])) < 1e-6
+    eng = _engine(cuda_device, 1, 6)
+    eng.set_client_weights(0, w)
+    eng.load_data([x], [y])
+    eng.forward_backward()
+    logits = eng.ws_array("logits", torch.float32, 10)[0, :6].cpu().numpy()
+    np.testing.assert_allclose(logits, gold["logits"], rtol=2e-4, atol=2e-5)
+    loss, acc, seen = eng.epoch_metrics()
+    assert abs(float(loss[0]) - float(gold["loss"])) < 2e-5 and int(seen[0]) == 6
+    got = eng.layout.views(eng.G[0])
+    for k, t in got.items():
+        a = t.reshape(-1).cpu().numpy()
+        ref = gold[f"grad/{k}/sample"]
+        s = a[::97] if a.size > 4096 else a
+        if k.startswith("conv") and k.endswith(".bias"):
+            assert np.abs(s).max() < 1e-5 and np.abs(ref).max() < 1e-5
+            continue
+        _close(s, ref, k)
+    # eval-mode forward uses the running statistics, updated once by the training-mode pass above
+    _, _, _, lg = eng.evaluate()
+    np.testing.assert_allclose(lg.cpu().numpy(), gold["logits_eval"], rtol=2e-4, atol=2e-5)
+
+
+def test_batched_ragged_clients_with_injected_dropout_vs_oracle(cuda_device):
+    """3 clients with different weights, ragged batch sizes and injected dropout masks, one launch sequence."""
+    sizes = [8, 5, 2]
+    B, p = 8, 0.3
+    eng = _engine(cuda_device, 3, B, dropout_rate=p)
+    gen = torch.Generator().manual_seed(3)
+    keep = [[(torch.rand((B,) + s, generator=gen) >= p) for s in MASK_SHAPES] for _ in sizes]
+    flat = torch.stack([torch.cat([m.reshape(B, -1) for m in ms], dim=1) for ms in keep])       # [K, B, 15104]
+    eng.drop_keep = flat.to(torch.uint8).to(cuda_device).contiguous()
+    ws, xs, ys = [], [], []
+    for k, n in enumerate(sizes):
+        w = OM.init_weights(MODEL, 30 + k)
+        for i in range(1, 7):                      # non-trivial BatchNorm affine parameters
+            w[f"bn{i}.weight"] = 1.0 + 0.2 * torch.randn(w[f"bn{i}.weight"].shape, generator=gen)
+            w[f"bn{i}.bias"] = 0.1 * torch.randn(w[f"bn{i}.bias"].shape, generator=gen)
+        ws.append(w)
+        x, y = _data(40 + k, n)
+        xs.append(x); ys.append(y)
+        eng.set_client_weights(k, w)
+    eng.load_data(xs, ys)
+    eng.forward_backward()
+    for k, n in enumerate(sizes):
+        masks = [m[:n].float() for m in keep[k]]
+        loss, logits, grads = OT.loss_and_grads(MODEL, ws[k], xs[k], ys[k], train=True, dropout_rate=p, masks=masks)
+        np.testing.assert_allclose(eng.ws_array("logits", torch.float32, 10)[k, :n].cpu().numpy(), logits.numpy(),
+                                   rtol=2e-4, atol=2e-5)
+        _grad_check(eng.layout.views(eng.G[k]), grads, k)
+
+
+@pytest.mark.parametrize("opt", ["adam", "sgd", "adamw"])
+def test_training_trajectory_matches_reference_golden(cuda_device, opt):
+    """2 epochs x 3 steps of the unmodified reference LocalTrainer (golden) vs the kernels, BN buffers included."""
+    gold = load_golden(f"train_cifar10_cnn_{opt}.npz")
+    w = OM.init_weights(MODEL, 12)
+    x, y = _data(22, 24)
+    eng = _engine(cuda_device, 1, 8)
+    eng.set_client_weights(0, w)
+    eng.load_data([x], [y])
+    lr = 1e-3 if opt != "sgd" else 1e-2
+    loss, acc, samples = eng.train(2, lr, opt)
+    g_loss, g_acc, g_ep, g_n = gold["metrics"]
+    assert samples[0] == int(g_n)
+    assert abs(loss[0] - g_loss) < 2e-3 and abs(acc[0] - g_acc) < 1e-9
+    got = eng.client_weights(0, "cpu")
+    if opt == "sgd":
+        noise = {k: v for k, v in got.items() if k.startswith("conv") and k.endswith(".bias")}
+        rest = {k: v for k, v in got.items() if k not in noise}
+        digest_check(gold, "w", rest, rtol=5e-4, atol=5e-6)
+        for k, v in noise.items():          # zero-gradient parameters: they must not have moved
+            np.testing.assert_allclose(v.numpy(), w[k].numpy(), atol=1e-6)
+    else:
+        # conv biases feeding BatchNorm see pure rounding-noise gradients, which Adam turns into +-lr steps
+        rest = {k: v for k, v in got.items() if not (k.startswith("conv") and k.endswith(".bias"))}
+        adam_trajectory_check(gold, "w", rest, w, lr, rel_l2=2e-2)
+        for k, v in got.items():
+            assert float((v - w[k]).abs().max()) <= 6.5 * lr, k       # 6 Adam steps of at most ~lr each
+    bufs = _bn_buffers(eng)
+    if opt == "sgd":
+        digest_check(gold, "buf", bufs, rtol=1e-3, atol=1e-5)
+    else:
+        # running_mean carries the conv bias, which random-walks by +-lr per Adam step (see above)
+        digest_check(gold, "buf", {k: v for k, v in bufs.items() if k.endswith("var")}, rtol=2e-3, atol=1e-5)
+        digest_check(gold, "buf", {k: v for k, v in bufs.items() if k.endswith("mean")}, rtol=0, atol=6.5 * lr)
+
+
+def test_local_trainer_drop_in_cifar(cuda_device):
+    from torch.utils.data import DataLoader, TensorDataset
+    from flb200.models_pytorch import ModelFactory
+    from flb200.training import LocalTrainer
+    gold = load_golden("train_cifar10_cnn_sgd.npz")
+    model = ModelFactory.create_model(MODEL, dropout_rate=0.0)
+    assert model.get_parameter_count() == 1470890
+    model.set_model_weights(OM.init_weights(MODEL, 12))
+    x, y = _data(22, 24)
+    loader = DataLoader(TensorDataset(x, y), batch_size=8, shuffle=False)
+    trainer = LocalTrainer(model, cuda_device)
+    m = trainer.train_local_model(loader, 2, learning_rate=1e-2, optimizer_type="sgd", save_checkpoints=False)
+    g_loss, g_acc, g_ep, g_n = gold["metrics"]
+    assert (m.epochs_completed, m.samples_processed) == (int(g_ep), int(g_n))
+    assert abs(m.loss - g_loss) < 2e-3
+    bufs = {k: b.float() for k, b in model.named_buffers() if "num_batches" not in k}
+    digest_check(gold, "buf", bufs, rtol=1e-3, atol=1e-5)
+    assert int(model.bn1.num_batches_tracked) == 6
+    # eval-mode forward through the kernels (running statistics) vs the oracle on the trained weights
+    wts = {k: v.cpu() for k, v in model.get_model_weights().items()}
+    ref = OM.forward(MODEL, wts, x, train=False, bn_state={k: v.cpu() for k, v in bufs.items()})
+    logits = model.eval()(x.to(cuda_device))
+    np.testing.assert_allclose(logits.cpu().numpy(), ref.numpy(), rtol=2e-4, atol=2e-5)
+    ev = trainer.evaluate_model(loader)
+    assert ev["total_samples"] == 24 and abs(ev["overall_accuracy"] - float((ref.argmax(1) == y).float().mean())) < 1e-9
+
+
+def test_per_sample_dp_is_refused_for_batchnorm_model(cuda_device):
+    from flb200 import FlbError
+    eng = _engine(cuda_device, 1, 8)
+    eng.configure_dp("per_sample", 1.0, 1.0)
+    x, y = _data(1, 8)
+    eng.load_data([x], [y])
+    with pytest.raises(FlbError, match="BatchNorm"):
+        eng.train(1, 1e-3, "adam")
+
+
+def test_cifar_round_sgd_vs_oracle(cuda_device):
+    """One federated round (train -> update-level DP with injected noise -> FedAvg, q8 off) on CIFAR10CNN."""
+    from flb200.simulation import FederatedRoundEngine
+    from oracle import round as OR
+    K, sizes = 3, [16, 11, 8]
+    spec = OM.model_spec(MODEL)
+    w0 = OM.init_weights(MODEL, 3)
+    data = [OR.synthetic_client_data(MODEL, c, n=sizes[c]) for c in range(K)]
+    gen = torch.Generator().manual_seed(5)
+    zs = [{k: torch.randn(spec[k], generator=gen) * 1e-3 for k in spec} for _ in range(K)]
+    ref, info = OR.federated_round(MODEL, w0, K, dp=True, zs=zs, data=data, batch_size=8, lr=1e-2, optimizer="sgd")
+    eng = FederatedRoundEngine(MODEL, K, cuda_device, batch_size=8, learning_rate=1e-2, optimizer_type="sgd",
+                               dp_mode="update", dropout_rate=0.0, precision="fp32")
+    eng.set_global_weights(w0)
+    eng.load_data([d[0] for d in data], [d[1] for d in data], sizes)
+    rows = eng.layout.new_rows(K, eng.device)
+    for k, z in enumerate(zs):
+        eng.layout.flatten_into(rows[k], z)
+    eng.dp_z = rows
+    out = eng.run_round()
+    assert out["samples"] == sizes
+    np.testing.assert_allclose(out["losses"], info["losses"], atol=1e-3)
+    got = eng.global_weights("cpu")
+    for name in ref:
+        np.testing.assert_allclose(got[name].numpy(), ref[name].numpy(), rtol=5e-4, atol=5e-6, err_msg=name)
