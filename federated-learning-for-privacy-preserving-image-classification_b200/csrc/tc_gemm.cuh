@@ -122,14 +122,14 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
 
 // Traits interface:
 //   struct Params;                                   kernel parameter block (holds CUtensorMaps by value)
-//   static constexpr int STAGES, STAGE_BYTES, RESIDENT_BYTES, TMEM_COLS;
+//   static constexpr int STAGES, STAGE_BYTES, RESIDENT_BYTES, TMEM_COLS, MINB (CTAs per SM the kernel is built for);
 //   __device__ bool setup(const Params&, int& num_kb)          CTA-uniform; false -> nothing to do
 //   __device__ void stage_resident(uint8_t* res, int tid)      all threads (generic-proxy writes)
 //   __device__ void load(int kb, uint8_t* stage, uint64_t* bar) producer lane: expect_tx + TMA boxes
 //   __device__ void mma(int kb, uint32_t stage_addr, uint32_t res_addr, uint32_t tmem)   MMA lane
 //   __device__ void epilogue(uint32_t tmem, int quarter, int lane)   epilogue warps, quarter = warp % 4
 template <class T>
-__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ typename T::Params p) {
+__global__ void __launch_bounds__(THREADS, T::MINB) gemm_kernel(const __grid_constant__ typename T::Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], accum_bar;

@@ -11,7 +11,26 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 // optimizer over [K, ld]; torch.optim semantics (training.py:244-255): Adam(lr) | SGD(lr, momentum=0.9) | AdamW(lr)
-__global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P) {
+// W (reference layout) -> Wt (tap-major) for every tensor-core conv layer; DIR 1: Gt -> G for the live layers
+template <int DIR>
+__global__ void __launch_bounds__(256) tc_repack_kernel(flb_train_args a, TcConvTab t) {
+    const int k = blockIdx.y;
+    const float* W = a.W + (long long)k * a.ld;
+    float* G = a.G + (long long)k * a.ld;
+    float* wt = t.wt + (long long)k * t.ldt;
+    const float* gt = t.gt + (long long)k * t.ldt;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < t.ldt; e += gridDim.x * 256) {
+        int i = 0;
+        while (i + 1 < t.n && e >= t.toff[i + 1]) ++i;
+        const int r = e - t.toff[i], cin = t.cin[i], cout = t.cout[i];
+        const int ci = r % cin, co = (r / cin) % cout, tap = r / (cin * cout);
+        const int p = t.woff[i] + (co * cin + ci) * 9 + tap;
+        if (DIR == 0) wt[e] = W[p];
+        else if (t.gt_live[i]) G[p] = gt[e];
+    }
+}
+
+__global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P, TcConvTab tab) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
@@ -27,6 +46,8 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P)
     const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
     const float inv_b = 1.f / (float)bsz;
     const float* zrow = a.dp_z ? a.dp_z + (long long)k * a.ld : nullptr;
+    float* wt = tab.wt + (long long)k * tab.ldt;
+    const float* gt = tab.gt + (long long)k * tab.ldt;
     const int P4 = (P + 3) >> 2;
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -38,7 +59,9 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P)
         for (int e = 0; e < 4; ++e) {
             const int p = c4 * 4 + e;
             if (p >= P) break;
-            float g = G[p];
+            int layer = 0;
+            const int q = tab.n ? tc_tab_map(tab, p, layer) : -1;
+            float g = (q >= 0 && tab.gt_live[layer]) ? gt[q] : G[p];
             if (a.dp_mode == 1) g = (g + a.dp_sigma * (zrow ? zrow[p] : z[e])) * inv_b;   // (sum clipped + N(0, sigma^2)) / B
             float w = W[p];
             if (a.opt == 1) {                               // SGD with momentum, dampening 0
@@ -55,6 +78,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P)
                 w = w - step_size * (m / denom);                             // param.addcdiv_(m, denom, -step_size)
             }
             W[p] = w;
+            if (q >= 0) wt[q] = w;
         }
     }
 }
@@ -96,6 +120,15 @@ int check_args(const flb_train_args* a) {
 
 int num_params(const flb_train_args& a) { return a.model == 0 ? simplecnn::num_params() : cifar::num_params(); }
 
+TcConvTab tab_of(const flb_train_args& a) {
+    TcConvTab t;
+    if (a.model == 0) simplecnn::tc_tab(a, &t); else cifar::tc_tab(a, &t);
+    return t;
+}
+int repack_blocks(const flb_train_args& a, const TcConvTab& t) {
+    return max(1, min(flb_cdiv(t.ldt, 256), (flb_num_sms() * 8 + a.K - 1) / a.K));
+}
+
 }  // namespace
 
 extern "C" long long flb_train_ws_bytes(int model, int K, int B) {
@@ -113,6 +146,8 @@ extern "C" long long flb_train_bn_floats(int model) { return model == 1 ? cifar:
 extern "C" int flb_train_begin_epoch(const flb_train_args* a, void* stream) {
     if (int rc = check_args(a)) return rc;
     begin_epoch_kernel<<<flb_cdiv(a->K, 256), 256, 0, (cudaStream_t)stream>>>(*a);
+    const TcConvTab t = tab_of(*a);
+    if (t.n) tc_repack_kernel<0><<<dim3(repack_blocks(*a, t), a->K), 256, 0, (cudaStream_t)stream>>>(*a, t);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -135,7 +170,11 @@ static int fwd_bwd(const flb_train_args& a, cudaStream_t st) {
 
 extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {
     if (int rc = check_args(a)) return rc;
-    return fwd_bwd(*a, (cudaStream_t)stream);
+    if (int rc = fwd_bwd(*a, (cudaStream_t)stream)) return rc;
+    const TcConvTab t = tab_of(*a);          // the step proper never needs G in the reference layout; this entry does
+    if (t.n) tc_repack_kernel<1><<<dim3(repack_blocks(*a, t), a->K), 256, 0, (cudaStream_t)stream>>>(*a, t);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
 }
 
 extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
@@ -144,7 +183,7 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     if (int rc = fwd_bwd(*a, st)) return rc;
     const int P = num_params(*a);
     const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
-    optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P);
+    optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P, tab_of(*a));
     MARK("optimizer");
     advance_kernel<<<1, 1024, 0, st>>>(*a);
     MARK("advance");

@@ -49,6 +49,8 @@ struct SimpleCnnWs {
     float* norm2;    // [K][B]              per-sample squared gradient norms (dp_mode 1)
     float* coef;     // [K][B]              per-sample clip coefficients
     float* g1ps;     // [K][B][320]         per-sample conv1 weight+bias gradients (dp_mode 1)
+    float* wt;       // [K][9][64][32]      conv2 weights, tap-major (tensor-core path)
+    float* gt;       // [K][9][64][32]      conv2 weight gradients, tap-major
 };
 
 // per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
@@ -67,6 +69,30 @@ extern StepProfile g_prof;
         }                                                                 \
     } while (0)
 
+// Tensor-core conv layers keep a second, tap-major copy of their weights, Wt[tap][Cout][Cin] per client (both GEMM
+// operands become plain TMA boxes), and accumulate their weight gradients in the same layout (Gt).  The optimizer
+// kernel reads Gt / writes Wt through this table, so the reference-layout rows W / G stay the API.
+struct TcConvTab {
+    int n = 0;                       // tensor-core conv layers (0: fp32 path)
+    int woff[5], cin[5], cout[5], toff[5];
+    int gt_live[5];                  // this layer's wgrad accumulated into Gt (else into the reference-layout row G)
+    int ldt = 0;
+    float* wt = nullptr;             // [K, ldt]
+    float* gt = nullptr;             // [K, ldt]
+};
+// reference-layout offset p -> tap-major offset (or -1 when p is not a tensor-core conv weight)
+__device__ __forceinline__ int tc_tab_map(const TcConvTab& t, int p, int& layer) {
+    for (int i = 0; i < t.n; ++i) {
+        const int r = p - t.woff[i];
+        if (r >= 0 && r < t.cout[i] * t.cin[i] * 9) {
+            const int tap = r % 9, ci = (r / 9) % t.cin[i], co = r / (9 * t.cin[i]);
+            layer = i;
+            return t.toff[i] + (tap * t.cout[i] + co) * t.cin[i] + ci;
+        }
+    }
+    return -1;
+}
+
 // model-specific launch sequences (train_simplecnn.cu, train_cifar.cu), dispatched by train_api.cu
 namespace simplecnn {
 int num_params();
@@ -75,6 +101,7 @@ long long ws_offset(int K, int B, const char* name);
 int forward(const flb_train_args& a, cudaStream_t st);
 int forward_backward(const flb_train_args& a, cudaStream_t st);
 int step_launches(const flb_train_args& a);
+void tc_tab(const flb_train_args& a, TcConvTab* t);
 }
 namespace cifar {
 int num_params();
@@ -84,6 +111,7 @@ long long ws_offset(int K, int B, const char* name);
 int forward(const flb_train_args& a, cudaStream_t st);
 int forward_backward(const flb_train_args& a, cudaStream_t st);
 int step_launches(const flb_train_args& a);
+void tc_tab(const flb_train_args& a, TcConvTab* t);
 }
 
 static inline size_t flb_align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -112,6 +140,8 @@ static inline size_t simplecnn_ws_carve(void* base, int K, int B, SimpleCnnWs* w
     CARVE(norm2, float, KB);
     CARVE(coef, float, KB);
     CARVE(g1ps, float, KB * 320);
+    CARVE(wt, float, (size_t)K * 18432);
+    CARVE(gt, float, (size_t)K * 18432);
 #undef CARVE
     return off;
 }

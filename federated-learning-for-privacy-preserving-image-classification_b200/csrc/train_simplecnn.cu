@@ -22,12 +22,12 @@
 #include <string.h>
 
 namespace tc {
-int conv_fwd_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, int woff, int boff, cudaStream_t st);
-int conv_dgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, int woff, cudaStream_t st);
-int conv_wgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int woff, int splits, cudaStream_t st);
-int fc_fwd_3136_128(const flb_train_args& a, const float* act, float* out, int woff, int splits, cudaStream_t st);
-int fc_dgrad_3136_128(const flb_train_args& a, const float* dout, float* dact, int woff, cudaStream_t st);
-int fc_wgrad_3136_128(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st);
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st);
+int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
+int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
+int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
+int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
 }  // namespace tc
 
 namespace {
@@ -397,6 +397,7 @@ __global__ void clip_coef_kernel(flb_train_args a, SimpleCnnWs ws) {
 }
 
 const ConvGeom kConv2{32, 64, 14, 14, 16, 16};
+constexpr int kLdt = 9 * 64 * 32;          // tap-major conv2 weights per client
 
 int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     const int K = a.K, B = a.B;
@@ -407,7 +408,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     MARK("conv1_fwd_pool");
     const int tcm = tc_mask_of(a);
     if (tcm & TC_CONV2_FWD) {
-        if (int rc = tc::conv_fwd_32_64(a, kConv2, ws.a1p, ws.z2, Off::c2w, Off::c2b, st)) return rc;
+        if (int rc = tc::conv_fwd(a, kConv2, ws.a1p, ws.z2, ws.wt, kLdt, Off::c2b, st)) return rc;
     } else {
         ConvFwdProb p{}; p.a = a; p.g = kConv2; p.xin_all = ws.a1p; p.z_all = ws.z2; p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, B * PP2, 64, 1, K, st);
@@ -416,7 +417,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     pool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("pool2");
     if (tcm & TC_FC1_FWD) {
-        if (int rc = tc::fc_fwd_3136_128(a, ws.a2, ws.hpre, Off::f1w, 7, st)) return rc;
+        if (int rc = tc::fc_fwd(a, ws.a2, ws.hpre, 3136, 128, Off::f1w, 7, st)) return rc;
     } else {
         LinFwdProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.act_all = ws.a2; p.out_all = ws.hpre;
         simt::launch(p, B, 128, 14, K, st);
@@ -441,7 +442,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     // ---- activation gradients ----
     const int tcm = tc_mask_of(a);
     if (tcm & TC_FC1_DGRAD) {
-        if (int rc = tc::fc_dgrad_3136_128(a, ws.dh, ws.da2, Off::f1w, st)) return rc;
+        if (int rc = tc::fc_dgrad(a, ws.dh, ws.da2, 3136, 128, Off::f1w, st)) return rc;
     } else {
         LinDgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.dout_all = ws.dh; p.dact_all = ws.da2;
         simt::launch(p, B, 3136, 1, K, st);
@@ -450,7 +451,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     unpool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("unpool2");
     if (tcm & TC_CONV2_DGRAD) {
-        if (int rc = tc::conv_dgrad_32_64(a, kConv2, ws.z2, ws.da1p, Off::c2w, st)) return rc;
+        if (int rc = tc::conv_dgrad(a, kConv2, ws.z2, ws.da1p, ws.wt, kLdt, st)) return rc;
     } else {
         ConvDgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.dx_all = ws.da1p; p.woff = Off::c2w;
         simt::launch(p, B * PP2, 32, 1, K, st);
@@ -476,7 +477,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     MARK("head_wgrad");
     if (tcm & TC_FC1_WGRAD) {
         if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.dh, coef, 128);
-        if (int rc = tc::fc_wgrad_3136_128(a, ws.dh, ws.a2, Off::f1w, st)) return rc;
+        if (int rc = tc::fc_wgrad(a, ws.dh, ws.a2, 3136, 128, Off::f1w, st)) return rc;
     } else {
         LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
         p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
@@ -486,7 +487,8 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     if (tcm & TC_CONV2_WGRAD) {
         conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, coef != nullptr);
         if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
-        if (int rc = tc::conv_wgrad_32_64(a, kConv2, ws.a1p, ws.z2, Off::c2w, 16, st)) return rc;
+        FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));
+        if (int rc = tc::conv_wgrad(a, kConv2, ws.a1p, ws.z2, ws.gt, kLdt, st)) return rc;
     } else {
         ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
         p.woff = Off::c2w; p.boff = Off::c2b;
@@ -521,4 +523,14 @@ int forward(const flb_train_args& a, cudaStream_t st) {
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
 int step_launches(const flb_train_args& a) { return a.dp_mode == 1 ? 16 : 12; }
+void tc_tab(const flb_train_args& a, TcConvTab* t) {
+    const int m = tc_mask_of(a);
+    if (!(m & (TC_CONV2_FWD | TC_CONV2_DGRAD | TC_CONV2_WGRAD))) return;
+    SimpleCnnWs ws;
+    simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
+    t->n = 1;
+    t->woff[0] = Off::c2w; t->cin[0] = 32; t->cout[0] = 64; t->toff[0] = 0;
+    t->gt_live[0] = (m & TC_CONV2_WGRAD) ? 1 : 0;
+    t->ldt = kLdt; t->wt = ws.wt; t->gt = ws.gt;
+}
 }  // namespace simplecnn

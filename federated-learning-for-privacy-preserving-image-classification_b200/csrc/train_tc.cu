@@ -8,8 +8,9 @@
 //   fc wgrad    D[Out, In]       = dout[B, Out]^T * act[B, In]                                   both MN-major
 // "px" runs over the zero-padded NHWC grid (train_common.cuh), so a 3x3 tap is a row shift of the TMA box and the
 // out-of-range rows come back as zeros from the TMA unit -- implicit GEMM with no im2col buffer and no halo code.
-// Weights stay in the reference's [Cout][Cin][3][3] layout in HBM; the conv weight operand (73.7 KB for conv2) is
-// permuted into the canonical swizzled layout by the CTA's threads once and stays resident in shared memory.
+// Conv weights are read from a per-client "tap-major" copy Wt[tap][Cout][Cin] (train_common.cuh TcConvTab) that the
+// optimizer kernel keeps in sync with the reference-layout row, so BOTH operands of every GEMM are plain TMA boxes and
+// no CTA spends time permuting weights; conv weight gradients are accumulated in the same layout (Gt).
 #include "tc_gemm.cuh"
 
 namespace tc {
@@ -56,12 +57,16 @@ static int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_
 
 __device__ __forceinline__ int tap_shift(int tap, int Wp) { return (tap / 3 - 1) * Wp + (tap % 3 - 1); }
 
-// ---- conv forward -------------------------------------------------------------------------------------------
+
+template <int N> struct Pow2Cols { static constexpr int value = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : (N <= 256 ? 256 : 512))); };
+
+// ---- conv forward: D[128 px, COUT] = sum_{tap, cin chunk} X[px + shift(tap), 32] * Wt[tap][COUT][32]^T ---------------
 template <int CIN, int COUT>
-struct ConvFwdTC {
-    struct Params { CUtensorMap map_x; flb_train_args a; ConvGeom g; float* z_all; int woff, boff; };
-    static constexpr int CH = CIN / 32, NKB = 9 * CH;
-    static constexpr int STAGES = 4, STAGE_BYTES = 128 * 128, RESIDENT_BYTES = NKB * COUT * 128, TMEM_COLS = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
+struct ConvFwdT {
+    struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff; };
+    static constexpr int CH = CIN / 32, NKB = 9 * CH, A_BYTES = 128 * 128, B_BYTES = COUT * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = COUT > 64 ? 3 : 4, RESIDENT_BYTES = 0;
+    static constexpr int TMEM_COLS = Pow2Cols<COUT>::value, MINB = 2;
     int client, m0, row0;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
@@ -72,25 +77,19 @@ struct ConvFwdTC {
         num_kb = NKB;
         return true;
     }
-    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_x); }
-    __device__ void stage_resident(const Params& p, uint8_t* res, int tid) {
-        const float* w = p.a.W + (long long)client * p.a.ld + p.woff;
-        for (int s = tid; s < COUT * CIN * 9; s += THREADS) {           // coalesced read of [Cout][Cin][9]
-            const int tap = s % 9, ci = (s / 9) % CIN, n = s / (9 * CIN);
-            const int kb = tap * CH + ci / 32;
-            *reinterpret_cast<float*>(res + (size_t)kb * COUT * 128 + sw128_offset(n, ci & 31)) = w[s];
-        }
-    }
+    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_w); }
+    __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int tap = kb / CH, c = kb % CH;
         mbar_expect_tx(bar, STAGE_BYTES);
         tma_load_2d(&p.map_x, stage, bar, c * 32, row0 + m0 + tap_shift(tap, p.g.Wp));
+        tma_load_3d(&p.map_w, stage + A_BYTES, bar, c * 32, tap * COUT, client);
     }
-    __device__ void mma(int kb, uint32_t stage, uint32_t res, uint32_t tmem) {
+    __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(res + kb * COUT * 128 + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + A_BYTES + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -111,12 +110,13 @@ struct ConvFwdTC {
     }
 };
 
-// ---- conv dgrad ---------------------------------------------------------------------------------------------
+// ---- conv dgrad: D[128 px, CIN] = sum_{tap, cout chunk} dZ[px - shift(tap), 32] * Wt[tap][32 cout][CIN] ---------------
 template <int CIN, int COUT>
-struct ConvDgradTC {
-    struct Params { CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* dx_all; int woff; };
-    static constexpr int CH = COUT / 32, NKB = 9 * CH;
-    static constexpr int STAGES = 4, STAGE_BYTES = 128 * 128, RESIDENT_BYTES = NKB * CIN * 128, TMEM_COLS = CIN <= 32 ? 32 : (CIN <= 64 ? 64 : 128);
+struct ConvDgradT {
+    struct Params { CUtensorMap map_dz; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* dx_all; };
+    static constexpr int CH = COUT / 32, NKB = 9 * CH, NCH = CIN / 32, A_BYTES = 128 * 128, B_BYTES = NCH * 4096;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = CIN > 64 ? 3 : 4, RESIDENT_BYTES = 0;
+    static constexpr int TMEM_COLS = Pow2Cols<CIN>::value, MINB = 2;
     int client, m0, row0;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
@@ -127,25 +127,21 @@ struct ConvDgradTC {
         num_kb = NKB;
         return true;
     }
-    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_dz); }
-    __device__ void stage_resident(const Params& p, uint8_t* res, int tid) {
-        const float* w = p.a.W + (long long)client * p.a.ld + p.woff;
-        for (int s = tid; s < COUT * CIN * 9; s += THREADS) {
-            const int tap = s % 9, ci = (s / 9) % CIN, co = s / (9 * CIN);
-            const int kb = tap * CH + co / 32;                              // B tile rows = cin (N), k = cout
-            *reinterpret_cast<float*>(res + (size_t)kb * CIN * 128 + sw128_offset(ci, co & 31)) = w[s];
-        }
-    }
+    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_dz); tma_prefetch_desc(&p.map_w); }
+    __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int tap = kb / CH, c = kb % CH;
         mbar_expect_tx(bar, STAGE_BYTES);
         tma_load_2d(&p.map_dz, stage, bar, c * 32, row0 + m0 - tap_shift(tap, p.g.Wp));
+#pragma unroll
+        for (int nc = 0; nc < NCH; ++nc)                        // B is MN-major: rows = cout (K), 32-wide cin (N) chunks
+            tma_load_3d(&p.map_w, stage + A_BYTES + nc * 4096, bar, nc * 32, tap * COUT + c * 32, client);
     }
-    __device__ void mma(int kb, uint32_t stage, uint32_t res, uint32_t tmem) {
-        constexpr uint32_t id = idesc_tf32(128, CIN, false, false);
+    __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
+        constexpr uint32_t id = idesc_tf32(128, CIN, false, true);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(res + kb * CIN * 128 + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -163,32 +159,38 @@ struct ConvDgradTC {
     }
 };
 
-// ---- conv wgrad ---------------------------------------------------------------------------------------------
-template <int CIN, int COUT>
-struct ConvWgradTC {
-    struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; int woff; int kb_per_split; };
-    static constexpr int ACH = 9 * CIN / 32, MT = (ACH * 32 + 127) / 128, ASLOTS = MT * 4, BCH = COUT / 32;
-    static constexpr int A_BYTES = ASLOTS * 4096, STAGE_BYTES = A_BYTES + BCH * 4096;
-    static constexpr int STAGES = 3, RESIDENT_BYTES = 0, TMEM_COLS = MT * COUT <= 64 ? 64 : (MT * COUT <= 128 ? 128 : (MT * COUT <= 256 ? 256 : 512));
-    int client, row0, kb0;
+// ---- conv wgrad: Gt[tap][co][ci] += sum_px X[px + shift(tap)][ci] * dZ[px][co] ----------------------------------------
+// M = (tap, ci) in 32-row chunks, N = co, K = pixels (split over blockIdx.x); blockIdx.z selects MTC of the M tiles.
+template <int CIN, int COUT, int MTC>
+struct ConvWgradT {
+    struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* gt_all; long long ldt; int kb_per_split; };
+    static constexpr int CCH = CIN / 32, ACH = 9 * CCH, BCH = COUT / 32;
+    static constexpr int A_BYTES = MTC * 4 * 4096, STAGE_BYTES = A_BYTES + BCH * 4096;
+    static constexpr int STAGES = STAGE_BYTES * 3 <= 200 * 1024 ? 3 : 2, RESIDENT_BYTES = 0;
+    static constexpr int TMEM_COLS = Pow2Cols<MTC * COUT>::value, MINB = 1;
+    static_assert(MTC * COUT <= 512, "accumulators must fit TMEM");
+    int client, row0, kb0, chunk0, nch, total_rows;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
         const int bsz = flb_bsz(p.a, client);
-        const int total = bsz * p.g.PP() / 32;
+        total_rows = bsz * p.g.PP();
+        const int total = (total_rows + 31) / 32;
         kb0 = blockIdx.x * p.kb_per_split;
         if (kb0 >= total) return false;
         num_kb = min(p.kb_per_split, total - kb0);
         row0 = client * p.a.B * p.g.PP();
-        return true;
+        chunk0 = blockIdx.z * MTC * 4;
+        nch = min(MTC * 4, ACH - chunk0);
+        return nch > 0;
     }
     __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_dz); }
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int px = row0 + (kb0 + kb) * 32;
-        mbar_expect_tx(bar, (ACH + BCH) * 4096);
+        mbar_expect_tx(bar, (nch + BCH) * 4096);
 #pragma unroll 1
-        for (int ch = 0; ch < ACH; ++ch) {                       // chunk = (tap, 32-channel slice of Cin)
-            const int tap = ch / (CIN / 32), c = ch % (CIN / 32);
+        for (int ch = 0; ch < nch; ++ch) {                       // chunk = (tap, 32-channel slice of Cin)
+            const int gc = chunk0 + ch, tap = gc / CCH, c = gc % CCH;
             tma_load_2d(&p.map_x, stage + ch * 4096, bar, c * 32, px + tap_shift(tap, p.g.Wp));
         }
 #pragma unroll
@@ -196,42 +198,44 @@ struct ConvWgradTC {
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, true, true);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+        const int ksteps = min(4, (total_rows - (kb0 + kb) * 32) >> 3);      // rows per image are a multiple of 8
+        const int mtiles = (nch + 3) >> 2;
+        for (int k = 0; k < ksteps; ++k)
+            for (int mt = 0; mt < mtiles; ++mt)
                 mma_tf32(tmem + mt * COUT, smem_desc_mn(stage + mt * 4 * 4096 + k * 1024, 4096, 512),
                          smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
-        float* gw = p.a.G + (long long)client * p.a.ld + p.woff;
+        float* gt = p.gt_all + (long long)client * p.ldt;
+        const int mtiles = (nch + 3) >> 2;
 #pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-            const int row = mt * 128 + quarter * 32 + lane;          // row = chunk * 32 + (cin within the slice)
-            const int ch = row >> 5, tap = ch / (CIN / 32), ci = (ch % (CIN / 32)) * 32 + (row & 31);
-            const bool ok = ch < ACH;
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int row = mt * 128 + quarter * 32 + lane;          // row = local chunk * 32 + (cin within the slice)
+            const int ch = row >> 5, gc = chunk0 + ch, tap = gc / CCH, ci = (gc % CCH) * 32 + (row & 31);
+            const bool ok = ch < nch;
 #pragma unroll 1
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + mt * COUT + c0, v);
                 if (ok) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) atomicAdd(&gw[((c0 + i) * CIN + ci) * 9 + tap], v[i]);
+                    for (int i = 0; i < 32; ++i) atomicAdd(&gt[((long long)tap * COUT + c0 + i) * CIN + ci], v[i]);   // lanes = consecutive ci
                 }
             }
         }
     }
 };
 
-// ---- linear forward (split-K) --------------------------------------------------------------------------------
+// ---- linear forward (swap-AB, split-K): D[128 out, B] += W[out, k] * act[b, k] --------------------------------------
 template <int IN, int OUT>
-struct FcFwdTC {
+struct FcFwdT {
     struct Params { CUtensorMap map_w; CUtensorMap map_act; flb_train_args a; float* out_all; int kb_per_split; };
-    static_assert(OUT == 128, "one 128-row accumulator tile");
-    static constexpr int STAGES = 6, STAGE_BYTES = 128 * 128 + 32 * 128, RESIDENT_BYTES = 0, TMEM_COLS = 32;
-    int client, kb0, bsz;
+    static_assert(OUT % 128 == 0, "whole 128-row accumulator tiles");
+    static constexpr int STAGES = 6, STAGE_BYTES = 128 * 128 + 32 * 128, RESIDENT_BYTES = 0, TMEM_COLS = 32, MINB = 1;
+    int client, kb0, bsz, mt;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
+        mt = blockIdx.z;
         bsz = flb_bsz(p.a, client);
         if (bsz == 0) return false;
         constexpr int total = (IN + 31) / 32;
@@ -245,7 +249,7 @@ struct FcFwdTC {
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int k0 = (kb0 + kb) * 32;
         mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_3d(&p.map_w, stage, bar, k0, 0, client);
+        tma_load_3d(&p.map_w, stage, bar, k0, mt * 128, client);
         tma_load_2d(&p.map_act, stage + 128 * 128, bar, k0, client * p.a.B);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
@@ -255,7 +259,7 @@ struct FcFwdTC {
             mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + 128 * 128 + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
-        const int j = quarter * 32 + lane;
+        const int j = mt * 128 + quarter * 32 + lane;
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16), v);
         float* out = p.out_all + (long long)client * p.a.B * OUT + j;
@@ -265,11 +269,11 @@ struct FcFwdTC {
     }
 };
 
-// ---- linear dgrad ---------------------------------------------------------------------------------------------
+// ---- linear dgrad: D[128 in, B] = sum_out W[out, in] * dout[b, out] ---------------------------------------------------
 template <int IN, int OUT>
-struct FcDgradTC {
+struct FcDgradT {
     struct Params { CUtensorMap map_w; CUtensorMap map_dout; flb_train_args a; float* dact_all; };
-    static constexpr int STAGES = 4, STAGE_BYTES = 4 * 4096 + 4096, RESIDENT_BYTES = 0, TMEM_COLS = 32;
+    static constexpr int STAGES = 4, STAGE_BYTES = 4 * 4096 + 4096, RESIDENT_BYTES = 0, TMEM_COLS = 32, MINB = 2;
     int client, m0, bsz;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
@@ -306,18 +310,19 @@ struct FcDgradTC {
     }
 };
 
-// ---- linear wgrad ---------------------------------------------------------------------------------------------
+// ---- linear wgrad: D[128 out, 256 in] = sum_b dout[b, out] * act[b, in] ------------------------------------------------
 template <int IN, int OUT>
-struct FcWgradTC {
+struct FcWgradT {
     struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
-    static_assert(OUT == 128, "one 128-row accumulator tile");
-    static constexpr int STAGES = 1, STAGE_BYTES = 4 * 4096 + 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 256;
-    int client, n0, ksteps;
+    static_assert(OUT % 128 == 0, "whole 128-row accumulator tiles");
+    static constexpr int STAGES = 1, STAGE_BYTES = 4 * 4096 + 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 256, MINB = 1;
+    int client, n0, ksteps, mt;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
+        mt = blockIdx.z;
         if (flb_bsz(p.a, client) == 0) return false;
         n0 = blockIdx.x * 256;
-        ksteps = p.a.B / 8;              // rows bsz..B-1 of dout are zero (head kernel); rows >= B belong to the next client
+        ksteps = p.a.B / 8;              // rows bsz..B-1 of dout are zero (producer kernels); rows >= B belong to the next client
         num_kb = 1;
         return true;
     }
@@ -326,7 +331,7 @@ struct FcWgradTC {
     __device__ void load(const Params& p, int, uint8_t* stage, uint64_t* bar) {
         mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(&p.map_dout, stage + c * 4096, bar, 32 * c, client * p.a.B);
+        for (int c = 0; c < 4; ++c) tma_load_2d(&p.map_dout, stage + c * 4096, bar, mt * 128 + 32 * c, client * p.a.B);
 #pragma unroll
         for (int c = 0; c < 8; ++c) tma_load_2d(&p.map_act, stage + 4 * 4096 + c * 4096, bar, n0 + 32 * c, client * p.a.B);
     }
@@ -336,7 +341,7 @@ struct FcWgradTC {
             mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
-        const int j = quarter * 32 + lane;
+        const int j = mt * 128 + quarter * 32 + lane;
         float* g = p.a.G + (long long)client * p.a.ld + p.woff + (long long)j * IN;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
@@ -354,6 +359,7 @@ struct FcWgradTC {
 template <class T>
 static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = (size_t)T::STAGES * T::STAGE_BYTES + T::RESIDENT_BYTES + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
         FLB_CUDA(cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -363,32 +369,75 @@ static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
     return FLB_OK;
 }
 
-// ---- host entry points used by the step orchestrator (train_simplecnn.cu) ------------------------------------------
-int conv_fwd_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, int woff, int boff, cudaStream_t st) {
-    using T = ConvFwdTC<32, 64>;
-    T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 128)) return rc;
-    p.a = a; p.g = g; p.z_all = z; p.woff = woff; p.boff = boff;
-    return launch<T>(p, dim3((a.B * g.PP() + 127) / 128, a.K), st);
+// tap-major conv weights of all clients as a 3-D tensor {Cin, 9*Cout, K}; box_rows x 32 boxes
+static int make_wt_map(CUtensorMap* m, const float* wt, long long ldt, int cin, int cout, int K, uint32_t box_rows, bool mn_major) {
+    const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)9 * cout, (uint64_t)K};
+    const uint64_t strides[2] = {(uint64_t)cin * sizeof(float), (uint64_t)ldt * sizeof(float)};
+    const uint32_t box[3] = {32, box_rows, 1};
+    return make_map(m, wt, 3, dims, strides, box, mn_major);
 }
 
-int conv_dgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, int woff, cudaStream_t st) {
-    using T = ConvDgradTC<32, 64>;
-    T::Params p;
-    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 128)) return rc;
-    p.a = a; p.g = g; p.dx_all = dx; p.woff = woff;
+template <int CIN, int COUT>
+static int conv_fwd_t(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st) {
+    using T = ConvFwdT<CIN, COUT>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 128)) return rc;
+    if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, COUT, false)) return rc;
+    p.a = a; p.g = g; p.z_all = z; p.boff = boff;
     return launch<T>(p, dim3((a.B * g.PP() + 127) / 128, a.K), st);
 }
-
-int conv_wgrad_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int woff, int splits, cudaStream_t st) {
-    using T = ConvWgradTC<32, 64>;
-    T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32, true)) return rc;
-    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32, true)) return rc;
-    p.a = a; p.g = g; p.woff = woff;
-    const int total = a.B * g.PP() / 32;
+template <int CIN, int COUT>
+static int conv_dgrad_t(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
+    using T = ConvDgradT<CIN, COUT>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 128)) return rc;
+    if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, 32, true)) return rc;
+    p.a = a; p.g = g; p.dx_all = dx;
+    return launch<T>(p, dim3((a.B * g.PP() + 127) / 128, a.K), st);
+}
+template <int CIN, int COUT, int MTC>
+static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
+    using T = ConvWgradT<CIN, COUT, MTC>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 32, true)) return rc;
+    p.a = a; p.g = g; p.gt_all = gt; p.ldt = ldt;
+    constexpr int groups = (T::ACH + MTC * 4 - 1) / (MTC * 4);
+    const int total = (a.B * g.PP() + 31) / 32;
+    int splits = flb_num_sms() / (a.K * groups);             // one wave of CTAs over the GPU
+    splits = splits < 1 ? 1 : (splits > total ? total : splits);
     p.kb_per_split = (total + splits - 1) / splits;
-    return launch<T>(p, dim3(splits, a.K), st);
+    splits = (total + p.kb_per_split - 1) / p.kb_per_split;
+    return launch<T>(p, dim3(splits, a.K, groups), st);
+}
+
+// ---- host entry points used by the step orchestrators ---------------------------------------------------------------------
+bool conv_supported(int cin, int cout) {
+    return (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && cout == 128);
+}
+#define FLB_CONV_DISPATCH(FN, ...)                                                            \
+    if (g.Cin == 32 && g.Cout == 32) return FN<32, 32>(__VA_ARGS__);                          \
+    if (g.Cin == 32 && g.Cout == 64) return FN<32, 64>(__VA_ARGS__);                          \
+    if (g.Cin == 64 && g.Cout == 64) return FN<64, 64>(__VA_ARGS__);                          \
+    if (g.Cin == 64 && g.Cout == 128) return FN<64, 128>(__VA_ARGS__);                        \
+    if (g.Cin == 128 && g.Cout == 128) return FN<128, 128>(__VA_ARGS__);                      \
+    flb_set_error("tensor-core conv: unsupported channels %d -> %d", g.Cin, g.Cout);          \
+    return FLB_ERR_UNSUPPORTED;
+
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st) {
+    FLB_CONV_DISPATCH(conv_fwd_t, a, g, xin, z, wt, ldt, boff, st)
+}
+int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
+    FLB_CONV_DISPATCH(conv_dgrad_t, a, g, dz, dx, wt, ldt, st)
+}
+int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
+    if (g.Cin == 32 && g.Cout == 32) return conv_wgrad_t<32, 32, 3>(a, g, xin, dz, gt, ldt, st);
+    if (g.Cin == 32 && g.Cout == 64) return conv_wgrad_t<32, 64, 3>(a, g, xin, dz, gt, ldt, st);
+    if (g.Cin == 64 && g.Cout == 64) return conv_wgrad_t<64, 64, 5>(a, g, xin, dz, gt, ldt, st);
+    if (g.Cin == 64 && g.Cout == 128) return conv_wgrad_t<64, 128, 3>(a, g, xin, dz, gt, ldt, st);
+    if (g.Cin == 128 && g.Cout == 128) return conv_wgrad_t<128, 128, 3>(a, g, xin, dz, gt, ldt, st);
+    flb_set_error("tensor-core conv wgrad: unsupported channels %d -> %d", g.Cin, g.Cout);
+    return FLB_ERR_UNSUPPORTED;
 }
 
 static int make_w_map(CUtensorMap* m, const flb_train_args& a, int woff, int in, int out, uint32_t box_rows, bool mn_major = false) {
@@ -398,32 +447,51 @@ static int make_w_map(CUtensorMap* m, const flb_train_args& a, int woff, int in,
     return make_map(m, a.W + woff, 3, dims, strides, box, mn_major);
 }
 
-int fc_fwd_3136_128(const flb_train_args& a, const float* act, float* out, int woff, int splits, cudaStream_t st) {
-    using T = FcFwdTC<3136, 128>;
-    T::Params p;
-    if (int rc = make_w_map(&p.map_w, a, woff, 3136, 128, 128)) return rc;
-    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, 3136, 32)) return rc;
+template <int IN, int OUT>
+static int fc_fwd_t(const flb_train_args& a, const float* act, float* out, int woff, int splits, cudaStream_t st) {
+    using T = FcFwdT<IN, OUT>;
+    typename T::Params p;
+    if (int rc = make_w_map(&p.map_w, a, woff, IN, OUT, 128)) return rc;
+    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32)) return rc;
     p.a = a; p.out_all = out;
-    p.kb_per_split = (98 + splits - 1) / splits;
-    return launch<T>(p, dim3(splits, a.K), st);
+    constexpr int total = (IN + 31) / 32;
+    p.kb_per_split = (total + splits - 1) / splits;
+    return launch<T>(p, dim3((total + p.kb_per_split - 1) / p.kb_per_split, a.K, OUT / 128), st);
 }
-
-int fc_dgrad_3136_128(const flb_train_args& a, const float* dout, float* dact, int woff, cudaStream_t st) {
-    using T = FcDgradTC<3136, 128>;
-    T::Params p;
-    if (int rc = make_w_map(&p.map_w, a, woff, 3136, 128, 32, true)) return rc;
-    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32)) return rc;
+template <int IN, int OUT>
+static int fc_dgrad_t(const flb_train_args& a, const float* dout, float* dact, int woff, cudaStream_t st) {
+    using T = FcDgradT<IN, OUT>;
+    typename T::Params p;
+    if (int rc = make_w_map(&p.map_w, a, woff, IN, OUT, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, OUT, 32)) return rc;
     p.a = a; p.dact_all = dact;
-    return launch<T>(p, dim3((3136 + 127) / 128, a.K), st);
+    return launch<T>(p, dim3((IN + 127) / 128, a.K), st);
+}
+template <int IN, int OUT>
+static int fc_wgrad_t(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
+    using T = FcWgradT<IN, OUT>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, OUT, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32, true)) return rc;
+    p.a = a; p.woff = woff;
+    return launch<T>(p, dim3((IN + 255) / 256, a.K, OUT / 128), st);
 }
 
-int fc_wgrad_3136_128(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
-    using T = FcWgradTC<3136, 128>;
-    T::Params p;
-    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32, true)) return rc;
-    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, 3136, 32, true)) return rc;
-    p.a = a; p.woff = woff;
-    return launch<T>(p, dim3((3136 + 255) / 256, a.K), st);
+#define FLB_FC_DISPATCH(FN, ...)                                                              \
+    if (in == 3136 && out == 128) return FN<3136, 128>(__VA_ARGS__);                          \
+    if (in == 2048 && out == 512) return FN<2048, 512>(__VA_ARGS__);                          \
+    if (in == 512 && out == 256) return FN<512, 256>(__VA_ARGS__);                            \
+    flb_set_error("tensor-core linear: unsupported shape %d -> %d", in, out);                 \
+    return FLB_ERR_UNSUPPORTED;
+
+int fc_fwd(const flb_train_args& a, const float* act, float* outp, int in, int out, int woff, int splits, cudaStream_t st) {
+    FLB_FC_DISPATCH(fc_fwd_t, a, act, outp, woff, splits, st)
+}
+int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int out, int woff, cudaStream_t st) {
+    FLB_FC_DISPATCH(fc_dgrad_t, a, dout, dact, woff, st)
+}
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int out, int woff, cudaStream_t st) {
+    FLB_FC_DISPATCH(fc_wgrad_t, a, dout, act, woff, st)
 }
 
 }  // namespace tc
