@@ -16,6 +16,15 @@
 #include "philox.cuh"
 #include <string.h>
 
+namespace tc {
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st);
+int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
+int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
+int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
+int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
+}  // namespace tc
+
 namespace {
 
 constexpr int NCONV = 6;
@@ -25,13 +34,16 @@ constexpr int DROP_PER_SAMPLE = 8192 + 4096 + 2048 + 512 + 256;     // injected 
 
 struct Net {
     int cin[NCONV], cout[NCONV], cw[NCONV], cb[NCONV], bw[NCONV], bb[NCONV], coff[NCONV];
-    int f1w, f1b, f2w, f2b, f3w, f3b, P;
+    int toff[NCONV];                 // tap-major copy (layers 2..6; conv1 with Cin = 3 stays on CUDA cores)
+    int f1w, f1b, f2w, f2b, f3w, f3b, P, ldt;
 };
 constexpr Net make_net() {
     Net n{};
     const int ci[NCONV] = {3, 32, 32, 64, 64, 128}, co[NCONV] = {32, 32, 64, 64, 128, 128};
-    int off = 0, c = 0;
+    int off = 0, c = 0, t = 0;
     for (int i = 0; i < NCONV; ++i) {
+        n.toff[i] = t;
+        if (i > 0) t += co[i] * ci[i] * 9;
         n.cin[i] = ci[i]; n.cout[i] = co[i];
         n.cw[i] = off; off += co[i] * ci[i] * 9;
         n.cb[i] = off; off += co[i];
@@ -46,6 +58,7 @@ constexpr Net make_net() {
     n.f3w = off; off += 10 * 256;
     n.f3b = off; off += 10;
     n.P = off;
+    n.ldt = t;
     return n;
 }
 constexpr Net kNet = make_net();
@@ -58,6 +71,7 @@ constexpr ConvGeom geom(int level, int cin, int cout) {
                       : ConvGeom{cin, cout, 8, 8, 10, 9, 88};
 }
 constexpr int PP32 = 1096, PP16 = 296, PP8 = 88;
+constexpr int kNetLdt = kNet.ldt;
 
 struct CifarWs {
     float *z1, *y1, *z2, *p1;          // grid 32: conv1 out, bn1+relu, conv2 out; grid 16: pooled+dropped (conv3 input)
@@ -67,6 +81,7 @@ struct CifarWs {
     float *hpre1, *h1, *m1, *hpre2, *h, *logits, *dlog, *dh2, *dh1, *da;
     float *d32a, *d32b, *d16p, *d16a, *d16b, *d8p, *d8a, *d8b;
     double* acc;                       // [K][4][448]
+    float *wt, *gt;                    // [K][ldt] tap-major conv weights / weight gradients (tensor-core path)
 };
 
 size_t carve(void* base, int K, int B, CifarWs* ws) {
@@ -93,6 +108,8 @@ size_t carve(void* base, int K, int B, CifarWs* ws) {
     CARVE(d16p, float, KB * PP16 * 32); CARVE(d16a, float, KB * PP16 * 64); CARVE(d16b, float, KB * PP16 * 64);
     CARVE(d8p, float, KB * PP8 * 64); CARVE(d8a, float, KB * PP8 * 128); CARVE(d8b, float, KB * PP8 * 128);
     CARVE(acc, double, (size_t)K * 4 * BN_CH);
+    CARVE(wt, float, (size_t)K * kNetLdt);
+    CARVE(gt, float, (size_t)K * kNetLdt);
 #undef CARVE
     return off;
 }
@@ -356,7 +373,8 @@ __global__ void __launch_bounds__(256) unpool_kernel(flb_train_args a, ConvGeom 
 // y_all is given.  CTA (0, k) writes dgamma / dbeta into G.
 template <int C>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* y_all,
-                                                           float* dy_all, const double* acc, int coff, int gwoff, int gboff) {
+                                                           float* dy_all, const double* acc, int coff, int gwoff, int gboff,
+                                                           int conv_boff) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
@@ -383,6 +401,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
     const int PP = g.PP(), rows = bsz * PP;
     const long long base = (long long)k * a.B * PP * C;
     const long long total = (long long)rows * C;
+    float bsum = 0.f;                         // this thread always sees the same channel (256 % C == 0)
     for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
         const int r = (int)(e / C), c = (int)(e % C);
         float o = 0.f;
@@ -393,6 +412,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
             o = s_c0[c] * (gv - s_c1[c] - xhat * s_c2[c]);
         }
         dy_all[base + e] = o;
+        bsum += o;
+    }
+    if (conv_boff >= 0) {                     // conv bias gradient = column sums of dz (tensor-core path; the fp32 wgrad
+        __shared__ float red[256];            // GEMM carries it as an extra column).  Exactly zero in exact arithmetic.
+        red[tid] = bsum;
+        __syncthreads();
+        if (tid < C) {
+            for (int i = 1; i < 256 / C; ++i) bsum += red[tid + i * C];
+            atomicAdd(&a.G[(long long)k * a.ld + conv_boff + tid], bsum);
+        }
     }
 }
 
@@ -548,7 +577,8 @@ template <int C>
 void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, const float* y, float* dy, double* acc, int layer, cudaStream_t st) {
     const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
     bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, y, acc, kNet.coff[layer]);
-    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
+    const int conv_boff = (a.precision == 1 && layer > 0) ? kNet.cb[layer] : -1;
+    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
 template <int C>
 void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float* y, const double* acc, int layer, cudaStream_t st) {
@@ -556,30 +586,44 @@ void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float*
     bn_relu_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
 }
 
-void conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, int layer, cudaStream_t st) {
+struct Ctx { const flb_train_args& a; const CifarWs& ws; cudaStream_t st; int rc = FLB_OK; bool tc; bool tc_wgrad; };
+
+void conv_fwd(Ctx& c, const ConvGeom& g, const float* xin, float* z, int layer) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc) { if (int rc = tc::conv_fwd(a, g, xin, z, c.ws.wt + kNet.toff[layer], kNet.ldt, kNet.cb[layer], st)) c.rc = rc; return; }
     ConvFwdProb p{}; p.a = a; p.g = g; p.xin_all = xin; p.z_all = z; p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
     simt::launch(p, a.B * g.PP(), g.Cout, 1, a.K, st);
 }
-void conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, int layer, cudaStream_t st) {
+void conv_dgrad(Ctx& c, const ConvGeom& g, const float* dz, float* dx, int layer) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc) { if (int rc = tc::conv_dgrad(a, g, dz, dx, c.ws.wt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
     ConvDgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.dx_all = dx; p.woff = kNet.cw[layer];
     simt::launch(p, a.B * g.PP(), g.Cin, 1, a.K, st);
 }
-void conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, int layer, cudaStream_t st) {
+void conv_wgrad(Ctx& c, const ConvGeom& g, const float* xin, const float* dz, int layer) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc) { if (int rc = tc::conv_wgrad(a, g, xin, dz, c.ws.gt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
     ConvWgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.xin_all = xin; p.coef_all = nullptr;
     p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
     const int tiles = ((g.Cout + 63) / 64) * ((9 * g.Cin + 1 + 63) / 64);
     const int splits = max(1, min(64, flb_num_sms() * 2 / (tiles * a.K)));
     simt::launch(p, g.Cout, 9 * g.Cin + 1, splits, a.K, st);
 }
-void lin_fwd(const flb_train_args& a, const float* act, float* out, int In, int Out, int woff, int splits, cudaStream_t st) {
+void lin_fwd(Ctx& c, const float* act, float* out, int In, int Out, int woff, int splits) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc) { if (int rc = tc::fc_fwd(a, act, out, In, Out, woff, splits, st)) c.rc = rc; return; }
     LinFwdProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.act_all = act; p.out_all = out;
     simt::launch(p, a.B, Out, splits, a.K, st);
 }
-void lin_dgrad(const flb_train_args& a, const float* dout, float* dact, int In, int Out, int woff, cudaStream_t st) {
+void lin_dgrad(Ctx& c, const float* dout, float* dact, int In, int Out, int woff) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc) { if (int rc = tc::fc_dgrad(a, dout, dact, In, Out, woff, st)) c.rc = rc; return; }
     LinDgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.dout_all = dout; p.dact_all = dact;
     simt::launch(p, a.B, In, 1, a.K, st);
 }
-void lin_wgrad(const flb_train_args& a, const float* dout, const float* act, int In, int Out, int woff, cudaStream_t st) {
+void lin_wgrad(Ctx& c, const float* dout, const float* act, int In, int Out, int woff) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (c.tc_wgrad) { if (int rc = tc::fc_wgrad(a, dout, act, In, Out, woff, st)) c.rc = rc; return; }
     LinWgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.boff = 0; p.dout_all = dout; p.act_all = act; p.coef_all = nullptr;
     simt::launch(p, Out, In, 1, a.K, st);
 }
@@ -596,6 +640,7 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     FLB_CUDA(cudaMemsetAsync(ws.hpre2, 0, sizeof(float) * KB * 256, st));
     MARK("begin");
     const bool stats = !a.eval_mode;
+    Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
     {
         Conv1FwdProb p{}; p.a = a; p.g = G1; p.z_all = ws.z1; p.woff = kNet.cw[0]; p.boff = kNet.cb[0];
         simt::launch(p, B * PP32, 32, 1, K, st);
@@ -604,35 +649,35 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     if (stats) bn_stats<32>(a, G1, ws.z1, ws.acc, kNet.coff[0], st);
     bn_apply<32>(a, G1, ws.z1, ws.y1, ws.acc, 0, st);
     MARK("bn1");
-    conv_fwd(a, G2, ws.y1, ws.z2, 1, st);
+    conv_fwd(cx, G2, ws.y1, ws.z2, 1);
     MARK("conv2_fwd");
     if (stats) bn_stats<32>(a, G2, ws.z2, ws.acc, kNet.coff[1], st);
     bn_relu_pool_drop_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.z2, ws.p1, ws.i1, ws.acc, kNet.coff[1], kNet.bw[1], kNet.bb[1], 0, 0);
     MARK("bn2_pool");
-    conv_fwd(a, G3, ws.p1, ws.z3, 2, st);
+    conv_fwd(cx, G3, ws.p1, ws.z3, 2);
     MARK("conv3_fwd");
     if (stats) bn_stats<64>(a, G3, ws.z3, ws.acc, kNet.coff[2], st);
     bn_apply<64>(a, G3, ws.z3, ws.y3, ws.acc, 2, st);
     MARK("bn3");
-    conv_fwd(a, G4, ws.y3, ws.z4, 3, st);
+    conv_fwd(cx, G4, ws.y3, ws.z4, 3);
     MARK("conv4_fwd");
     if (stats) bn_stats<64>(a, G4, ws.z4, ws.acc, kNet.coff[3], st);
     bn_relu_pool_drop_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.z4, ws.p2, ws.i2, ws.acc, kNet.coff[3], kNet.bw[3], kNet.bb[3], 1, 8192);
     MARK("bn4_pool");
-    conv_fwd(a, G5, ws.p2, ws.z5, 4, st);
+    conv_fwd(cx, G5, ws.p2, ws.z5, 4);
     MARK("conv5_fwd");
     if (stats) bn_stats<128>(a, G5, ws.z5, ws.acc, kNet.coff[4], st);
     bn_apply<128>(a, G5, ws.z5, ws.y5, ws.acc, 4, st);
     MARK("bn5");
-    conv_fwd(a, G6, ws.y5, ws.z6, 5, st);
+    conv_fwd(cx, G6, ws.y5, ws.z6, 5);
     MARK("conv6_fwd");
     if (stats) bn_stats<128>(a, G6, ws.z6, ws.acc, kNet.coff[5], st);
     bn_relu_pool_drop_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.z6, ws.a, ws.i3, ws.acc, kNet.coff[5], kNet.bw[5], kNet.bb[5], 2, 8192 + 4096);
     MARK("bn6_pool");
-    lin_fwd(a, ws.a, ws.hpre1, 2048, 512, kNet.f1w, 8, st);
+    lin_fwd(cx, ws.a, ws.hpre1, 2048, 512, kNet.f1w, 8);
     MARK("fc1_fwd");
     fc_bias_relu_drop_kernel<<<per_sample, 256, 0, st>>>(a, ws.hpre1, ws.h1, ws.m1, 512, kNet.f1b, 3, 8192 + 4096 + 2048);
-    lin_fwd(a, ws.h1, ws.hpre2, 512, 256, kNet.f2w, 4, st);
+    lin_fwd(cx, ws.h1, ws.hpre2, 512, 256, kNet.f2w, 4);
     MARK("fc2_fwd");
     static bool configured = false;
     if (!configured) {
@@ -641,6 +686,7 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     }
     head_fwd_bwd_kernel<<<K, 256, kHeadSmem, st>>>(a, ws);
     MARK("head_fwd_bwd");
+    if (cx.rc) return cx.rc;
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -653,48 +699,50 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     // gradients accumulated with atomics (conv weights / biases) start from zero; everything else is stored
     FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, kNet.f1w * sizeof(float), K, st));
     if (int rc = forward_impl(a, ws, st)) return rc;
+    Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
+    if (cx.tc) FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kNet.ldt, st));
 
     head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws);
-    lin_wgrad(a, ws.dh2, ws.h1, 512, 256, kNet.f2w, st);
-    lin_dgrad(a, ws.dh2, ws.dh1, 512, 256, kNet.f2w, st);
+    lin_wgrad(cx, ws.dh2, ws.h1, 512, 256, kNet.f2w);
+    lin_dgrad(cx, ws.dh2, ws.dh1, 512, 256, kNet.f2w);
     fc1_mask_bias_kernel<<<K, 512, 0, st>>>(a, ws);
     MARK("fc23_bwd");
-    lin_wgrad(a, ws.dh1, ws.a, 2048, 512, kNet.f1w, st);
-    lin_dgrad(a, ws.dh1, ws.da, 2048, 512, kNet.f1w, st);
+    lin_wgrad(cx, ws.dh1, ws.a, 2048, 512, kNet.f1w);
+    lin_dgrad(cx, ws.dh1, ws.da, 2048, 512, kNet.f1w);
     MARK("fc1_bwd");
 
     // block 3 (8x8, 128 channels)
     unpool_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.da, ws.a, ws.i3, ws.d8a);
     bn_bwd<128>(a, G6, ws.z6, nullptr, ws.d8a, ws.acc, 5, st);
     MARK("bn6_bwd");
-    conv_wgrad(a, G6, ws.y5, ws.d8a, 5, st);
-    conv_dgrad(a, G6, ws.d8a, ws.d8b, 5, st);
+    conv_wgrad(cx, G6, ws.y5, ws.d8a, 5);
+    conv_dgrad(cx, G6, ws.d8a, ws.d8b, 5);
     MARK("conv6_bwd");
     bn_bwd<128>(a, G5, ws.z5, ws.y5, ws.d8b, ws.acc, 4, st);
     MARK("bn5_bwd");
-    conv_wgrad(a, G5, ws.p2, ws.d8b, 4, st);
-    conv_dgrad(a, G5, ws.d8b, ws.d8p, 4, st);
+    conv_wgrad(cx, G5, ws.p2, ws.d8b, 4);
+    conv_dgrad(cx, G5, ws.d8b, ws.d8p, 4);
     MARK("conv5_bwd");
 
     // block 2 (16x16, 64 channels)
     unpool_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.d16a);
     bn_bwd<64>(a, G4, ws.z4, nullptr, ws.d16a, ws.acc, 3, st);
     MARK("bn4_bwd");
-    conv_wgrad(a, G4, ws.y3, ws.d16a, 3, st);
-    conv_dgrad(a, G4, ws.d16a, ws.d16b, 3, st);
+    conv_wgrad(cx, G4, ws.y3, ws.d16a, 3);
+    conv_dgrad(cx, G4, ws.d16a, ws.d16b, 3);
     MARK("conv4_bwd");
     bn_bwd<64>(a, G3, ws.z3, ws.y3, ws.d16b, ws.acc, 2, st);
     MARK("bn3_bwd");
-    conv_wgrad(a, G3, ws.p1, ws.d16b, 2, st);
-    conv_dgrad(a, G3, ws.d16b, ws.d16p, 2, st);
+    conv_wgrad(cx, G3, ws.p1, ws.d16b, 2);
+    conv_dgrad(cx, G3, ws.d16b, ws.d16p, 2);
     MARK("conv3_bwd");
 
     // block 1 (32x32, 32 channels)
     unpool_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.d32a);
     bn_bwd<32>(a, G2, ws.z2, nullptr, ws.d32a, ws.acc, 1, st);
     MARK("bn2_bwd");
-    conv_wgrad(a, G2, ws.y1, ws.d32a, 1, st);
-    conv_dgrad(a, G2, ws.d32a, ws.d32b, 1, st);
+    conv_wgrad(cx, G2, ws.y1, ws.d32a, 1);
+    conv_dgrad(cx, G2, ws.d32a, ws.d32b, 1);
     MARK("conv2_bwd");
     bn_bwd<32>(a, G1, ws.z1, ws.y1, ws.d32b, ws.acc, 0, st);
     MARK("bn1_bwd");
@@ -704,6 +752,7 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
         simt::launch(p, 32, 28, splits, K, st);
     }
     MARK("conv1_wgrad");
+    if (cx.rc) return cx.rc;
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -730,5 +779,15 @@ int forward(const flb_train_args& a, cudaStream_t st) {
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
 int step_launches(const flb_train_args&) { return 22 + 32; }
-void tc_tab(const flb_train_args&, TcConvTab*) {}
+void tc_tab(const flb_train_args& a, TcConvTab* t) {
+    if (a.precision != 1) return;
+    CifarWs ws;
+    carve(a.ws, a.K, a.B, &ws);
+    t->n = NCONV - 1;
+    for (int i = 1; i < NCONV; ++i) {
+        t->woff[i - 1] = kNet.cw[i]; t->cin[i - 1] = kNet.cin[i]; t->cout[i - 1] = kNet.cout[i];
+        t->toff[i - 1] = kNet.toff[i]; t->gt_live[i - 1] = 1;
+    }
+    t->ldt = kNet.ldt; t->wt = ws.wt; t->gt = ws.gt;
+}
 }  // namespace cifar
