@@ -25,8 +25,26 @@ import torch  # noqa: E402
 
 MODEL = "simple_cnn"
 CLIENTS_PER_GPU = 10
-FLOP_PER_SAMPLE = 25.0e6          # fwd + bwd, 2 * MAC
 METRIC = "DP-SGD client samples/s (one FedAvg round: local epoch + update-level DP + aggregation)"
+# workloads (BASELINE.json configs): the default is configs[1]; the others are extra measurements for profiles/
+WORKLOADS = {
+    "mnist_dp": dict(model="simple_cnn", clients_per_gpu=10, total_clients=None, compression=None, scaling="weak",
+                     desc="configs[1]: SimpleCNN MNIST-shaped 28x28, 10 clients/GPU x 1 local epoch (batch 32, Adam 1e-3, dropout 0.25), "
+                          "update-level DP (eps=1, delta=1e-5, C=1), FedAvg"),
+    "mnist_dp50": dict(model="simple_cnn", clients_per_gpu=None, total_clients=50, compression=None, scaling="strong",
+                       desc="configs[2]: SimpleCNN MNIST-shaped, 50 clients sharded over the GPUs x 1 local epoch (batch 32, Adam 1e-3, "
+                            "dropout 0.25), update-level DP, FedAvg"),
+    "cifar_dp_q8": dict(model="cifar10_cnn", clients_per_gpu=None, total_clients=100, compression="q8", scaling="strong",
+                        desc="configs[3]: CIFAR10CNN 32x32x3, 100 clients sharded over the GPUs x 1 local epoch (batch 32, Adam 1e-3, "
+                             "dropout 0.3), update-level DP, uint8-quantised updates, FedAvg"),
+}
+# fwd + bwd algorithmic FLOPs per sample of the GEMM-shaped kernels (2 * MAC)
+GEMM_FLOPS = {
+    "simple_cnn": {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288,
+                   "fc1_fwd": 2 * 3136 * 128, "fc1_dgrad": 2 * 3136 * 128, "fc1_wgrad": 2 * 3136 * 128},
+    "cifar10_cnn": {f"conv{i}_fwd": 2 * hw * ci * 9 * co for i, (hw, ci, co) in
+                    enumerate([(1024, 3, 32), (1024, 32, 32), (256, 32, 64), (256, 64, 64), (64, 64, 128), (64, 128, 128)], start=1)},
+}
 
 
 def peaks():
@@ -68,11 +86,12 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_baseline_run(n_clients: int, threads: int, rounds: int = 1):
+def cpu_baseline_run(n_clients: int, threads: int, rounds: int = 1, model: str = "simple_cnn"):
     """The reference path restated on the CPU (oracle/round.py: LocalTrainer loop + update-level DP + FedAvg), on a
     bounded sample of the same workload.  Returns (samples/s, sample description)."""
     from oracle import models as OM
     from oracle import round as OR
+    MODEL = model
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     w0 = OM.init_weights(MODEL, 0)
@@ -119,7 +138,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("FLB_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--dp-mode", default="update", choices=["update", "per_sample", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mnist_dp", choices=list(WORKLOADS))
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    MODEL = wl["model"]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
@@ -138,11 +160,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    n_clients = CLIENTS_PER_GPU * world
+    n_clients = wl["total_clients"] or wl["clients_per_gpu"] * world
 
     eng = FederatedRoundEngine(MODEL, n_clients, dev, rank=rank, world_size=world, process_group=pg, batch_size=32,
                                local_epochs=1, learning_rate=1e-3, optimizer_type="adam", dp_mode=args.dp_mode,
-                               epsilon=1.0, delta=1e-5, max_grad_norm=1.0, dropout_rate=0.25, precision=args.precision)
+                               epsilon=1.0, delta=1e-5, max_grad_norm=1.0, dropout_rate=None, precision=args.precision,
+                               compression=wl["compression"])
     torch.manual_seed(0)
     w0 = ModelFactory.create_model(MODEL).get_model_weights()
     eng.set_global_weights(w0)
@@ -222,8 +245,7 @@ def main():
     pk = peaks()
     K_local, B = len(eng.client_ids), 32
     # algorithmic FLOPs of the GEMM-shaped kernels per launch (all resident clients, full batch)
-    flops = {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288,
-             "fc1_fwd": 2 * 3136 * 128, "fc1_dgrad": 2 * 3136 * 128, "fc1_wgrad": 2 * 3136 * 128}
+    flops = GEMM_FLOPS[MODEL]
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0
     if top in flops:
         ach = flops[top] * B * K_local / (acc[top] * 1e-3) / 1e12
@@ -236,10 +258,9 @@ def main():
 
     launches_round = tr.launches_per_epoch() + (2 if args.dp_mode == "update" else 0) + 1
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: SimpleCNN MNIST-shaped 28x28, 10 clients/GPU x 1 local epoch (batch 32, Adam 1e-3, dropout 0.25), "
-                                   "update-level DP (eps=1, delta=1e-5, C=1), FedAvg" + (" + NCCL all-reduce" if world > 1 else ""),
+            "config": {"workload": wl["desc"] + (" + NCCL all-reduce" if world > 1 else ""),
                        "clients": n_clients, "samples_per_round": samples_round, "dp_mode": args.dp_mode, "precision": args.precision,
                        "l2": "flushed (256 MB write) before every timed round", "round_ms": ms / args.steps},
             "e2e": {"value": samples_round * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
@@ -248,7 +269,8 @@ def main():
             "roofline": roof, "clocks": sampler.summary()}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, sample = cpu_baseline_run(CLIENTS_PER_GPU, threads, 4)
+        v, sample = (cpu_baseline_run(CLIENTS_PER_GPU, threads, 4) if MODEL == "simple_cnn"
+                     else cpu_baseline_run(4, threads, 1, MODEL))
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line))

@@ -44,6 +44,9 @@ void flb_set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 
+struct SideLane { bool ready = false; cudaStream_t s = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; };
+SideLane* flb_side_lane();   // per host thread and device; nullptr if it cannot be created
+
 int flb_num_sms();   // SM count of the current device (148 on B200), cached
 
 static inline int flb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

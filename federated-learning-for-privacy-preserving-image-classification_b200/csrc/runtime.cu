@@ -24,6 +24,22 @@ int flb_num_sms() {
     return FLB_NUM_SMS_B200;
 }
 
+// A second stream per host thread (and device) on which the weight-gradient kernels of a step run beside the
+// activation-gradient chain; fork / join go through events, so the pair is capturable into one CUDA graph.
+SideLane* flb_side_lane() {
+    static thread_local SideLane lanes[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideLane& l = lanes[dev];
+    if (!l.ready) {
+        if (cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreateWithFlags(&l.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        l.ready = true;
+    }
+    return &l;
+}
+
 extern "C" const char* flb_last_error(void) { return g_err; }
 
 extern "C" int flb_version(void) { return 100; }

@@ -49,36 +49,64 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
     float* wt = tab.wt + (long long)k * tab.ldt;
     const float* gt = tab.gt + (long long)k * tab.ldt;
     const int P4 = (P + 3) >> 2;
+    const bool adam = a.opt != 1;
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
+        const int p0 = c4 * 4;
+        const bool whole = p0 + 3 < P;           // rows are 128 B aligned (ld % 32 == 0): 16 B vector access per quad
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
         float z[4] = {0.f, 0.f, 0.f, 0.f};
+        int q[4] = {-1, -1, -1, -1};
+        if (whole) {
+            const float4 g4 = *reinterpret_cast<const float4*>(G + p0), w4 = *reinterpret_cast<const float4*>(W + p0);
+            g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+            if (adam || t > 1) { const float4 m4 = *reinterpret_cast<const float4*>(M + p0); m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w; }
+            if (adam) { const float4 v4 = *reinterpret_cast<const float4*>(V + p0); v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w; }
+            if (a.dp_mode == 1 && zrow) { const float4 z4 = *reinterpret_cast<const float4*>(zrow + p0); z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w; }
+        } else {
+            for (int e = 0; e < 4 && p0 + e < P; ++e) {
+                g[e] = G[p0 + e]; w[e] = W[p0 + e]; m[e] = M[p0 + e]; v[e] = V[p0 + e];
+                if (a.dp_mode == 1 && zrow) z[e] = zrow[p0 + e];
+            }
+        }
+        if (tab.n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int layer = 0;
+                q[e] = p0 + e < P ? tc_tab_map(tab, p0 + e, layer) : -1;
+                if (q[e] >= 0 && tab.gt_live[layer]) g[e] = gt[q[e]];
+            }
+        }
         if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
             const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
             z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int p = c4 * 4 + e;
-            if (p >= P) break;
-            int layer = 0;
-            const int q = tab.n ? tc_tab_map(tab, p, layer) : -1;
-            float g = (q >= 0 && tab.gt_live[layer]) ? gt[q] : G[p];
-            if (a.dp_mode == 1) g = (g + a.dp_sigma * (zrow ? zrow[p] : z[e])) * inv_b;   // (sum clipped + N(0, sigma^2)) / B
-            float w = W[p];
-            if (a.opt == 1) {                               // SGD with momentum, dampening 0
-                const float buf = t == 1 ? g : fmaf(mu, M[p], g);
-                M[p] = buf;
-                w = w - lr * buf;
+            if (a.dp_mode == 1) g[e] = (g[e] + a.dp_sigma * z[e]) * inv_b;     // (sum clipped + N(0, sigma^2)) / B
+            if (!adam) {                                    // SGD with momentum, dampening 0
+                const float buf = t == 1 ? g[e] : fmaf(mu, m[e], g[e]);
+                m[e] = buf;
+                w[e] = w[e] - lr * buf;
             } else {
-                if (a.opt == 2) w = w * decay;      // AdamW decoupled decay
-                float m = M[p], v = V[p];
-                m = m + (g - m) * omb1;                           // exp_avg.lerp_(grad, 1 - beta1)
-                v = v * b2 + omb2 * g * g;                  // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-                M[p] = m; V[p] = v;
-                const float denom = sqrtf(v) / bc2_sqrt + eps;
-                w = w - step_size * (m / denom);                             // param.addcdiv_(m, denom, -step_size)
+                if (a.opt == 2) w[e] = w[e] * decay;        // AdamW decoupled decay
+                m[e] = m[e] + (g[e] - m[e]) * omb1;         // exp_avg.lerp_(grad, 1 - beta1)
+                v[e] = v[e] * b2 + omb2 * g[e] * g[e];      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+                const float denom = sqrtf(v[e]) / bc2_sqrt + eps;
+                w[e] = w[e] - step_size * (m[e] / denom);   // param.addcdiv_(m, denom, -step_size)
             }
-            W[p] = w;
-            if (q >= 0) wt[q] = w;
+        }
+        if (whole) {
+            *reinterpret_cast<float4*>(W + p0) = make_float4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<float4*>(M + p0) = make_float4(m[0], m[1], m[2], m[3]);
+            if (adam) *reinterpret_cast<float4*>(V + p0) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int e = 0; e < 4 && p0 + e < P; ++e) { W[p0 + e] = w[e]; M[p0 + e] = m[e]; if (adam) V[p0 + e] = v[e]; }
+        }
+        if (tab.n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (q[e] >= 0) wt[q[e]] = w[e];
         }
     }
 }

@@ -97,37 +97,45 @@ __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, S
     }
 }
 
-// conv2 epilogue on the fp32 path: ReLU + 2x2 max-pool + argmax from z2 (bias included), NCHW-flattened output
-__global__ void __launch_bounds__(256) pool2_kernel(flb_train_args a, SimpleCnnWs ws) {
-    const int b = blockIdx.x, k = blockIdx.y;
+// conv2 epilogue: ReLU + 2x2 max-pool + argmax from z2 (bias included), NCHW-flattened output.
+// One thread per (pooled position, 4 channels): 16 B loads along the channel axis; grid (7 pooled rows * B, K).
+__global__ void __launch_bounds__(112) pool2_kernel(flb_train_args a, SimpleCnnWs ws) {
+    const int b = blockIdx.x / 7, ph = blockIdx.x % 7, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
     const float* z = ws.z2 + kb * (PP2 * 64);
     float* o = ws.a2 + kb * 3136;
     uint8_t* idx = ws.idx2 + kb * 3136;
-    for (int e = threadIdx.x; e < 3136; e += 256) {
-        const int c = e & 63, pp = e >> 6, ph = pp / 7, pw = pp % 7;
-        float best = -INFINITY;
-        int bi = 0;
+    const int pw = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4, pp = ph * 7 + pw;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float v = z[((2 * ph + i) * WP2 + 2 * pw + j) * 64 + c];
-                if (v > best) { best = v; bi = i * 2 + j; }
-            }
-        o[c * 49 + pp] = fmaxf(best, 0.f);
-        idx[c * 49 + pp] = (uint8_t)bi;
+        for (int j = 0; j < 2; ++j) {
+            const float4 v4 = *reinterpret_cast<const float4*>(z + ((2 * ph + i) * WP2 + 2 * pw + j) * 64 + c);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v[e] > best[e]) { best[e] = v[e]; bi[e] = i * 2 + j; }
+        }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o[(c + e) * 49 + pp] = fmaxf(best[e], 0.f);
+        idx[(c + e) * 49 + pp] = (uint8_t)bi[e];
     }
 }
 
-
 // ------------------------------------------------------------------------------------------------
-// classifier head: fc1 bias + ReLU + dropout, fc2, softmax cross-entropy, dlogits, dh.  One CTA per client.
+// classifier head: fc1 bias + ReLU + dropout, fc2, softmax cross-entropy, dlogits, dh.
+// grid (K, HEAD_PARTS): each CTA owns a slice of the client's batch; the epoch accumulators take one atomic per CTA.
+constexpr int HEAD_PARTS = 4;
 __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, SimpleCnnWs ws) {
     const int k = blockIdx.x;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
+    const int per = (a.B + gridDim.y - 1) / gridDim.y, b0 = blockIdx.y * per;
+    const int nloc = max(0, min(bsz, b0 + per) - b0);          // live samples of this slice
     __shared__ float sh[32][129];
     __shared__ float sw2[10][129];
     __shared__ float slog[32][10];
@@ -135,12 +143,15 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     __shared__ float red[2];
     const int tid = threadIdx.x;
     const float* W = a.W + (long long)k * a.ld;
-    const long long kb = (long long)k * a.B;
+    const long long kb = (long long)k * a.B + b0;
+    // rows bsz..B-1 of dh feed the tensor-core fc1 wgrad as zeros (its K extent is the whole batch)
+    for (int e = nloc * 128 + tid; e < min(per, a.B - b0) * 128; e += 256) ws.dh[kb * 128 + e] = 0.f;
+    if (nloc == 0) return;
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
     const int step = *a.step_ctr;
     // h = dropout(relu(hpre + b1)); the multiplier (0 or 1/(1-p), and 0 where ReLU is inactive) is kept in dh's
     // slot until the backward part below overwrites it
-    for (int e = tid; e < bsz * 128; e += 256) {
+    for (int e = tid; e < nloc * 128; e += 256) {
         const int b = e >> 7, j = e & 127;
         const float pre = ws.hpre[kb * 128 + e] + W[Off::f1b + j];
         float mult = pre > 0.f ? 1.f : 0.f;
@@ -148,10 +159,11 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
             bool keep;
             if (a.drop_keep) keep = a.drop_keep[kb * 128 + e] != 0;
             else {
+                const int eg = b0 * 128 + e;                   // element index within the client's [B, 128] block
                 const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
-                                                  ((unsigned long long)a.tcount[k] << 12) + (e >> 2));
+                                                  ((unsigned long long)a.tcount[k] << 12) + (eg >> 2));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-                keep = flb_u01(rr[e & 3]) >= a.drop_p;
+                keep = flb_u01(rr[eg & 3]) >= a.drop_p;
             }
             mult = keep ? mult * keep_scale : 0.f;
         }
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     for (int e = tid; e < 1280; e += 256) sw2[e >> 7][e & 127] = W[Off::f2w + e];
     if (tid < 2) red[tid] = 0.f;
     __syncthreads();
-    for (int e = tid; e < bsz * 10; e += 256) {
+    for (int e = tid; e < nloc * 10; e += 256) {
         const int b = e / 10, j = e % 10;
         float acc = W[Off::f2b + j];
 #pragma unroll 8
@@ -172,8 +184,8 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
         ws.logits[kb * 10 + e] = acc;
     }
     __syncthreads();
-    if (tid < bsz) {
-        const int y = a.y[a.sample_off[k] + (long long)step * a.B + tid];
+    if (tid < nloc) {
+        const int y = a.y[a.sample_off[k] + (long long)step * a.B + b0 + tid];
         float mx = slog[tid][0];
         int am = 0;
         for (int j = 1; j < 10; ++j) if (slog[tid][j] > mx) { mx = slog[tid][j]; am = j; }
@@ -192,20 +204,20 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     }
     __syncthreads();
     if (tid == 0) {
-        a.loss_sum[k] += red[0] / (float)bsz;          // running_loss += loss.item()   (training.py:200)
-        a.correct[k] += (int)(red[1] + 0.5f);          // correct += (pred == y).sum()  (training.py:201-203)
-        a.nbatch[k] += 1;
-        a.nseen[k] += bsz;
+        atomicAdd(&a.loss_sum[k], red[0] / (float)bsz);     // running_loss += loss.item()   (training.py:200)
+        atomicAdd(&a.correct[k], (int)(red[1] + 0.5f));     // correct += (pred == y).sum()  (training.py:201-203)
+        if (blockIdx.y == 0) {
+            a.nbatch[k] += 1;
+            a.nseen[k] += bsz;
+        }
     }
-    for (int e = tid; e < bsz * 128; e += 256) {
+    for (int e = tid; e < nloc * 128; e += 256) {
         const int b = e >> 7, j = e & 127;
         float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < 10; ++c) acc = fmaf(sdl[b][c], sw2[c][j], acc);
         ws.dh[kb * 128 + e] = acc * ws.dh[kb * 128 + e];
     }
-    // rows bsz..B-1 of dh feed the tensor-core fc1 wgrad as zeros (its K extent is the whole batch)
-    for (int e = bsz * 128 + tid; e < a.B * 128; e += 256) ws.dh[kb * 128 + e] = 0.f;
 }
 
 // fc2 weight/bias gradients (tiny): one CTA per client
@@ -243,22 +255,18 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(flb_train_args a, Simpl
     }
 }
 
-// conv2 bias gradient (tensor-core path; the fp32 path gets it as an extra GEMM column): per-sample column sums of dz
-__global__ void __launch_bounds__(256) conv2_bias_grad_kernel(flb_train_args a, SimpleCnnWs ws, int use_coef) {
+// conv2 bias gradient (tensor-core path; the fp32 path gets it as an extra GEMM column): every pooling window routes
+// its upstream gradient to exactly one conv2 output, so sum_px dz2[px][c] = sum_pp [a2 > 0] * da2[c*49 + pp].
+__global__ void __launch_bounds__(64) conv2_bias_grad_kernel(flb_train_args a, SimpleCnnWs ws, int use_coef) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
-    const float* dz = ws.z2 + kb * (PP2 * 64);
-    const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int c = threadIdx.x;
+    const float* da2 = ws.da2 + kb * 3136 + c * 49;
+    const float* a2 = ws.a2 + kb * 3136 + c * 49;
     float acc = 0.f;
-    for (int px = part; px < PP2; px += 4) acc += dz[px * 64 + c];
-    __shared__ float red[4][64];
-    red[part][c] = acc;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const float v = (red[0][c] + red[1][c] + red[2][c] + red[3][c]) * (use_coef ? ws.coef[kb] : 1.f);
-        atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], v);
-    }
+    for (int pp = 0; pp < 49; ++pp) acc += a2[pp] > 0.f ? da2[pp] : 0.f;
+    atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], acc * (use_coef ? ws.coef[kb] : 1.f));
 }
 
 // dp_mode 1, tensor-core wgrads: TMA cannot scale an operand in flight, so the activation gradients are scaled by
@@ -276,24 +284,26 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(flb_train_args a, float
     }
 }
 
-// max-unpool + ReLU backward into the padded NHWC dz2 grid (every position written, pads = 0)
+// max-unpool + ReLU backward into the padded NHWC dz2 grid (every position written, pads = 0).
+// One thread per (grid position, 4 channels), 16 B stores; grid (16 grid rows * B, K).
 __global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCnnWs ws) {
-    const int b = blockIdx.x, k = blockIdx.y;
+    const int b = blockIdx.x >> 4, h = blockIdx.x & 15, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
     const float* da2 = ws.da2 + kb * 3136;
     const float* a2 = ws.a2 + kb * 3136;
     const uint8_t* idx = ws.idx2 + kb * 3136;
-    float* dz = ws.z2 + kb * (PP2 * 64);
-    for (int e = threadIdx.x; e < PP2 * 64; e += 256) {
-        const int c = e & 63, pos = e >> 6, h = pos >> 4, w = pos & 15;
-        float v = 0.f;
-        if (h < 14 && w < 14) {
-            const int src = c * 49 + (h >> 1) * 7 + (w >> 1);
-            if (idx[src] == ((h & 1) * 2 + (w & 1)) && a2[src] > 0.f) v = da2[src];
+    const int w = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h < 14 && w < 14) {
+        const int pp = (h >> 1) * 7 + (w >> 1), code = (h & 1) * 2 + (w & 1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int src = (c + e) * 49 + pp;
+            if (idx[src] == code && a2[src] > 0.f) v[e] = da2[src];
         }
-        dz[e] = v;
     }
+    *reinterpret_cast<float4*>(ws.z2 + kb * (PP2 * 64) + (h * WP2 + w) * 64 + c) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // conv1 weight + bias gradient of one sample (max-unpool + ReLU backward folded in): 32 x (9 + 1) values.
@@ -414,7 +424,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
         simt::launch(p, B * PP2, 64, 1, K, st);
     }
     MARK("conv2_fwd");
-    pool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    pool2_kernel<<<dim3(7 * B, K), 112, 0, st>>>(a, ws);
     MARK("pool2");
     if (tcm & TC_FC1_FWD) {
         if (int rc = tc::fc_fwd(a, ws.a2, ws.hpre, 3136, 128, Off::f1w, 7, st)) return rc;
@@ -423,7 +433,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
         simt::launch(p, B, 128, 14, K, st);
     }
     MARK("fc1_fwd");
-    head_fwd_bwd_kernel<<<K, 256, 0, st>>>(a, ws);
+    head_fwd_bwd_kernel<<<dim3(K, HEAD_PARTS), 256, 0, st>>>(a, ws);
     MARK("head_fwd_bwd");
     FLB_LAUNCH_CHECK();
     return FLB_OK;
@@ -439,8 +449,48 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     if (a.dp_mode == 1) FLB_CUDA(cudaMemsetAsync(ws.norm2, 0, sizeof(float) * (size_t)K * B, st));
     if (int rc = forward(a, ws, st)) return rc;
 
-    // ---- activation gradients ----
+    // Weight gradients do not feed the activation-gradient chain: without per-sample clipping they run on a side
+    // stream beside it (fork / join by events -- one graph with parallel branches when the epoch is captured).
+    SideLane* lane = (a.dp_mode == 0 && !g_prof.on) ? flb_side_lane() : nullptr;
     const int tcm = tc_mask_of(a);
+    const float* coef = nullptr;
+
+    auto wgrads_head_fc1 = [&](cudaStream_t st) -> int {
+        head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws, a.dp_mode == 1);
+        MARK("head_wgrad");
+        if (tcm & TC_FC1_WGRAD) {
+            if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.dh, coef, 128);
+            if (int rc = tc::fc_wgrad(a, ws.dh, ws.a2, 3136, 128, Off::f1w, st)) return rc;
+        } else {
+            LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
+            p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
+            simt::launch(p, 128, 3136, 1, K, st);
+        }
+        MARK("fc1_wgrad");
+        return FLB_OK;
+    };
+    auto wgrads_conv2 = [&](cudaStream_t st) -> int {
+        if (tcm & TC_CONV2_WGRAD) {
+            conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, coef != nullptr);
+            if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
+            FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));
+            if (int rc = tc::conv_wgrad(a, kConv2, ws.a1p, ws.z2, ws.gt, kLdt, st)) return rc;
+        } else {
+            ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
+            p.woff = Off::c2w; p.boff = Off::c2b;
+            simt::launch(p, 64, 289, 16, K, st);
+        }
+        MARK("conv2_wgrad");
+        return FLB_OK;
+    };
+
+    if (lane) {
+        FLB_CUDA(cudaEventRecord(lane->ev[0], st));
+        FLB_CUDA(cudaStreamWaitEvent(lane->s, lane->ev[0], 0));
+        if (int rc = wgrads_head_fc1(lane->s)) return rc;
+    }
+
+    // ---- activation gradients ----
     if (tcm & TC_FC1_DGRAD) {
         if (int rc = tc::fc_dgrad(a, ws.dh, ws.da2, 3136, 128, Off::f1w, st)) return rc;
     } else {
@@ -448,8 +498,13 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         simt::launch(p, B, 3136, 1, K, st);
     }
     MARK("fc1_dgrad");
-    unpool2_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    unpool2_kernel<<<dim3(16 * B, K), 256, 0, st>>>(a, ws);
     MARK("unpool2");
+    if (lane) {
+        FLB_CUDA(cudaEventRecord(lane->ev[1], st));
+        FLB_CUDA(cudaStreamWaitEvent(lane->s, lane->ev[1], 0));
+        if (int rc = wgrads_conv2(lane->s)) return rc;
+    }
     if (tcm & TC_CONV2_DGRAD) {
         if (int rc = tc::conv_dgrad(a, kConv2, ws.z2, ws.da1p, ws.wt, kLdt, st)) return rc;
     } else {
@@ -459,7 +514,6 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     MARK("conv2_dgrad");
 
     // ---- per-sample clip coefficients (dp_mode 1) ----
-    const float* coef = nullptr;
     if (a.dp_mode == 1) {
         linear_ghost_norm_kernel<<<per_sample, 128, 0, st>>>(a, ws);
         {
@@ -473,31 +527,17 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     }
 
     // ---- weight gradients ----
-    head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws, a.dp_mode == 1);
-    MARK("head_wgrad");
-    if (tcm & TC_FC1_WGRAD) {
-        if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.dh, coef, 128);
-        if (int rc = tc::fc_wgrad(a, ws.dh, ws.a2, 3136, 128, Off::f1w, st)) return rc;
-    } else {
-        LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
-        p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
-        simt::launch(p, 128, 3136, 1, K, st);
+    if (!lane) {
+        if (int rc = wgrads_head_fc1(st)) return rc;
+        if (int rc = wgrads_conv2(st)) return rc;
     }
-    MARK("fc1_wgrad");
-    if (tcm & TC_CONV2_WGRAD) {
-        conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, coef != nullptr);
-        if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
-        FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));
-        if (int rc = tc::conv_wgrad(a, kConv2, ws.a1p, ws.z2, ws.gt, kLdt, st)) return rc;
-    } else {
-        ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
-        p.woff = Off::c2w; p.boff = Off::c2b;
-        simt::launch(p, 64, 289, 16, K, st);
-    }
-    MARK("conv2_wgrad");
     if (a.dp_mode == 1) conv1_ps_reduce_kernel<<<K, 320, 0, st>>>(a, ws);
     else conv1_bwd_kernel<<<per_sample, 256, 0, st>>>(a, ws, 0);
     MARK("conv1_wgrad");
+    if (lane) {
+        FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
+        FLB_CUDA(cudaStreamWaitEvent(st, lane->ev[2], 0));
+    }
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -522,7 +562,12 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     return ::forward(a, ws, st);
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
-int step_launches(const flb_train_args& a) { return a.dp_mode == 1 ? 16 : 12; }
+int step_launches(const flb_train_args& a) {
+    const int m = tc_mask_of(a);
+    int n = 12 + ((m & TC_CONV2_WGRAD) ? 1 : 0);                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
+    if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 1 : 0);
+    return n;
+}
 void tc_tab(const flb_train_args& a, TcConvTab* t) {
     const int m = tc_mask_of(a);
     if (!(m & (TC_CONV2_FWD | TC_CONV2_DGRAD | TC_CONV2_WGRAD))) return;
