@@ -24,6 +24,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -185,6 +188,93 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<T::TMEM_COLS>(tmem);
+}
+
+// Persistent variant for GEMMs with many independent output tiles (conv fwd / dgrad): gridDim.x CTAs each walk the
+// tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run decoupled: the TMA producer streams k-blocks of
+// tile i+1 while the MMA lane is still on tile i, and the accumulator is double-buffered in TMEM (2 x ACC_COLS
+// columns) so the epilogue warps drain tile i while the MMAs of tile i+1 are issued.
+// Extra Traits members:  static constexpr int ACC_COLS;
+//                        __device__ bool tile_setup(const Params&, int tile, int& num_kb)   (same answer for every role)
+//                        static __host__ __device__ int num_tiles(const Params&)
+template <class T>
+__global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const __grid_constant__ typename T::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base;
+    constexpr int TCOLS = 2 * T::ACC_COLS <= 32 ? 32 : (2 * T::ACC_COLS <= 64 ? 64 : (2 * T::ACC_COLS <= 128 ? 128 : (2 * T::ACC_COLS <= 256 ? 256 : 512)));
+    static_assert(2 * T::ACC_COLS <= 512, "double-buffered accumulator must fit TMEM");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = T::num_tiles(p);
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+        T t0;
+        t0.prefetch(p);
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            T t;
+            uint32_t it = 0;                                   // k-blocks issued so far (all tiles)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int num_kb = 0;
+                if (!t.tile_setup(p, tile, num_kb)) continue;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            T t;
+            uint32_t it = 0, nt = 0;                           // k-blocks / tiles consumed so far
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int num_kb = 0;
+                if (!t.tile_setup(p, tile, num_kb)) continue;
+                const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);          // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), 0, tmem + acc * T::ACC_COLS);
+                    mma_commit(&empty_bar[s]);
+                }
+                mma_commit(&tfull_bar[acc]);
+                ++nt;
+            }
+        }
+    } else {
+        T t;
+        uint32_t nt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            t.epilogue(p, tmem + acc * T::ACC_COLS, warp & 3, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            ++nt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TCOLS>(tmem);
 }
 
 }  // namespace tc

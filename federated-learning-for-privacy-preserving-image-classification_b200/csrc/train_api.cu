@@ -30,18 +30,47 @@ __global__ void __launch_bounds__(256) tc_repack_kernel(flb_train_args a, TcConv
     }
 }
 
+__device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, const TcConvTab& tab, int k, int bsz);
+
+// grid (blocks, K).  Also advances the minibatch counter and the clients' optimizer step counts (what
+// flb_train_advance does on its own for the forward-only path).
 __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P, TcConvTab tab) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
-    if (bsz == 0) return;
+    if (bsz > 0) optimizer_body(a, P, tab, k, bsz);
+    // The last CTA to finish advances the step: every CTA has read *step_ctr / tcount before it takes its ticket.
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int ticket = atomicAdd(&a.step_ctr[1], 1);
+        s_last = ticket == (int)(gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        for (int c = threadIdx.x; c < a.K; c += blockDim.x)
+            if (flb_bsz(a, c) > 0) a.tcount[c] += 1;
+        __syncthreads();
+        if (threadIdx.x == 0) { a.step_ctr[0] += 1; a.step_ctr[1] = 0; __threadfence(); }
+    }
+}
+
+__device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, const TcConvTab& tab, int k, int bsz) {
     const int t = a.tcount[k] + 1;
     float* W = a.W + (long long)k * a.ld;
     float* G = a.G + (long long)k * a.ld;
     float* M = a.M + (long long)k * a.ld;
     float* V = a.V + (long long)k * a.ld;
     // scalars are formed in double and rounded to fp32 once, like Python floats entering fp32 tensor ops
-    const double bc1d = 1.0 - pow(a.beta1, (double)t), bc2d = 1.0 - pow(a.beta2, (double)t);
-    const float step_size = (float)(a.lr / bc1d), bc2_sqrt = (float)sqrt(bc2d);
+    // (one thread per CTA: pow() in double is hundreds of instructions)
+    __shared__ float s_sc[2];
+    if (threadIdx.x == 0) {
+        const double bc1d = 1.0 - pow(a.beta1, (double)t), bc2d = 1.0 - pow(a.beta2, (double)t);
+        s_sc[0] = (float)(a.lr / bc1d);
+        s_sc[1] = (float)(1.0 / sqrt(bc2d));
+    }
+    __syncthreads();
+    const float step_size = s_sc[0], inv_bc2_sqrt = s_sc[1];
     const float lr = (float)a.lr, omb1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, omb2 = (float)(1.0 - a.beta2);
     const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
     const float inv_b = 1.f / (float)bsz;
@@ -50,6 +79,11 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
     const float* gt = tab.gt + (long long)k * tab.ldt;
     const int P4 = (P + 3) >> 2;
     const bool adam = a.opt != 1;
+    int tab_lo = 0x7fffffff, tab_hi = 0;
+    for (int i = 0; i < tab.n; ++i) {
+        tab_lo = min(tab_lo, tab.woff[i]);
+        tab_hi = max(tab_hi, tab.woff[i] + tab.cout[i] * tab.cin[i] * 9);
+    }
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
         const int p0 = c4 * 4;
         const bool whole = p0 + 3 < P;           // rows are 128 B aligned (ld % 32 == 0): 16 B vector access per quad
@@ -69,7 +103,8 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
                 if (a.dp_mode == 1 && zrow) z[e] = zrow[p0 + e];
             }
         }
-        if (tab.n) {
+        const bool mapped = tab.n && p0 + 3 >= tab_lo && p0 < tab_hi;     // quad touches a tensor-core conv weight range
+        if (mapped) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int layer = 0;
@@ -92,8 +127,11 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
                 if (a.opt == 2) w[e] = w[e] * decay;        // AdamW decoupled decay
                 m[e] = m[e] + (g[e] - m[e]) * omb1;         // exp_avg.lerp_(grad, 1 - beta1)
                 v[e] = v[e] * b2 + omb2 * g[e] * g[e];      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-                const float denom = sqrtf(v[e]) / bc2_sqrt + eps;
-                w[e] = w[e] - step_size * (m[e] / denom);   // param.addcdiv_(m, denom, -step_size)
+                // denom = sqrt(v) / sqrt(1 - b2^t) + eps; param.addcdiv_(m, denom, -step_size).  The two divisions use the
+                // fast reciprocal forms (<= 2 ulp): Adam trajectories are compared at +-lr granularity anyway
+                // (conftest.adam_trajectory_check) and IEEE division made this kernel instruction-bound (ncu).
+                const float denom = fmaf(__fsqrt_rn(v[e]), inv_bc2_sqrt, eps);
+                w[e] = w[e] - step_size * __fdividef(m[e], denom);
             }
         }
         if (whole) {
@@ -103,7 +141,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
         } else {
             for (int e = 0; e < 4 && p0 + e < P; ++e) { W[p0 + e] = w[e]; M[p0 + e] = m[e]; if (adam) V[p0 + e] = v[e]; }
         }
-        if (tab.n) {
+        if (mapped) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
                 if (q[e] >= 0) wt[q[e]] = w[e];
@@ -121,7 +159,7 @@ __global__ void advance_kernel(flb_train_args a) {
 __global__ void begin_epoch_kernel(flb_train_args a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < a.K) { a.loss_sum[k] = 0.f; a.correct[k] = 0; a.nbatch[k] = 0; a.nseen[k] = 0; }
-    if (k == 0) *a.step_ctr = 0;
+    if (k == 0) { a.step_ctr[0] = 0; a.step_ctr[1] = 0; }
 }
 
 int check_args(const flb_train_args* a) {
@@ -213,8 +251,6 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
     optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P, tab_of(*a));
     MARK("optimizer");
-    advance_kernel<<<1, 1024, 0, st>>>(*a);
-    MARK("advance");
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -222,7 +258,7 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
 // number of kernel launches (memsets excluded) one flb_train_step issues for these args
 extern "C" int flb_train_step_launches(const flb_train_args* a) {
     if (!a) return -1;
-    return 2 + (a->model == 0 ? simplecnn::step_launches(*a) : cifar::step_launches(*a));
+    return 1 + (a->model == 0 ? simplecnn::step_launches(*a) : cifar::step_launches(*a));
 }
 
 // One step with a CUDA event after every kernel.  Synchronises the stream (profiling aid, not the product path).

@@ -25,6 +25,8 @@ namespace tc {
 int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st);
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
+int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* pooled, uint8_t* idx, const float* wt,
+                        long long ldt, int boff, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
@@ -417,15 +419,16 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     conv1_fwd_pool_kernel<<<per_sample, 256, 0, st>>>(a, ws);
     MARK("conv1_fwd_pool");
     const int tcm = tc_mask_of(a);
-    if (tcm & TC_CONV2_FWD) {
-        if (int rc = tc::conv_fwd(a, kConv2, ws.a1p, ws.z2, ws.wt, kLdt, Off::c2b, st)) return rc;
+    if (tcm & TC_CONV2_FWD) {          // bias + ReLU + max-pool fused into the GEMM epilogue: z2 is never written
+        if (int rc = tc::conv_fwd_pool_32_64(a, kConv2, ws.a1p, ws.a2, ws.idx2, ws.wt, kLdt, Off::c2b, st)) return rc;
+        MARK("conv2_fwd_pool");
     } else {
         ConvFwdProb p{}; p.a = a; p.g = kConv2; p.xin_all = ws.a1p; p.z_all = ws.z2; p.woff = Off::c2w; p.boff = Off::c2b;
         simt::launch(p, B * PP2, 64, 1, K, st);
+        MARK("conv2_fwd");
+        pool2_kernel<<<dim3(7 * B, K), 112, 0, st>>>(a, ws);
+        MARK("pool2");
     }
-    MARK("conv2_fwd");
-    pool2_kernel<<<dim3(7 * B, K), 112, 0, st>>>(a, ws);
-    MARK("pool2");
     if (tcm & TC_FC1_FWD) {
         if (int rc = tc::fc_fwd(a, ws.a2, ws.hpre, 3136, 128, Off::f1w, 7, st)) return rc;
     } else {
@@ -564,7 +567,7 @@ int forward(const flb_train_args& a, cudaStream_t st) {
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
 int step_launches(const flb_train_args& a) {
     const int m = tc_mask_of(a);
-    int n = 12 + ((m & TC_CONV2_WGRAD) ? 1 : 0);                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
+    int n = 12 + ((m & TC_CONV2_WGRAD) ? 1 : 0) - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
     if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 1 : 0);
     return n;
 }

@@ -61,9 +61,25 @@ __device__ __forceinline__ int tap_shift(int tap, int Wp) { return (tap / 3 - 1)
 template <int N> struct Pow2Cols { static constexpr int value = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : (N <= 256 ? 256 : 512))); };
 
 // ---- conv forward: D[128 px, COUT] = sum_{tap, cin chunk} X[px + shift(tap), 32] * Wt[tap][COUT][32]^T ---------------
-template <int CIN, int COUT>
+// POOL (SimpleCNN conv2: 16-wide grid, 256 rows per image, so a 128-row tile is 8 whole grid rows): the epilogue applies
+// bias + ReLU + 2x2 max-pool (+argmax) with warp shuffles -- a warp's 32 accumulator rows are two adjacent grid rows --
+// and writes fc1's NCHW-flattened input directly; the pre-pool activation never goes to HBM.
+template <int CIN, int COUT, bool POOL = false>
 struct ConvFwdT {
-    struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff; };
+    struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff;
+                    float* pool_out; uint8_t* pool_idx; };
+    static constexpr int ACC_COLS = COUT;
+    static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
+    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
+        const int tpc = (p.a.B * p.g.PP() + 127) / 128;
+        client = tile / tpc;
+        const int bsz = flb_bsz(p.a, client);
+        m0 = (tile - client * tpc) * 128;
+        if (m0 >= bsz * p.g.PP()) return false;
+        row0 = client * p.a.B * p.g.PP();
+        num_kb = NKB;
+        return true;
+    }
     static constexpr int CH = CIN / 32, NKB = 9 * CH, A_BYTES = 128 * 128, B_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = COUT > 64 ? 3 : 4, RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<COUT>::value, MINB = 2;
@@ -94,6 +110,36 @@ struct ConvFwdT {
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
         const float* bias = p.a.W + (long long)client * p.a.ld + p.boff;
+        if (POOL) {
+            // lane = (grid row parity, grid column): window (ph, pw) = lanes {2pw, 2pw+1, 16+2pw, 17+2pw}
+            const int b = m >> 8, r = m & 255, h = r >> 4, w = r & 15;
+            const bool owner = (lane < 16) && !(lane & 1) && w < 14 && h < 14;
+            const long long kb = (long long)client * p.a.B + b;
+            const int pp = (h >> 1) * 7 + (w >> 1);
+            float* o = p.pool_out + kb * (COUT * 49) + pp;
+            uint8_t* oi = p.pool_idx + kb * (COUT * 49) + pp;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = v[i] + __ldg(&bias[c0 + i]);
+                    const float x1 = __shfl_xor_sync(0xffffffffu, x, 1), x16 = __shfl_xor_sync(0xffffffffu, x, 16),
+                                x17 = __shfl_xor_sync(0xffffffffu, x, 17);
+                    if (owner) {
+                        float best = x;
+                        int bi = 0;
+                        if (x1 > best) { best = x1; bi = 1; }
+                        if (x16 > best) { best = x16; bi = 2; }
+                        if (x17 > best) { best = x17; bi = 3; }
+                        o[(c0 + i) * 49] = fmaxf(best, 0.f);
+                        oi[(c0 + i) * 49] = (uint8_t)bi;
+                    }
+                }
+            }
+            return;
+        }
         float* z = p.z_all + ((long long)row0 + m) * COUT;
         const bool ok = m < p.a.B * p.g.PP();
 #pragma unroll 1
@@ -102,9 +148,10 @@ struct ConvFwdT {
             tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
             if (ok) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(z + c0 + i) = make_float4(v[i] + bias[c0 + i], v[i + 1] + bias[c0 + i + 1],
-                                                                         v[i + 2] + bias[c0 + i + 2], v[i + 3] + bias[c0 + i + 3]);
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                    *reinterpret_cast<float4*>(z + c0 + i) = make_float4(v[i] + bv.x, v[i + 1] + bv.y, v[i + 2] + bv.z, v[i + 3] + bv.w);
+                }
             }
         }
     }
@@ -114,6 +161,18 @@ struct ConvFwdT {
 template <int CIN, int COUT>
 struct ConvDgradT {
     struct Params { CUtensorMap map_dz; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* dx_all; };
+    static constexpr int ACC_COLS = CIN;
+    static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
+    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
+        const int tpc = (p.a.B * p.g.PP() + 127) / 128;
+        client = tile / tpc;
+        const int bsz = flb_bsz(p.a, client);
+        m0 = (tile - client * tpc) * 128;
+        if (m0 >= bsz * p.g.PP()) return false;
+        row0 = client * p.a.B * p.g.PP();
+        num_kb = NKB;
+        return true;
+    }
     static constexpr int CH = COUT / 32, NKB = 9 * CH, NCH = CIN / 32, A_BYTES = 128 * 128, B_BYTES = NCH * 4096;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = CIN > 64 ? 3 : 4, RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<CIN>::value, MINB = 2;
@@ -369,6 +428,21 @@ static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
     return FLB_OK;
 }
 
+template <class T>
+static int launch_persistent(const typename T::Params& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)T::STAGES * T::STAGE_BYTES + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        FLB_CUDA(cudaFuncSetAttribute(gemm_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles = T::num_tiles(p);
+    const int grid = tiles < flb_num_sms() * T::MINB ? tiles : flb_num_sms() * T::MINB;
+    gemm_persistent_kernel<T><<<grid, THREADS, smem, st>>>(p);
+    return FLB_OK;
+}
+
 // tap-major conv weights of all clients as a 3-D tensor {Cin, 9*Cout, K}; box_rows x 32 boxes
 static int make_wt_map(CUtensorMap* m, const float* wt, long long ldt, int cin, int cout, int K, uint32_t box_rows, bool mn_major) {
     const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)9 * cout, (uint64_t)K};
@@ -383,8 +457,19 @@ static int conv_fwd_t(const flb_train_args& a, const ConvGeom& g, const float* x
     typename T::Params p;
     if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 128)) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, COUT, false)) return rc;
-    p.a = a; p.g = g; p.z_all = z; p.boff = boff;
-    return launch<T>(p, dim3((a.B * g.PP() + 127) / 128, a.K), st);
+    p.a = a; p.g = g; p.z_all = z; p.boff = boff; p.pool_out = nullptr; p.pool_idx = nullptr;
+    return launch_persistent<T>(p, st);
+}
+// SimpleCNN conv2 with the fused bias + ReLU + max-pool epilogue (16-wide grid, 256 rows per image)
+int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* pooled, uint8_t* idx, const float* wt,
+                        long long ldt, int boff, cudaStream_t st) {
+    using T = ConvFwdT<32, 64, true>;
+    if (g.Wp != 16 || g.PP() != 256 || g.Cin != 32 || g.Cout != 64) { flb_set_error("conv_fwd_pool_32_64: geometry"); return FLB_ERR_ARG; }
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 128)) return rc;
+    if (int rc = make_wt_map(&p.map_w, wt, ldt, 32, 64, a.K, 64, false)) return rc;
+    p.a = a; p.g = g; p.z_all = nullptr; p.boff = boff; p.pool_out = pooled; p.pool_idx = idx;
+    return launch_persistent<T>(p, st);
 }
 template <int CIN, int COUT>
 static int conv_dgrad_t(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
@@ -393,7 +478,7 @@ static int conv_dgrad_t(const flb_train_args& a, const ConvGeom& g, const float*
     if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 128)) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, 32, true)) return rc;
     p.a = a; p.g = g; p.dx_all = dx;
-    return launch<T>(p, dim3((a.B * g.PP() + 127) / 128, a.K), st);
+    return launch_persistent<T>(p, st);
 }
 template <int CIN, int COUT, int MTC>
 static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {

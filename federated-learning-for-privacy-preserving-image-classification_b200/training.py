@@ -87,7 +87,7 @@ class BatchedClientTrainer:
         self.M = lay.new_rows(K, dev)
         self.V = lay.new_rows(K, dev)
         self.tcount = torch.zeros(K, dtype=torch.int32, device=dev)
-        self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)
         self.loss_sum = torch.zeros(K, dtype=torch.float32, device=dev)
         self.correct = torch.zeros(K, dtype=torch.int32, device=dev)
         self.nbatch = torch.zeros(K, dtype=torch.int32, device=dev)

@@ -73,7 +73,8 @@ typedef struct flb_train_args {
     const int* y;                 /* [sum N_c] labels                                                */
     const long long* sample_off;  /* [K]                                                             */
     const int* nsamples;          /* [K]                                                             */
-    int* step_ctr;                /* [1] current minibatch index within the epoch (device-advanced)  */
+    int* step_ctr;                /* [2] [0] current minibatch index within the epoch (device-advanced);
+                                     [1] scratch ticket counter of the optimizer kernel (kept at 0)      */
     /* state, client-major rows of pitch ld floats, reference layer order/layouts                    */
     float* W;                     /* [K, ld] parameters                                              */
     float* G;                     /* [K, ld] gradients (scratch)                                     */
