@@ -42,6 +42,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > SPIN_LIMIT) __trap();
     }
 }
+// one lane of a converged warp; the same lane every time
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok));
+    return ok != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -83,6 +93,12 @@ __device__ __forceinline__ uint64_t smem_desc_raw(uint32_t addr, uint32_t lbo, u
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout_type << 61);
 }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) { return smem_desc_raw(addr, lbo, sbo, 2); }
+// K-major SW128 operand that starts at an arbitrary 128-byte row of a 1024-byte-aligned swizzled tile (the shifted
+// windows of the halo convolutions).  Measured on B200: the tensor core un-swizzles with the ABSOLUTE shared-memory
+// address bits (chunk bits [4:6] ^= row bits [7:9]), so a start address that is only 128-byte aligned needs nothing
+// else -- setting the descriptor's "matrix base offset" field (bits 49-51) to the row phase gives WRONG results here;
+// it stays 0.
+__device__ __forceinline__ uint64_t smem_desc_row(uint32_t addr) { return smem_desc_raw(addr, 16, 1024, 2); }
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) { return smem_desc_raw(addr, lbo, sbo, 1); }
 
 // instruction descriptor: D = fp32, A = B = tf32, dense; a_mn / b_mn select MN-major operands
@@ -161,25 +177,29 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem = tmem_base;
 
+    // The producer and MMA warps run their loops with ALL lanes (warp-uniform control flow) and predicate only the
+    // issuing instructions on one elected lane: descriptors, coordinates and barrier addresses then live in uniform
+    // registers.  (Putting the whole loop under `if (lane == 0)` made the compiler wrap every UTCHMMA / UTMALDG in an
+    // ELECT + R2UR.BROADCAST waterfall loop, ~150 cycles per instruction -- measured, see profiles/.)
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % T::STAGES, it = kb / T::STAGES;
-                mbar_wait(&empty_bar[s], (it & 1) ^ 1);
-                t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
-            }
+        t.lead = elect_one();
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % T::STAGES, it = kb / T::STAGES;
+            mbar_wait(&empty_bar[s], (it & 1) ^ 1);
+            t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % T::STAGES, it = kb / T::STAGES;
-                mbar_wait(&full_bar[s], it & 1);
-                tc_fence_after();
-                t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), smem_u32(resident), tmem);
-                mma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
-            }
-            mma_commit(&accum_bar);                 // accumulator complete
+        t.lead = elect_one();
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % T::STAGES, it = kb / T::STAGES;
+            mbar_wait(&full_bar[s], it & 1);
+            tc_fence_after();
+            t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), smem_u32(resident), tmem);
+            if (t.lead) mma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+            __syncwarp();
         }
+        if (t.lead) mma_commit(&accum_bar);                 // accumulator complete
     } else {
         mbar_wait(&accum_bar, 0);
         tc_fence_after();
@@ -221,45 +241,151 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
     tc_fence_after();
     const uint32_t tmem = tmem_base;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            T t;
-            uint32_t it = 0;                                   // k-blocks issued so far (all tiles)
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                int num_kb = 0;
-                if (!t.tile_setup(p, tile, num_kb)) continue;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
-                }
+    if (warp == 0) {                                           // all lanes run the loop; one elected lane issues (see gemm_kernel)
+        T t;
+        t.lead = elect_one();
+        uint32_t it = 0;                                       // k-blocks issued so far (all tiles)
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                t.load(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            T t;
-            uint32_t it = 0, nt = 0;                           // k-blocks / tiles consumed so far
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                int num_kb = 0;
-                if (!t.tile_setup(p, tile, num_kb)) continue;
-                const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], aph ^ 1);          // the epilogue has drained this accumulator
+        T t;
+        t.lead = elect_one();
+        uint32_t it = 0, nt = 0;                               // k-blocks / tiles consumed so far
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], aph ^ 1);              // the epilogue has drained this accumulator
+            tc_fence_after();
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), 0, tmem + acc * T::ACC_COLS);
-                    mma_commit(&empty_bar[s]);
-                }
-                mma_commit(&tfull_bar[acc]);
-                ++nt;
+                t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), 0, tmem + acc * T::ACC_COLS);
+                if (t.lead) mma_commit(&empty_bar[s]);
+                __syncwarp();
             }
+            if (t.lead) mma_commit(&tfull_bar[acc]);
+            ++nt;
         }
     } else {
         T t;
         uint32_t nt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            t.epilogue(p, tmem + acc * T::ACC_COLS, warp & 3, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            ++nt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TCOLS>(tmem);
+}
+
+// Halo convolution with RESIDENT weights: like the persistent kernel, but each CTA owns a contiguous range of tiles
+// (consecutive tiles belong to the same client), keeps that client's whole tap-major weight tensor in shared memory and
+// streams only the activation boxes; the weights are re-loaded (w_full / w_empty handshake) when the client changes.
+// Extra Traits members: W_BYTES; load_w(p, wres, bar); load_a(p, kb, stage, bar); mma(kb, stage_addr, wres_addr, tmem).
+template <class T>
+__global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_constant__ typename T::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* wres = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* stages = wres + T::W_BYTES;
+    __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], tfull_bar[2], tempty_bar[2], wfull_bar, wempty_bar;
+    __shared__ uint32_t tmem_base;
+    constexpr int TCOLS = 2 * T::ACC_COLS <= 32 ? 32 : (2 * T::ACC_COLS <= 64 ? 64 : (2 * T::ACC_COLS <= 128 ? 128 : (2 * T::ACC_COLS <= 256 ? 256 : 512)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = T::num_tiles(p);
+    const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        mbar_init(&wfull_bar, 1);
+        mbar_init(&wempty_bar, 1);
+        fence_barrier_init();
+        T t0_;
+        t0_.prefetch(p);
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base;
+
+    if (warp == 0) {                                           // all lanes run the loop; one elected lane issues (see gemm_kernel)
+        T t;
+        t.lead = elect_one();
+        uint32_t it = 0, wuse = 0;
+        int cur = -1;
+        for (int tile = t0; tile < t1; ++tile) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            if (t.client != cur) {
+                mbar_wait(&wempty_bar, (wuse & 1) ^ 1);                // every MMA that read the old weights has completed
+                t.load_w(p, wres, &wfull_bar);
+                __syncwarp();
+                cur = t.client;
+                ++wuse;
+            }
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                t.load_a(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        T t, tn;
+        t.lead = elect_one();
+        uint32_t it = 0, nt = 0, wuse = 0;
+        int cur = -1;
+        for (int tile = t0; tile < t1; ++tile) {
+            int num_kb = 0;
+            if (!t.tile_setup(p, tile, num_kb)) continue;
+            if (t.client != cur) {
+                mbar_wait(&wfull_bar, wuse & 1);
+                cur = t.client;
+                ++wuse;
+            }
+            const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), smem_u32(wres), tmem + acc * T::ACC_COLS);
+                if (t.lead) mma_commit(&empty_bar[s]);
+                __syncwarp();
+            }
+            if (t.lead) mma_commit(&tfull_bar[acc]);
+            ++nt;
+            // hand the weight buffer back when the next live tile belongs to another client
+            int nxt = tile + 1, nkb = 0;
+            while (nxt < t1 && !tn.tile_setup(p, nxt, nkb)) ++nxt;
+            if (nxt < t1 && tn.client != cur && t.lead) mma_commit(&wempty_bar);
+            __syncwarp();
+        }
+    } else {
+        T t;
+        uint32_t nt = 0;
+        for (int tile = t0; tile < t1; ++tile) {
             int num_kb = 0;
             if (!t.tile_setup(p, tile, num_kb)) continue;
             const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;

@@ -286,26 +286,39 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(flb_train_args a, float
     }
 }
 
-// max-unpool + ReLU backward into the padded NHWC dz2 grid (every position written, pads = 0).
-// One thread per (grid position, 4 channels), 16 B stores; grid (16 grid rows * B, K).
+// max-unpool + ReLU backward into the padded NHWC dz2 grid (every position written, pads = 0).  The pooled-side
+// arrays are NCHW-flattened (fc1's input order) and the grid is NHWC: they are staged through shared memory so that
+// both the global reads and the 16 B global writes are coalesced.  grid (2 * B, K): one CTA per half image (8 grid rows).
 __global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCnnWs ws) {
-    const int b = blockIdx.x >> 4, h = blockIdx.x & 15, k = blockIdx.y;
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
     const float* da2 = ws.da2 + kb * 3136;
     const float* a2 = ws.a2 + kb * 3136;
     const uint8_t* idx = ws.idx2 + kb * 3136;
-    const int w = threadIdx.x >> 4, c = (threadIdx.x & 15) * 4;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (h < 14 && w < 14) {
-        const int pp = (h >> 1) * 7 + (w >> 1), code = (h & 1) * 2 + (w & 1);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int src = (c + e) * 49 + pp;
-            if (idx[src] == code && a2[src] > 0.f) v[e] = da2[src];
-        }
+    // pooled rows needed by grid rows [8*half, 8*half + 8): ph in [4*half, 4*half + 4) (ph = 7 does not exist)
+    const int ph0 = half * 4, nph = half ? 3 : 4;
+    __shared__ float s_val[64][29];          // [c][(ph - ph0) * 7 + pw], value or 0 where ReLU was inactive
+    __shared__ uint8_t s_code[64][29];
+    for (int e = threadIdx.x; e < 64 * nph * 7; e += 256) {
+        const int c = e / (nph * 7), j = e - c * (nph * 7);
+        const int src = c * 49 + ph0 * 7 + j;
+        s_val[c][j] = a2[src] > 0.f ? da2[src] : 0.f;
+        s_code[c][j] = idx[src];
     }
-    *reinterpret_cast<float4*>(ws.z2 + kb * (PP2 * 64) + (h * WP2 + w) * 64 + c) = make_float4(v[0], v[1], v[2], v[3]);
+    __syncthreads();
+    float* dz = ws.z2 + kb * (PP2 * 64) + half * (8 * WP2 * 64);
+    for (int e = threadIdx.x; e < 8 * WP2 * 16; e += 256) {        // (grid position, channel quad)
+        const int c = (e & 15) * 4, pos = e >> 4, hl = pos >> 4, w = pos & 15, h = half * 8 + hl;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (h < 14 && w < 14) {
+            const int j = ((h >> 1) - ph0) * 7 + (w >> 1), code = (h & 1) * 2 + (w & 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (s_code[c + q][j] == code) v[q] = s_val[c + q][j];
+        }
+        *reinterpret_cast<float4*>(dz + pos * 64 + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
 }
 
 // conv1 weight + bias gradient of one sample (max-unpool + ReLU backward folded in): 32 x (9 + 1) values.
@@ -501,7 +514,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         simt::launch(p, B, 3136, 1, K, st);
     }
     MARK("fc1_dgrad");
-    unpool2_kernel<<<dim3(16 * B, K), 256, 0, st>>>(a, ws);
+    unpool2_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
     MARK("unpool2");
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[1], st));

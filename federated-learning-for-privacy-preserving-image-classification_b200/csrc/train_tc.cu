@@ -12,6 +12,7 @@
 // optimizer kernel keeps in sync with the reference-layout row, so BOTH operands of every GEMM are plain TMA boxes and
 // no CTA spends time permuting weights; conv weight gradients are accumulated in the same layout (Gt).
 #include "tc_gemm.cuh"
+#include <type_traits>
 
 namespace tc {
 
@@ -68,6 +69,7 @@ template <int CIN, int COUT, bool POOL = false>
 struct ConvFwdT {
     struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff;
                     float* pool_out; uint8_t* pool_idx; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int ACC_COLS = COUT;
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
@@ -97,15 +99,15 @@ struct ConvFwdT {
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int tap = kb / CH, c = kb % CH;
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_2d(&p.map_x, stage, bar, c * 32, row0 + m0 + tap_shift(tap, p.g.Wp));
-        tma_load_3d(&p.map_w, stage + A_BYTES, bar, c * 32, tap * COUT, client);
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
+        if (this->lead) tma_load_2d(&p.map_x, stage, bar, c * 32, row0 + m0 + tap_shift(tap, p.g.Wp));
+        if (this->lead) tma_load_3d(&p.map_w, stage + A_BYTES, bar, c * 32, tap * COUT, client);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + A_BYTES + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            if (this->lead) mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + A_BYTES + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -161,6 +163,7 @@ struct ConvFwdT {
 template <int CIN, int COUT>
 struct ConvDgradT {
     struct Params { CUtensorMap map_dz; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* dx_all; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int ACC_COLS = CIN;
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
@@ -190,17 +193,17 @@ struct ConvDgradT {
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int tap = kb / CH, c = kb % CH;
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_2d(&p.map_dz, stage, bar, c * 32, row0 + m0 - tap_shift(tap, p.g.Wp));
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
+        if (this->lead) tma_load_2d(&p.map_dz, stage, bar, c * 32, row0 + m0 - tap_shift(tap, p.g.Wp));
 #pragma unroll
         for (int nc = 0; nc < NCH; ++nc)                        // B is MN-major: rows = cout (K), 32-wide cin (N) chunks
-            tma_load_3d(&p.map_w, stage + A_BYTES + nc * 4096, bar, nc * 32, tap * COUT + c * 32, client);
+            if (this->lead) tma_load_3d(&p.map_w, stage + A_BYTES + nc * 4096, bar, nc * 32, tap * COUT + c * 32, client);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, CIN, false, true);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
+            if (this->lead) mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -218,11 +221,98 @@ struct ConvDgradT {
     }
 };
 
+// ---- halo variants of conv fwd / dgrad ---------------------------------------------------------------------------------
+// The streamed kernels above re-read every activation row 9 times from L2 (once per tap) and were measured bound by
+// L2 -> SM traffic.  Here ONE TMA box of 128 + 2*(Wp+1) rows is staged per 32-channel chunk, and the nine taps are nine
+// MMA groups whose A descriptors start (Wp+1 + shift) rows into that box (smem_desc_row).  Activation traffic from L2
+// drops 9x -> (128 + 2*halo)/128, and the client's whole weight tensor stays resident in shared memory
+// (conv_resident_kernel) instead of riding along with every tile.
+constexpr int HALO_A_BYTES = 200 * 128;       // up to 128 + 2*34 rows (33-wide CIFAR grid), padded to a 1024-byte multiple
+
+template <int CIN, int COUT, bool POOL = false>
+struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL> {
+    using Base = ConvFwdT<CIN, COUT, POOL>;
+    using Params = typename Base::Params;
+    static constexpr int CH = CIN / 32, W_BYTES = CH * 9 * COUT * 128, STAGE_BYTES = HALO_A_BYTES;
+    static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
+    static_assert(STAGES >= 2, "resident weights leave no room for the activation pipeline");
+    int wp;
+    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
+        const bool ok = Base::tile_setup(p, tile, num_kb);
+        num_kb = CH;
+        wp = p.g.Wp;
+        return ok;
+    }
+    __device__ void load_w(const Params& p, uint8_t* wres, uint64_t* bar) {
+        if (this->lead) mbar_expect_tx(bar, W_BYTES);
+#pragma unroll 1
+        for (int i = 0; i < CH * 9; ++i)                       // tile (chunk c, tap): [COUT rows][32 cin], K-major SW128
+            if (this->lead) tma_load_3d(&p.map_w, wres + i * COUT * 128, bar, (i / 9) * 32, (i % 9) * COUT, this->client);
+    }
+    __device__ void load_a(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
+        const int halo = p.g.Wp + 1;
+        if (this->lead) mbar_expect_tx(bar, (128 + 2 * halo) * 128);
+        if (this->lead) tma_load_2d(&p.map_x, stage, bar, kb * 32, this->row0 + this->m0 - halo);
+    }
+    __device__ void mma(int kb, uint32_t stage, uint32_t wres, uint32_t tmem) {
+        constexpr uint32_t id = idesc_tf32(128, COUT, false, false);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_addr = stage + (uint32_t)(wp + 1 + tap_shift(tap, wp)) * 128u;
+            const uint32_t b_addr = wres + (uint32_t)(kb * 9 + tap) * (COUT * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (this->lead) mma_tf32(tmem, smem_desc_row(a_addr + k * 32), smem_desc(b_addr + k * 32, 16, 1024), id, kb > 0 || tap > 0 || k > 0);
+        }
+    }
+};
+
+template <int CIN, int COUT>
+struct ConvDgradHaloT : ConvDgradT<CIN, COUT> {
+    using Base = ConvDgradT<CIN, COUT>;
+    using Params = typename Base::Params;
+    static constexpr int CH = COUT / 32, NCH = CIN / 32, W_BYTES = CH * 9 * NCH * 4096, STAGE_BYTES = HALO_A_BYTES;
+    static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
+    static_assert(STAGES >= 2, "resident weights leave no room for the activation pipeline");
+    int wp;
+    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
+        const bool ok = Base::tile_setup(p, tile, num_kb);
+        num_kb = CH;
+        wp = p.g.Wp;
+        return ok;
+    }
+    __device__ void load_w(const Params& p, uint8_t* wres, uint64_t* bar) {
+        if (this->lead) mbar_expect_tx(bar, W_BYTES);
+#pragma unroll 1
+        for (int i = 0; i < CH * 9 * NCH; ++i) {               // tile (cout chunk c, tap, cin chunk nc): MN-major, [32 cout rows][32 cin]
+            const int nc = i % NCH, tap = (i / NCH) % 9, c = i / (NCH * 9);
+            if (this->lead) tma_load_3d(&p.map_w, wres + i * 4096, bar, nc * 32, tap * COUT + c * 32, this->client);
+        }
+    }
+    __device__ void load_a(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
+        const int halo = p.g.Wp + 1;
+        if (this->lead) mbar_expect_tx(bar, (128 + 2 * halo) * 128);
+        if (this->lead) tma_load_2d(&p.map_dz, stage, bar, kb * 32, this->row0 + this->m0 - halo);
+    }
+    __device__ void mma(int kb, uint32_t stage, uint32_t wres, uint32_t tmem) {
+        constexpr uint32_t id = idesc_tf32(128, CIN, false, true);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_addr = stage + (uint32_t)(wp + 1 - tap_shift(tap, wp)) * 128u;
+            const uint32_t b_addr = wres + (uint32_t)((kb * 9 + tap) * NCH) * 4096u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (this->lead) mma_tf32(tmem, smem_desc_row(a_addr + k * 32), smem_desc_mn(b_addr + k * 1024, 4096, 512), id, kb > 0 || tap > 0 || k > 0);
+        }
+    }
+};
+
 // ---- conv wgrad: Gt[tap][co][ci] += sum_px X[px + shift(tap)][ci] * dZ[px][co] ----------------------------------------
 // M = (tap, ci) in 32-row chunks, N = co, K = pixels (split over blockIdx.x); blockIdx.z selects MTC of the M tiles.
 template <int CIN, int COUT, int MTC>
 struct ConvWgradT {
     struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* gt_all; long long ldt; int kb_per_split; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int CCH = CIN / 32, ACH = 9 * CCH, BCH = COUT / 32;
     static constexpr int A_BYTES = MTC * 4 * 4096, STAGE_BYTES = A_BYTES + BCH * 4096;
     static constexpr int STAGES = STAGE_BYTES * 3 <= 200 * 1024 ? 3 : 2, RESIDENT_BYTES = 0;
@@ -246,14 +336,14 @@ struct ConvWgradT {
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int px = row0 + (kb0 + kb) * 32;
-        mbar_expect_tx(bar, (nch + BCH) * 4096);
+        if (this->lead) mbar_expect_tx(bar, (nch + BCH) * 4096);
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {                       // chunk = (tap, 32-channel slice of Cin)
             const int gc = chunk0 + ch, tap = gc / CCH, c = gc % CCH;
-            tma_load_2d(&p.map_x, stage + ch * 4096, bar, c * 32, px + tap_shift(tap, p.g.Wp));
+            if (this->lead) tma_load_2d(&p.map_x, stage + ch * 4096, bar, c * 32, px + tap_shift(tap, p.g.Wp));
         }
 #pragma unroll
-        for (int c = 0; c < BCH; ++c) tma_load_2d(&p.map_dz, stage + A_BYTES + c * 4096, bar, c * 32, px);
+        for (int c = 0; c < BCH; ++c) if (this->lead) tma_load_2d(&p.map_dz, stage + A_BYTES + c * 4096, bar, c * 32, px);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, true, true);
@@ -261,7 +351,7 @@ struct ConvWgradT {
         const int mtiles = (nch + 3) >> 2;
         for (int k = 0; k < ksteps; ++k)
             for (int mt = 0; mt < mtiles; ++mt)
-                mma_tf32(tmem + mt * COUT, smem_desc_mn(stage + mt * 4 * 4096 + k * 1024, 4096, 512),
+                if (this->lead) mma_tf32(tmem + mt * COUT, smem_desc_mn(stage + mt * 4 * 4096 + k * 1024, 4096, 512),
                          smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
@@ -289,6 +379,7 @@ struct ConvWgradT {
 template <int IN, int OUT>
 struct FcFwdT {
     struct Params { CUtensorMap map_w; CUtensorMap map_act; flb_train_args a; float* out_all; int kb_per_split; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static_assert(OUT % 128 == 0, "whole 128-row accumulator tiles");
     static constexpr int STAGES = 6, STAGE_BYTES = 128 * 128 + 32 * 128, RESIDENT_BYTES = 0, TMEM_COLS = 32, MINB = 1;
     int client, kb0, bsz, mt;
@@ -307,15 +398,15 @@ struct FcFwdT {
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
         const int k0 = (kb0 + kb) * 32;
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_3d(&p.map_w, stage, bar, k0, mt * 128, client);
-        tma_load_2d(&p.map_act, stage + 128 * 128, bar, k0, client * p.a.B);
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
+        if (this->lead) tma_load_3d(&p.map_w, stage, bar, k0, mt * 128, client);
+        if (this->lead) tma_load_2d(&p.map_act, stage + 128 * 128, bar, k0, client * p.a.B);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, 32, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + 128 * 128 + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            if (this->lead) mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + 128 * 128 + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int j = mt * 128 + quarter * 32 + lane;
@@ -332,6 +423,7 @@ struct FcFwdT {
 template <int IN, int OUT>
 struct FcDgradT {
     struct Params { CUtensorMap map_w; CUtensorMap map_dout; flb_train_args a; float* dact_all; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int STAGES = 4, STAGE_BYTES = 4 * 4096 + 4096, RESIDENT_BYTES = 0, TMEM_COLS = 32, MINB = 2;
     int client, m0, bsz;
     __device__ bool setup(const Params& p, int& num_kb) {
@@ -345,16 +437,16 @@ struct FcDgradT {
     __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_w); tma_prefetch_desc(&p.map_dout); }
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
-        mbar_expect_tx(bar, STAGE_BYTES);
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_3d(&p.map_w, stage + c * 4096, bar, m0 + 32 * c, kb * 32, client);   // rows = out features (K)
-        tma_load_2d(&p.map_dout, stage + 4 * 4096, bar, kb * 32, client * p.a.B);
+        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_3d(&p.map_w, stage + c * 4096, bar, m0 + 32 * c, kb * 32, client);   // rows = out features (K)
+        if (this->lead) tma_load_2d(&p.map_dout, stage + 4 * 4096, bar, kb * 32, client * p.a.B);
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, 32, true, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc(stage + 4 * 4096 + k * 32, 16, 1024), id, kb > 0 || k > 0);
+            if (this->lead) mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc(stage + 4 * 4096 + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int m = m0 + quarter * 32 + lane;
@@ -373,6 +465,7 @@ struct FcDgradT {
 template <int IN, int OUT>
 struct FcWgradT {
     struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
+    bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static_assert(OUT % 128 == 0, "whole 128-row accumulator tiles");
     static constexpr int STAGES = 1, STAGE_BYTES = 4 * 4096 + 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 256, MINB = 1;
     int client, n0, ksteps, mt;
@@ -388,16 +481,16 @@ struct FcWgradT {
     __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_dout); tma_prefetch_desc(&p.map_act); }
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int, uint8_t* stage, uint64_t* bar) {
-        mbar_expect_tx(bar, STAGE_BYTES);
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(&p.map_dout, stage + c * 4096, bar, mt * 128 + 32 * c, client * p.a.B);
+        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_dout, stage + c * 4096, bar, mt * 128 + 32 * c, client * p.a.B);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) tma_load_2d(&p.map_act, stage + 4 * 4096 + c * 4096, bar, n0 + 32 * c, client * p.a.B);
+        for (int c = 0; c < 8; ++c) if (this->lead) tma_load_2d(&p.map_act, stage + 4 * 4096 + c * 4096, bar, n0 + 32 * c, client * p.a.B);
     }
     __device__ void mma(int, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, 256, true, true);
         for (int k = 0; k < ksteps; ++k)
-            mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
+            if (this->lead) mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int j = mt * 128 + quarter * 32 + lane;
@@ -443,6 +536,21 @@ static int launch_persistent(const typename T::Params& p, cudaStream_t st) {
     return FLB_OK;
 }
 
+template <class T>
+static int launch_resident(const typename T::Params& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)T::W_BYTES + (size_t)T::STAGES * T::STAGE_BYTES + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        FLB_CUDA(cudaFuncSetAttribute(conv_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles = T::num_tiles(p);
+    const int grid = tiles < flb_num_sms() ? tiles : flb_num_sms();
+    conv_resident_kernel<T><<<grid, THREADS, smem, st>>>(p);
+    return FLB_OK;
+}
+
 // tap-major conv weights of all clients as a 3-D tensor {Cin, 9*Cout, K}; box_rows x 32 boxes
 static int make_wt_map(CUtensorMap* m, const float* wt, long long ldt, int cin, int cout, int K, uint32_t box_rows, bool mn_major) {
     const uint64_t dims[3] = {(uint64_t)cin, (uint64_t)9 * cout, (uint64_t)K};
@@ -453,32 +561,36 @@ static int make_wt_map(CUtensorMap* m, const float* wt, long long ldt, int cin, 
 
 template <int CIN, int COUT>
 static int conv_fwd_t(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st) {
-    using T = ConvFwdT<CIN, COUT>;
+    constexpr bool HALO = CIN * COUT * 36 <= 150 * 1024;          // the whole weight tensor stays resident in shared memory
+    using T = typename std::conditional<HALO, ConvFwdHaloT<(HALO ? CIN : 32), (HALO ? COUT : 32)>, ConvFwdT<CIN, COUT>>::type;
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 128)) return rc;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, HALO ? 128 + 2 * (g.Wp + 1) : 128)) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, COUT, false)) return rc;
     p.a = a; p.g = g; p.z_all = z; p.boff = boff; p.pool_out = nullptr; p.pool_idx = nullptr;
-    return launch_persistent<T>(p, st);
+    if constexpr (HALO) return launch_resident<T>(p, st);
+    else return launch_persistent<T>(p, st);
 }
 // SimpleCNN conv2 with the fused bias + ReLU + max-pool epilogue (16-wide grid, 256 rows per image)
 int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* pooled, uint8_t* idx, const float* wt,
                         long long ldt, int boff, cudaStream_t st) {
-    using T = ConvFwdT<32, 64, true>;
+    using T = ConvFwdHaloT<32, 64, true>;
     if (g.Wp != 16 || g.PP() != 256 || g.Cin != 32 || g.Cout != 64) { flb_set_error("conv_fwd_pool_32_64: geometry"); return FLB_ERR_ARG; }
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 128)) return rc;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 128 + 2 * (g.Wp + 1))) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, 32, 64, a.K, 64, false)) return rc;
     p.a = a; p.g = g; p.z_all = nullptr; p.boff = boff; p.pool_out = pooled; p.pool_idx = idx;
-    return launch_persistent<T>(p, st);
+    return launch_resident<T>(p, st);
 }
 template <int CIN, int COUT>
 static int conv_dgrad_t(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
-    using T = ConvDgradT<CIN, COUT>;
+    constexpr bool HALO = CIN * COUT * 36 <= 150 * 1024;
+    using T = typename std::conditional<HALO, ConvDgradHaloT<(HALO ? CIN : 32), (HALO ? COUT : 32)>, ConvDgradT<CIN, COUT>>::type;
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 128)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, HALO ? 128 + 2 * (g.Wp + 1) : 128)) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, 32, true)) return rc;
     p.a = a; p.g = g; p.dx_all = dx;
-    return launch_persistent<T>(p, st);
+    if constexpr (HALO) return launch_resident<T>(p, st);
+    else return launch_persistent<T>(p, st);
 }
 template <int CIN, int COUT, int MTC>
 static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
