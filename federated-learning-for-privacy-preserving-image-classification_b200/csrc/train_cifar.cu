@@ -72,6 +72,7 @@ constexpr ConvGeom geom(int level, int cin, int cout) {
 }
 constexpr int PP32 = 1096, PP16 = 296, PP8 = 88;
 constexpr int kNetLdt = kNet.ldt;
+constexpr int kC1W = kNet.cw[0], kC1B = kNet.cb[0];      // conv1 offsets as scalars (usable in device code)
 
 struct CifarWs {
     float *z1, *y1, *z2, *p1;          // grid 32: conv1 out, bn1+relu, conv2 out; grid 16: pooled+dropped (conv3 input)
@@ -115,55 +116,80 @@ size_t carve(void* base, int K, int B, CifarWs* ws) {
 }
 
 // ---- conv1 (Cin = 3): the input is the raw NCHW sample; K = 27 is too thin for a tensor-core tile -----------------
-struct Conv1FwdProb {
-    static constexpr bool A_MCONTIG = false, B_NCONTIG = false;
-    flb_train_args a; ConvGeom g; float* z_all; int woff, boff;
-    const float* x; float* z; const float* w; const float* bias;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        x = a.x + (a.sample_off[client] + (long long)(*a.step_ctr) * a.B) * (3 * g.H * g.W);
-        z = z_all + (long long)client * a.B * g.PP() * g.Cout;
-        w = a.W + (long long)client * a.ld + woff;
-        bias = a.W + (long long)client * a.ld + boff;
-        M = bsz * g.PP(); N = g.Cout; Kd = 27;
-        return true;
+// Direct 3->32 stencils (one CTA per sample): thread = (output channel, pixel lane); the 27 weights sit in registers,
+// the zero-haloed input planes in shared memory (every lane of a warp reads the same input pixel: broadcast).
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float* z_all) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    __shared__ float img[3][34][35];
+    const int tid = threadIdx.x;
+    const float* x = a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072;
+    for (int i = tid; i < 3 * 34 * 34; i += 256) {
+        const int ci = i / 1156, r = (i % 1156) / 34, c = i % 34;
+        img[ci][r][c] = (r >= 1 && r <= 32 && c >= 1 && c <= 32) ? x[ci * 1024 + (r - 1) * 32 + (c - 1)] : 0.f;
     }
-    __device__ float patch(int m, int k) const {             // k = ci * 9 + tap (the order of W[co][ci][3][3])
-        const int b = m / g.PP(), r = m - b * g.PP();
-        const int h = r / g.Wp, w_ = r - h * g.Wp;
-        if (h >= g.H || w_ >= g.W) return 0.f;
-        const int ci = k / 9, tap = k - ci * 9;
-        const int hh = h + tap / 3 - 1, ww = w_ + tap % 3 - 1;
-        if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) return 0.f;
-        return x[((long long)(b * 3 + ci) * g.H + hh) * g.W + ww];
+    const int c = tid & 31, g = tid >> 5;
+    const float* W = a.W + (long long)k * a.ld;
+    float w[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) w[i] = W[kC1W + c * 27 + i];
+    const float bias = W[kC1B + c];
+    __syncthreads();
+    float* z = z_all + ((long long)k * a.B + b) * PP32 * 32;
+    for (int p = g; p < 1024; p += 8) {
+        const int h = p >> 5, wc = p & 31;
+        float acc = bias;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) acc = fmaf(w[ci * 9 + r * 3 + q], img[ci][h + r][wc + q], acc);
+        z[(h * 33 + wc) * 32 + c] = acc;
     }
-    __device__ float loadA(int m, int k) const { return patch(m, k); }
-    __device__ float loadB(int n, int k) const { return __ldg(&w[n * 27 + k]); }
-    __device__ void store(int m, int n, float acc) { z[(long long)m * g.Cout + n] = acc + bias[n]; }
-    __device__ void finish() {}
-};
+}
 
-struct Conv1WgradProb {       // dW[co][k] = sum_rows dz[row][co] * patch(row, k); column 27 = bias gradient
-    static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
-    flb_train_args a; ConvGeom g; const float* dz_all; int woff, boff;
-    Conv1FwdProb f; const float* dz; float* gw; float* gb;
-    __device__ bool setup(int client, int& M, int& N, int& Kd) {
-        const int bsz = flb_bsz(a, client);
-        if (bsz == 0) return false;
-        f.a = a; f.g = g;
-        f.x = a.x + (a.sample_off[client] + (long long)(*a.step_ctr) * a.B) * (3 * g.H * g.W);
-        dz = dz_all + (long long)client * a.B * g.PP() * g.Cout;
-        gw = a.G + (long long)client * a.ld + woff;
-        gb = a.G + (long long)client * a.ld + boff;
-        M = g.Cout; N = 28; Kd = bsz * g.PP();
-        return true;
+// dW[c][ci][tap] += sum_px dz[px][c] * x[ci][px + shift(tap)], db[c] += sum_px dz[px][c]
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(flb_train_args a, const float* dz_all) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    __shared__ float img[3][34][35];
+    __shared__ float part[8][32][29];
+    const int tid = threadIdx.x;
+    const float* x = a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072;
+    for (int i = tid; i < 3 * 34 * 34; i += 256) {
+        const int ci = i / 1156, r = (i % 1156) / 34, c = i % 34;
+        img[ci][r][c] = (r >= 1 && r <= 32 && c >= 1 && c <= 32) ? x[ci * 1024 + (r - 1) * 32 + (c - 1)] : 0.f;
     }
-    __device__ float loadA(int m, int k) const { return dz[(long long)k * g.Cout + m]; }
-    __device__ float loadB(int n, int k) const { return n == 27 ? 1.f : f.patch(k, n); }
-    __device__ void store(int m, int n, float acc) { atomicAdd(n == 27 ? &gb[m] : &gw[m * 27 + n], acc); }
-    __device__ void finish() {}
-};
+    __syncthreads();
+    const int c = tid & 31, g = tid >> 5;
+    const float* dz = dz_all + ((long long)k * a.B + b) * PP32 * 32;
+    float acc[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+    for (int p = g; p < 1024; p += 8) {
+        const int h = p >> 5, wc = p & 31;
+        const float gv = dz[(h * 33 + wc) * 32 + c];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) acc[ci * 9 + r * 3 + q] = fmaf(gv, img[ci][h + r][wc + q], acc[ci * 9 + r * 3 + q]);
+        acc[27] += gv;
+    }
+#pragma unroll
+    for (int i = 0; i < 28; ++i) part[g][c][i] = acc[i];
+    __syncthreads();
+    float* G = a.G + (long long)k * a.ld;
+    for (int e = tid; e < 32 * 28; e += 256) {
+        const int cc = e / 28, i = e % 28;
+        float v = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) v += part[gg][cc][i];
+        atomicAdd(i == 27 ? &G[kC1B + cc] : &G[kC1W + cc * 27 + i], v);
+    }
+}
 
 // ---- BatchNorm ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool real_px(const ConvGeom& g, int r) {       // r = row within the client's [B * PP] rows
@@ -191,44 +217,63 @@ __device__ __forceinline__ void bn_moments(const flb_train_args& a, const double
 }
 
 // column sums over the real pixels of client k: MODE 0: (sum z, sum z^2) -> acc[0], acc[1];
-// MODE 1: g = relu-masked upstream gradient; (sum g * xhat, sum g) -> acc[2], acc[3]
+// MODE 1: g = relu-masked upstream gradient; (sum g * xhat, sum g) -> acc[2], acc[3].
+// thread = (channel quad, row lane): 16 B loads, two rows in flight per thread.
 template <int C, int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* dy_all,
                                                         const float* y_all, double* acc, int coff) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
-    constexpr int RL = 256 / C;
-    const int tid = threadIdx.x, c = tid % C, rl = tid / C;
+    constexpr int C4 = C / 4, RL = 256 / C4;
+    const int tid = threadIdx.x, cq = tid % C4, rl = tid / C4;
     const int PP = g.PP(), rows = bsz * PP;
     const int per = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
     const long long base = (long long)k * a.B * PP * C;
-    const float* z = z_all + base;
-    float mean = 0.f, invstd = 0.f, vb;
-    if (MODE == 1) bn_moments(a, acc, k, coff + c, bsz * g.H * g.W, mean, invstd, vb);
-    float s0 = 0.f, s1 = 0.f;
-    for (int r = r0 + rl; r < r1; r += RL) {
-        if (!real_px(g, r)) continue;
-        const long long e = (long long)r * C + c;
-        if (MODE == 0) {
-            const float v = z[e];
-            s0 += v;
-            s1 = fmaf(v, v, s1);
-        } else {
-            float gv = dy_all[base + e];
-            if (y_all && !(y_all[base + e] > 0.f)) gv = 0.f;
-            s0 = fmaf(gv, (z[e] - mean) * invstd, s0);
-            s1 += gv;
-        }
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
+    const float4* dy4 = MODE == 1 ? reinterpret_cast<const float4*>(dy_all + base) : nullptr;
+    const float4* y4 = (MODE == 1 && y_all) ? reinterpret_cast<const float4*>(y_all + base) : nullptr;
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, invstd[4] = {0.f, 0.f, 0.f, 0.f};
+    if (MODE == 1) {
+        float vb;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bn_moments(a, acc, k, coff + cq * 4 + e, bsz * g.H * g.W, mean[e], invstd[e], vb);
     }
-    __shared__ float red[2][256];
-    red[0][tid] = s0; red[1][tid] = s1;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    auto row = [&](int r) {
+        if (r >= r1 || !real_px(g, r)) return;
+        const long long e = (long long)r * C4 + cq;
+        const float4 zv = z4[e];
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+        if (MODE == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s0[q] += zz[q]; s1[q] = fmaf(zz[q], zz[q], s1[q]); }
+        } else {
+            const float4 gv4 = dy4[e];
+            float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
+            if (y4) {
+                const float4 yv = y4[e];
+                if (!(yv.x > 0.f)) gv[0] = 0.f;
+                if (!(yv.y > 0.f)) gv[1] = 0.f;
+                if (!(yv.z > 0.f)) gv[2] = 0.f;
+                if (!(yv.w > 0.f)) gv[3] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s0[q] = fmaf(gv[q], (zz[q] - mean[q]) * invstd[q], s0[q]); s1[q] += gv[q]; }
+        }
+    };
+    for (int r = r0 + rl; r < r1; r += 2 * RL) { row(r); row(r + RL); }
+    __shared__ float red[8][256];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { red[q][tid] = s0[q]; red[4 + q][tid] = s1[q]; }
     __syncthreads();
     if (tid < C) {
-        for (int i = 1; i < RL; ++i) { s0 += red[0][tid + i * C]; s1 += red[1][tid + i * C]; }
-        double* A = acc + (long long)k * 4 * BN_CH + (MODE == 0 ? 0 : 2 * BN_CH) + coff + c;
-        atomicAdd(A, (double)s0);
-        atomicAdd(A + BN_CH, (double)s1);
+        const int q = tid & 3, cq2 = tid >> 2;
+        float t0 = 0.f, t1 = 0.f;
+        for (int i = 0; i < RL; ++i) { t0 += red[q][i * C4 + cq2]; t1 += red[4 + q][i * C4 + cq2]; }
+        double* A = acc + (long long)k * 4 * BN_CH + (MODE == 0 ? 0 : 2 * BN_CH) + coff + tid;
+        atomicAdd(A, (double)t0);
+        atomicAdd(A + BN_CH, (double)t1);
     }
 }
 
@@ -400,27 +445,46 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
     __syncthreads();
     const int PP = g.PP(), rows = bsz * PP;
     const long long base = (long long)k * a.B * PP * C;
-    const long long total = (long long)rows * C;
-    float bsum = 0.f;                         // this thread always sees the same channel (256 % C == 0)
+    constexpr int C4 = C / 4;
+    float4* dy4 = reinterpret_cast<float4*>(dy_all + base);
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
+    const float4* y4 = y_all ? reinterpret_cast<const float4*>(y_all + base) : nullptr;
+    const long long total = (long long)rows * C4;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};        // this thread always sees the same channel quad (256 % C4 == 0)
+    const int c = (tid % C4) * 4;
     for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
-        const int r = (int)(e / C), c = (int)(e % C);
-        float o = 0.f;
+        const int r = (int)(e / C4);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
         if (real_px(g, r)) {
-            float gv = dy_all[base + e];
-            if (y_all && !(y_all[base + e] > 0.f)) gv = 0.f;
-            const float xhat = (z_all[base + e] - s_mean[c]) * s_invstd[c];
-            o = s_c0[c] * (gv - s_c1[c] - xhat * s_c2[c]);
+            const float4 gv4 = dy4[e], zv = z4[e];
+            float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
+            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+            if (y4) {
+                const float4 yv = y4[e];
+                if (!(yv.x > 0.f)) gv[0] = 0.f;
+                if (!(yv.y > 0.f)) gv[1] = 0.f;
+                if (!(yv.z > 0.f)) gv[2] = 0.f;
+                if (!(yv.w > 0.f)) gv[3] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float xhat = (zz[q] - s_mean[c + q]) * s_invstd[c + q];
+                o[q] = s_c0[c + q] * (gv[q] - s_c1[c + q] - xhat * s_c2[c + q]);
+                bsum[q] += o[q];
+            }
         }
-        dy_all[base + e] = o;
-        bsum += o;
+        dy4[e] = make_float4(o[0], o[1], o[2], o[3]);
     }
     if (conv_boff >= 0) {                     // conv bias gradient = column sums of dz (tensor-core path; the fp32 wgrad
-        __shared__ float red[256];            // GEMM carries it as an extra column).  Exactly zero in exact arithmetic.
-        red[tid] = bsum;
+        __shared__ float red[4][256];         // GEMM carries it as an extra column).  Exactly zero in exact arithmetic.
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[q][tid] = bsum[q];
         __syncthreads();
         if (tid < C) {
-            for (int i = 1; i < 256 / C; ++i) bsum += red[tid + i * C];
-            atomicAdd(&a.G[(long long)k * a.ld + conv_boff + tid], bsum);
+            const int q = tid & 3, cq2 = tid >> 2;
+            float t = 0.f;
+            for (int i = 0; i < 256 / C4; ++i) t += red[q][i * C4 + cq2];
+            atomicAdd(&a.G[(long long)k * a.ld + conv_boff + tid], t);
         }
     }
 }
@@ -570,19 +634,19 @@ __global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, Ci
 // ---- orchestration ------------------------------------------------------------------------------------------------------
 template <int C>
 void bn_stats(const flb_train_args& a, const ConvGeom& g, const float* z, double* acc, int coff, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
     bn_reduce_kernel<C, 0><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, nullptr, nullptr, acc, coff);
 }
 template <int C>
 void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, const float* y, float* dy, double* acc, int layer, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
     bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, y, acc, kNet.coff[layer]);
     const int conv_boff = (a.precision == 1 && layer > 0) ? kNet.cb[layer] : -1;
     bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
 template <int C>
 void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float* y, const double* acc, int layer, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 4 + a.K - 1) / a.K));
+    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
     bn_relu_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
 }
 
@@ -641,10 +705,7 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     MARK("begin");
     const bool stats = !a.eval_mode;
     Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
-    {
-        Conv1FwdProb p{}; p.a = a; p.g = G1; p.z_all = ws.z1; p.woff = kNet.cw[0]; p.boff = kNet.cb[0];
-        simt::launch(p, B * PP32, 32, 1, K, st);
-    }
+    conv1_fwd_kernel<<<per_sample, 256, 0, st>>>(a, ws.z1);
     MARK("conv1_fwd");
     if (stats) bn_stats<32>(a, G1, ws.z1, ws.acc, kNet.coff[0], st);
     bn_apply<32>(a, G1, ws.z1, ws.y1, ws.acc, 0, st);
@@ -746,11 +807,7 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     MARK("conv2_bwd");
     bn_bwd<32>(a, G1, ws.z1, ws.y1, ws.d32b, ws.acc, 0, st);
     MARK("bn1_bwd");
-    {
-        Conv1WgradProb p{}; p.a = a; p.g = G1; p.dz_all = ws.d32b; p.woff = kNet.cw[0]; p.boff = kNet.cb[0];
-        const int splits = max(1, min(64, flb_num_sms() * 2 / K));
-        simt::launch(p, 32, 28, splits, K, st);
-    }
+    conv1_wgrad_kernel<<<per_sample, 256, 0, st>>>(a, ws.d32b);
     MARK("conv1_wgrad");
     if (cx.rc) return cx.rc;
     FLB_LAUNCH_CHECK();
