@@ -57,33 +57,63 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons sampled DURING the timed regions: NVML when importable (sub-millisecond per sample),
+    else the nvidia-smi query of the profiling recipe."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag = index, [], False      # rows: [sm_mhz, sm_max_mhz, hw, hw_thermal, sw_thermal, sw_power]
+
+    def _nvml_loop(self) -> bool:
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remapping: torch index -> NVML handle through the PCI bus id
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(N.nvmlDeviceGetCount()):
+                    hh = N.nvmlDeviceGetHandleByIndex(i)
+                    if int(N.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                        h = hh
+                        break
+            if h is None:
+                h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = [N.nvmlClocksEventReasonHwSlowdown, N.nvmlClocksEventReasonHwThermalSlowdown,
+                    N.nvmlClocksEventReasonSwThermalSlowdown, N.nvmlClocksEventReasonSwPowerCap]
+            while not self.stop_flag:
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx] + [bool(r & b) for b in bits])
+                time.sleep(0.002)
+            return True
+        except Exception:
+            return False
 
     def run(self):
+        if self._nvml_loop():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [v.strip() for v in out.split(",")]
+                if len(c) >= 6 and c[0].isdigit():
+                    self.rows.append([int(c[0]), int(c[1]) if c[1].isdigit() else None] + [v.lower().startswith("active") for v in c[2:6]])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows)}
 
 
 def cpu_baseline_run(n_clients: int, threads: int, rounds: int = 1, model: str = "simple_cnn"):
@@ -121,8 +151,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: SimpleCNN MNIST-shaped, update-level DP, FedAvg; each step = 2 rounds of 10 clients",
-                       "clients_per_gpu": CLIENTS_PER_GPU},
+            "config": {"workload": WORKLOADS["mnist_dp"]["desc"], "clients": CLIENTS_PER_GPU, "dp_mode": "update", "precision": "fp32",
+                       "note": "CPU restatement of the reference path (oracle/round.py) on all host threads; each step = 2 rounds "
+                               "of the 10-client workload (bounded sample); dropout off (identity at p=0 costs the same)"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -208,7 +239,6 @@ def main():
     sampler.start()
     ms = timed_rounds(args.steps)
     barrier()
-    sampler.stop_flag = True
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -220,6 +250,7 @@ def main():
     barrier()
     ms_e2e = timed_rounds(args.steps, e2e=True)
     barrier()
+    sampler.stop_flag = True          # clocks sampled across both timed regions (device-resident and end-to-end)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -244,19 +275,45 @@ def main():
     top = max(acc, key=acc.get)
     pk = peaks()
     K_local, B = len(eng.client_ids), 32
-    # algorithmic FLOPs of the GEMM-shaped kernels per launch (all resident clients, full batch)
+    P = eng.layout.P
+    # ALGORITHMIC work per launch (all resident clients, full batches): FLOPs of the GEMM-shaped kernels,
+    # bytes of the memory-bound ones (every operand once)
     flops = GEMM_FLOPS[MODEL]
+    hbm_bytes = {"optimizer": 28.0 * P * K_local}                       # Adam: read g, m, v, w; write m, v, w
+    if MODEL == "simple_cnn":
+        hbm_bytes.update({"conv1_fwd_pool": (3136 + 25088 + 6272.0) * B * K_local,       # x in; pooled NHWC + argmax out
+                          "unpool2": (3136 * 9 + 256 * 64 * 4.0) * B * K_local,           # da2, a2, idx2 in; dz2 grid out
+                          "conv1_wgrad": (3136 + 25088 * 2 + 6272.0) * B * K_local})      # x, a1p, da1p, idx1 in
     tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")           # dram bytes per launch from `ncu --set full`
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(MODEL, {}).get(str(K_local), {}).get(top)
     if top in flops:
         ach = flops[top] * B * K_local / (acc[top] * 1e-3) / 1e12
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                "traffic": None, "peak_source": "0.5 x sustained bf16 of " + pk["source"] + " (TF32 = half bf16 rate)"}
+                "traffic": traffic, "peak_source": "0.5 x sustained bf16 of " + pk["source"] + " (TF32 = half the bf16 rate)"}
+    elif top in hbm_bytes:
+        ach = hbm_bytes[top] / (acc[top] * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": traffic, "peak_source": pk["source"], "algorithmic_bytes_per_launch": hbm_bytes[top]}
     else:
-        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": traffic}
     roof["share_of_step"] = acc[top] / step_ms
+    roof["how"] = ("CUDA events after every kernel of one training step, launched eagerly on the launch stream right after the "
+                   "timed region (the timed rounds replay a CUDA graph, which cannot be instrumented per kernel); mean of 5 steps")
     roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in acc.items()}
+    # the other kernels against their own rooflines, for the record
+    others = {}
+    for name, ms_k in acc.items():
+        if name in flops:
+            others[name] = {"TFLOP/s": round(flops[name] * B * K_local / (ms_k * 1e-3) / 1e12, 2), "frac_tensor": round(flops[name] * B * K_local / (ms_k * 1e-3) / 1e12 / tf32_peak, 4)}
+        elif name in hbm_bytes:
+            others[name] = {"GB/s": round(hbm_bytes[name] / (ms_k * 1e-3) / 1e9, 1), "frac_hbm": round(hbm_bytes[name] / (ms_k * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
+    roof["per_kernel"] = others
 
-    launches_round = tr.launches_per_epoch() + (2 if args.dp_mode == "update" else 0) + 1
+    # our kernels per round: the epoch's launch sequence + update-level DP (norm, clip+noise) + FedAvg (vector body, scalar tail)
+    launches_round = tr.launches_per_epoch() + (2 if args.dp_mode == "update" else 0) + 2
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",

@@ -48,20 +48,22 @@ constexpr int PP2 = 256;     // conv2 runs on a 16x16 padded grid (14x14 real)
 constexpr int WP2 = 16;
 
 // ------------------------------------------------------------------------------------------------
-// conv1: direct stencil, one CTA per (sample, client)
+// conv1: direct stencil fused with bias + ReLU + 2x2 max-pool; two CTAs per (sample, client), one per half image
+// (pooled rows 0-6 / 7-13), so that 2 * B * K CTAs cover the GPU even at 10 clients.
 __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, SimpleCnnWs ws) {
-    const int b = blockIdx.x, k = blockIdx.y;
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
-    __shared__ float img[30][31];
+    __shared__ float img[16][31];            // input rows 14*half - 1 .. 14*half + 14 with a zero halo
     __shared__ float w[32][9];
     __shared__ float bias[32];
     const int tid = threadIdx.x;
     const float* W = a.W + (long long)k * a.ld;
     const long long s = a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b;
     const float* x = a.x + s * 784;
-    for (int i = tid; i < 900; i += 256) {
-        const int r = i / 30, c = i % 30;
-        img[r][c] = (r >= 1 && r <= 28 && c >= 1 && c <= 28) ? x[(r - 1) * 28 + (c - 1)] : 0.f;
+    const int r0 = 14 * half - 1;
+    for (int i = tid; i < 16 * 30; i += 256) {
+        const int r = i / 30, c = i % 30, gr = r0 + r;
+        img[r][c] = (gr >= 0 && gr < 28 && c >= 1 && c <= 28) ? x[gr * 28 + (c - 1)] : 0.f;
     }
     for (int i = tid; i < 288; i += 256) w[i / 9][i % 9] = W[Off::c1w + i];
     if (tid < 32) bias[tid] = W[Off::c1b + tid];
@@ -74,13 +76,13 @@ __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, S
     const long long kb = (long long)k * a.B + b;
     float* outp = ws.a1p + kb * (PP2 * 32);
     uint8_t* idx = ws.idx1 + kb * (196 * 32);
-    for (int pp = g; pp < 196; pp += 8) {
-        const int ph = pp / 14, pw = pp % 14;
+    for (int pl = g; pl < 98; pl += 8) {
+        const int phl = pl / 14, pw = pl % 14, ph = half * 7 + phl;
         float p[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[i][j] = img[2 * ph + i][2 * pw + j];
+            for (int j = 0; j < 4; ++j) p[i][j] = img[2 * phl + i][2 * pw + j];
         float best = -INFINITY;
         int bi = 0;
 #pragma unroll
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, S
                 if (v > best) { best = v; bi = i * 2 + j; }
             }
         outp[(ph * WP2 + pw) * 32 + c] = fmaxf(best, 0.f);
-        idx[pp * 32 + c] = (uint8_t)bi;
+        idx[(ph * 14 + pw) * 32 + c] = (uint8_t)bi;
     }
 }
 
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(flb_train_args a, float
 // max-unpool + ReLU backward into the padded NHWC dz2 grid (every position written, pads = 0).  The pooled-side
 // arrays are NCHW-flattened (fc1's input order) and the grid is NHWC: they are staged through shared memory so that
 // both the global reads and the 16 B global writes are coalesced.  grid (2 * B, K): one CTA per half image (8 grid rows).
-__global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCnnWs ws) {
+__global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCnnWs ws, int bias_grad) {
     const int b = blockIdx.x >> 1, half = blockIdx.x & 1, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
@@ -307,6 +309,13 @@ __global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCn
         s_code[c][j] = idx[src];
     }
     __syncthreads();
+    // conv2 bias gradient (tensor-core wgrad path, no per-sample clipping): every pooling window routes its upstream
+    // gradient to exactly one conv2 output, so sum_px dz2[px][c] is the sum of this staged array over the windows
+    if (bias_grad && threadIdx.x < 64) {
+        float t = 0.f;
+        for (int j = 0; j < nph * 7; ++j) t += s_val[threadIdx.x][j];
+        atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + threadIdx.x], t);
+    }
     float* dz = ws.z2 + kb * (PP2 * 64) + half * (8 * WP2 * 64);
     for (int e = threadIdx.x; e < 8 * WP2 * 16; e += 256) {        // (grid position, channel quad)
         const int c = (e & 15) * 4, pos = e >> 4, hl = pos >> 4, w = pos & 15, h = half * 8 + hl;
@@ -322,10 +331,12 @@ __global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCn
 }
 
 // conv1 weight + bias gradient of one sample (max-unpool + ReLU backward folded in): 32 x (9 + 1) values.
-// dp_mode 0: atomically added into G.  dp_mode 1 (norm pass): stored per sample in g1ps and its squared norm
-// added to norm2; the clipped sum is formed later by conv1_ps_reduce_kernel.
+// dp_mode 0 (per_sample = 0): two CTAs per sample (pooled rows 0-6 / 7-13) atomically add their halves into G.
+// dp_mode 1 (norm pass, per_sample = 1): one CTA per sample; the values are stored per sample in g1ps and their squared
+// norm added to norm2; the clipped sum is formed later by conv1_ps_reduce_kernel.
 __global__ void __launch_bounds__(256) conv1_bwd_kernel(flb_train_args a, SimpleCnnWs ws, int per_sample) {
-    const int b = blockIdx.x, k = blockIdx.y;
+    const int nhalf = per_sample ? 1 : 2;
+    const int b = blockIdx.x / nhalf, half = blockIdx.x % nhalf, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     __shared__ float img[30][31];
     __shared__ float part[8][32][10];
@@ -336,26 +347,44 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(flb_train_args a, Simple
         const int r = i / 30, c = i % 30;
         img[r][c] = (r >= 1 && r <= 28 && c >= 1 && c <= 28) ? x[(r - 1) * 28 + (c - 1)] : 0.f;
     }
-    __syncthreads();
     const int c = tid & 31, g = tid >> 5;
     const long long kb = (long long)k * a.B + b;
     const float* da1 = ws.da1p + kb * (PP2 * 32);
     const float* a1 = ws.a1p + kb * (PP2 * 32);
     const uint8_t* idx = ws.idx1 + kb * (196 * 32);
+    const int pp0 = per_sample ? 0 : half * 98, npp = per_sample ? 196 : 98;
+    // all of this thread's gradient values first (independent loads in flight together), then the stencil updates
+    constexpr int MAXIT = 25;
+    float gvv[MAXIT];
+    int sel[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int pl = g + it * 8;
+        gvv[it] = 0.f; sel[it] = 0;
+        if (pl < npp) {
+            const int pp = pp0 + pl, o = ((pp / 14) * WP2 + pp % 14) * 32 + c;
+            const float av = a1[o], dv = da1[o];
+            gvv[it] = av > 0.f ? dv : 0.f;
+            sel[it] = idx[pp * 32 + c];
+        }
+    }
+    __syncthreads();
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-    for (int pp = g; pp < 196; pp += 8) {
-        const int ph = pp / 14, pw = pp % 14;
-        const int o = (ph * WP2 + pw) * 32 + c;
-        const float gv = a1[o] > 0.f ? da1[o] : 0.f;
-        const int sel = idx[pp * 32 + c];
-        const int y0 = 2 * ph + (sel >> 1), x0 = 2 * pw + (sel & 1);     // top-left of the 3x3 window in img (halo 1)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+    for (int it = 0; it < MAXIT; ++it) {
+        const int pl = g + it * 8;
+        if (pl < npp) {
+            const int pp = pp0 + pl, ph = pp / 14, pw = pp % 14;
+            const float gv = gvv[it];
+            const int y0 = 2 * ph + (sel[it] >> 1), x0 = 2 * pw + (sel[it] & 1);     // top-left of the 3x3 window in img (halo 1)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) acc[r * 3 + q] = fmaf(gv, img[y0 + r][x0 + q], acc[r * 3 + q]);
-        acc[9] += gv;
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) acc[r * 3 + q] = fmaf(gv, img[y0 + r][x0 + q], acc[r * 3 + q]);
+            acc[9] += gv;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) part[g][c][i] = acc[i];
@@ -429,7 +458,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     const dim3 per_sample(B, K);
     FLB_CUDA(cudaMemsetAsync(ws.hpre, 0, sizeof(float) * (size_t)K * B * 128, st));
     MARK("begin");
-    conv1_fwd_pool_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    conv1_fwd_pool_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
     MARK("conv1_fwd_pool");
     const int tcm = tc_mask_of(a);
     if (tcm & TC_CONV2_FWD) {          // bias + ReLU + max-pool fused into the GEMM epilogue: z2 is never written
@@ -487,9 +516,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
     };
     auto wgrads_conv2 = [&](cudaStream_t st) -> int {
         if (tcm & TC_CONV2_WGRAD) {
-            conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, coef != nullptr);
+            if (coef) conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, 1);      // else: fused into unpool2
             if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
             FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));
+            MARK("conv2_bias_grad");
             if (int rc = tc::conv_wgrad(a, kConv2, ws.a1p, ws.z2, ws.gt, kLdt, st)) return rc;
         } else {
             ConvWgradProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.coef_all = coef;
@@ -514,7 +544,8 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         simt::launch(p, B, 3136, 1, K, st);
     }
     MARK("fc1_dgrad");
-    unpool2_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
+    const int fused_bias = ((tcm & TC_CONV2_WGRAD) && a.dp_mode == 0) ? 1 : 0;
+    unpool2_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws, fused_bias);
     MARK("unpool2");
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[1], st));
@@ -548,7 +579,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         if (int rc = wgrads_conv2(st)) return rc;
     }
     if (a.dp_mode == 1) conv1_ps_reduce_kernel<<<K, 320, 0, st>>>(a, ws);
-    else conv1_bwd_kernel<<<per_sample, 256, 0, st>>>(a, ws, 0);
+    else conv1_bwd_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws, 0);
     MARK("conv1_wgrad");
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
@@ -580,8 +611,8 @@ int forward(const flb_train_args& a, cudaStream_t st) {
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
 int step_launches(const flb_train_args& a) {
     const int m = tc_mask_of(a);
-    int n = 12 + ((m & TC_CONV2_WGRAD) ? 1 : 0) - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
-    if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 1 : 0);
+    int n = 12 - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less; conv2 bias gradient: fused into unpool2                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
+    if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 2 : 0);
     return n;
 }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {

@@ -227,7 +227,8 @@ class BatchedClientTrainer:
         return out
 
     def launches_per_epoch(self) -> int:
-        return 1 + self.max_steps() * int(L.load().flb_train_step_launches(C.byref(self.args)))
+        prologue = 2 if self.precision == "tf32" else 1           # begin_epoch (+ the tap-major weight repack)
+        return prologue + self.max_steps() * int(L.load().flb_train_step_launches(C.byref(self.args)))
 
     def train(self, epochs: int, learning_rate: float = 0.001, optimizer_type: str = "adam"):
         """One call = one ``train_local_model`` for every client: fresh optimizer state (training.py:89), ``epochs``
