@@ -189,6 +189,8 @@ def main():
     pg = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     n_clients = wl["total_clients"] or wl["clients_per_gpu"] * world
