@@ -84,6 +84,7 @@ __device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, c
         tab_lo = min(tab_lo, tab.woff[i]);
         tab_hi = max(tab_hi, tab.woff[i] + tab.cout[i] * tab.cin[i] * 9);
     }
+#pragma unroll 2
     for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
         const int p0 = c4 * 4;
         const bool whole = p0 + 3 < P;           // rows are 128 B aligned (ld % 32 == 0): 16 B vector access per quad
