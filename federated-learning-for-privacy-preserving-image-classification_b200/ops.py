@@ -171,3 +171,47 @@ def q8_dequantize(q: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, seg_of
         L.call("flb_q8_dequantize", L.ptr(q), ldq, L.ptr(seg_off), L.ptr(scale), L.ptr(zp), L.ptr(out), ldq, K, Lyr, P,
                L.stream_ptr(q.device))
     return out
+
+
+def topk_count(n: int, sparsity_ratio: float) -> int:
+    """k = int(n * (1 - sparsity)), at least 1 (src/shared/compression.py:333-338)."""
+    k = int(n * (1 - max(0.0, min(1.0, sparsity_ratio))))
+    return k if k > 0 else 1
+
+
+def topk_select(x: torch.Tensor, seg_off: torch.Tensor, kk: Sequence[int], P: Optional[int] = None):
+    """Per-(client, layer) top-k by |x| over the K client rows.  Returns (idx int32 [K, ldk] layer-relative,
+    val fp32 [K, ldk], out_off int64 [L+1] on the device, kk int32 [L] on the device)."""
+    L.require_cuda_f32(x, "x")
+    L.ensure_device(x.device)
+    K, ld = x.shape[0], _row_stride(x)
+    dev = x.device
+    Lyr = seg_off.numel() - 1
+    if len(kk) != Lyr:
+        raise L.FlbError(f"topk_select: {len(kk)} counts for {Lyr} layers")
+    offs = [0]
+    for v in kk:
+        offs.append(offs[-1] + int(v))
+    ldk = max(offs[-1], 1)
+    kk_t = torch.tensor([int(v) for v in kk], dtype=torch.int32, device=dev)
+    off_t = torch.tensor(offs, dtype=torch.int64, device=dev)
+    idx = torch.empty((K, ldk), dtype=torch.int32, device=dev)
+    val = torch.empty((K, ldk), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.call("flb_topk_select", L.ptr(x), ld, L.ptr(seg_off), L.ptr(kk_t), L.ptr(off_t), L.ptr(idx), L.ptr(val), ldk, K, Lyr,
+               L.stream_ptr(dev))
+    return idx, val, off_t, kk_t
+
+
+def topk_scatter(idx: torch.Tensor, val: torch.Tensor, seg_off: torch.Tensor, kk_t: torch.Tensor, off_t: torch.Tensor,
+                 P: int, ld: Optional[int] = None) -> torch.Tensor:
+    """Dense [K, ld] rows rebuilt from the (index, value) pairs (zeros elsewhere)."""
+    dev = idx.device
+    L.ensure_device(dev)
+    K, ldk = idx.shape[0], _row_stride(idx)
+    ld = ld or (P + 31) // 32 * 32
+    out = torch.empty((K, ld), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.call("flb_topk_scatter", L.ptr(idx), L.ptr(val), ldk, L.ptr(seg_off), L.ptr(kk_t), L.ptr(off_t), L.ptr(out), ld, K,
+               seg_off.numel() - 1, P, L.stream_ptr(dev))
+    return out

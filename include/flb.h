@@ -62,6 +62,17 @@ int flb_q8_quantize(const float* x, long long ld, const long long* seg_off, uint
 int flb_q8_dequantize(const uint8_t* q, long long ldq, const long long* seg_off, const float* scale,
                       const float* zp, float* out, long long ld, int K, int L, long long P, void* stream);
 
+/* ---- top-k sparsification: src/shared/compression.py:327-365 (TopKSparsificationCompressor) ----------------
+ * For every (client c, layer l): the kk[l] entries of largest |x| of x[c*ld + seg_off[l] .. seg_off[l+1]) as
+ * (index relative to the layer start, value) pairs at [c*ldk + out_off[l] ..), in INDEX order; ties at the threshold keep
+ * the lowest indices.  out_off = exclusive prefix sums of kk (L+1 entries), ldk >= out_off[L].  Exact radix select. */
+int flb_topk_select(const float* x, long long ld, const long long* seg_off, const int* kk,
+                    const long long* out_off, int* idx_out, float* val_out, long long ldk,
+                    int K, int L, void* stream);
+/* inverse (_desparsify_tensor :346-365): dense[c, 0..P) = 0, then dense[c, seg_off[l] + idx] = val */
+int flb_topk_scatter(const int* idx, const float* val, long long ldk, const long long* seg_off, const int* kk,
+                     const long long* out_off, float* dense, long long ld, int K, int L, long long P, void* stream);
+
 /* ---- batched local training: src/shared/training.py:60-212 (LocalTrainer._train_epoch), ------------------
  *      models src/shared/models_pytorch.py:59-97 (SimpleCNN), optimizers training.py:244-255 ----------------
  * One call advances EVERY resident client by one minibatch step (zero_grad -> forward -> mean cross-entropy ->
