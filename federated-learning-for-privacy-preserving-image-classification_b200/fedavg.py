@@ -106,6 +106,19 @@ class FedAvgAggregator:
             if not old_model or not new_model:
                 return 1.0
             diff = norm = 0.0
+            names = [n for n in new_model.model_weights if n in old_model.model_weights]
+            nw = [new_model.model_weights[n] for n in names]
+            ow = [old_model.model_weights[n] for n in names]
+            if names and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == nw[0].device
+                             and t.shape == o.shape for t, o in zip(nw + ow, ow + nw)):
+                dev = nw[0].device                      # one launch + one read instead of two norms and syncs per layer
+                offs = [0]
+                for t in nw:
+                    offs.append(offs[-1] + t.numel())
+                sums = ops.delta_norms(torch.tensor([t.data_ptr() for t in nw], dtype=torch.int64).to(dev),
+                                       torch.tensor([t.data_ptr() for t in ow], dtype=torch.int64).to(dev),
+                                       torch.tensor(offs, dtype=torch.int64, device=dev), offs[-1], dev).sqrt().sum(0).cpu().tolist()
+                return min(1.0, max(0.0, sums[0] / sums[1] if sums[1] > 0 else 0.0))
             for name, new_w in new_model.model_weights.items():
                 if name in old_model.model_weights:
                     diff += torch.norm(new_w - old_model.model_weights[name].to(new_w.device)).item()

@@ -215,3 +215,32 @@ def topk_scatter(idx: torch.Tensor, val: torch.Tensor, seg_off: torch.Tensor, kk
         L.call("flb_topk_scatter", L.ptr(idx), L.ptr(val), ldk, L.ptr(seg_off), L.ptr(kk_t), L.ptr(off_t), L.ptr(out), ld, K,
                seg_off.numel() - 1, P, L.stream_ptr(dev))
     return out
+
+
+def update_stats(ptr_table: torch.Tensor, seg_off: torch.Tensor, K: int, P: int, device):
+    """One pass over K x L tensors addressed by a device pointer table: (max|x| fp32 [K, L], flags int32 [K, L] with
+    bit 0 = NaN present, bit 1 = Inf present)."""
+    L.ensure_device(device)
+    Lyr = seg_off.numel() - 1
+    mx = torch.empty((K, Lyr), dtype=torch.float32, device=device)
+    fl = torch.empty((K, Lyr), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        L.call("flb_update_stats", L.ptr(ptr_table), L.ptr(seg_off), L.ptr(mx), L.ptr(fl), K, Lyr, P, L.stream_ptr(device))
+    return mx, fl
+
+
+def rows_ptr_table(rows: torch.Tensor, offsets: Sequence[int]) -> torch.Tensor:
+    """Pointer table of the layers of every row of a [K, ld] matrix (for update_stats / delta_norms)."""
+    base, stride = rows.data_ptr(), _row_stride(rows) * 4
+    return torch.tensor([base + k * stride + 4 * int(o) for k in range(rows.shape[0]) for o in offsets],
+                        dtype=torch.int64).to(rows.device)
+
+
+def delta_norms(new_ptrs: torch.Tensor, old_ptrs: torch.Tensor, seg_off: torch.Tensor, P: int, device) -> torch.Tensor:
+    """Per layer (sum (new - old)^2, sum new^2) in double: [L, 2] on the device."""
+    L.ensure_device(device)
+    Lyr = seg_off.numel() - 1
+    out = torch.empty((Lyr, 2), dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        L.call("flb_delta_norms", L.ptr(new_ptrs), L.ptr(old_ptrs), L.ptr(seg_off), L.ptr(out), Lyr, P, L.stream_ptr(device))
+    return out

@@ -1,6 +1,7 @@
-"""Host-side update validation, same checks as the reference's ``ModelUpdateValidator``
-(src/shared/validation.py:21-111) and ``validate_model_compatibility`` (:256-282).  Pure bookkeeping
-around three reductions per tensor; the fused one-pass device version is SURVEY.md section 8(f) row 1."""
+"""Update validation, same checks and messages as the reference's ``ModelUpdateValidator``
+(src/shared/validation.py:21-111) and ``validate_model_compatibility`` (:256-282).  When the update's tensors live on
+a CUDA device the three reductions per tensor (isnan / isinf / abs().max(), each a pass and a host sync upstream) are
+ONE launch of ``flb_update_stats`` over all layers and one device -> host read."""
 from __future__ import annotations
 
 from datetime import datetime, timedelta
@@ -47,6 +48,26 @@ class ModelUpdateValidator:
         for name, t in weights.items():
             if not isinstance(t, torch.Tensor):
                 raise ValidationError(f"Weight for layer {name} must be a torch.Tensor")
+        ts = list(weights.values())
+        if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == ts[0].device for t in ts):
+            from . import ops
+            dev = ts[0].device
+            offs = [0]
+            for t in ts:
+                offs.append(offs[-1] + t.numel())
+            table = torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64).to(dev)
+            mx, fl = ops.update_stats(table, torch.tensor(offs, dtype=torch.int64, device=dev), 1, offs[-1], dev)
+            mx, fl = mx[0].cpu().tolist(), fl[0].cpu().tolist()          # the one read
+            for name, m, f in zip(weights, mx, fl):
+                if f & 1:
+                    raise ValidationError(f"NaN values found in layer {name}")
+                if f & 2:
+                    raise ValidationError(f"Infinite values found in layer {name}")
+                if m > self.max_weight_magnitude:
+                    raise ValidationError(
+                        f"Weight magnitude {m} exceeds maximum {self.max_weight_magnitude} in layer {name}")
+            return
+        for name, t in weights.items():
             if torch.isnan(t).any():
                 raise ValidationError(f"NaN values found in layer {name}")
             if torch.isinf(t).any():

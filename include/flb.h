@@ -62,6 +62,17 @@ int flb_q8_quantize(const float* x, long long ld, const long long* seg_off, uint
 int flb_q8_dequantize(const uint8_t* q, long long ldq, const long long* seg_off, const float* scale,
                       const float* zp, float* out, long long ld, int K, int L, long long P, void* stream);
 
+/* ---- one-pass update validation / convergence reductions --------------------------------------
+ * src/shared/validation.py:72-91 (isnan / isinf / abs().max() per tensor: 3 passes + 3 syncs each upstream) and
+ * src/aggregation/fedavg.py:144-190 (per-layer ||new - old||, ||new||).
+ * ptrs[k*L + l] = device pointer of tensor l of client k (seg_off gives the element counts).
+ * max_abs[k*L + l] = max |x| (NaN ignored), flags[k*L + l] = 1 if any NaN | 2 if any Inf. */
+int flb_update_stats(const float* const* ptrs, const long long* seg_off, float* max_abs, unsigned int* flags,
+                     int K, int L, long long P, void* stream);
+/* out[2l] = sum (new_l - old_l)^2, out[2l+1] = sum new_l^2, in double */
+int flb_delta_norms(const float* const* new_ptrs, const float* const* old_ptrs, const long long* seg_off,
+                    double* out, int L, long long P, void* stream);
+
 /* ---- top-k sparsification: src/shared/compression.py:327-365 (TopKSparsificationCompressor) ----------------
  * For every (client c, layer l): the kk[l] entries of largest |x| of x[c*ld + seg_off[l] .. seg_off[l+1]) as
  * (index relative to the layer start, value) pairs at [c*ldk + out_off[l] ..), in INDEX order; ties at the threshold keep
