@@ -65,20 +65,23 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False      # rows: [sm_mhz, sm_max_mhz, hw, hw_thermal, sw_thermal, sw_power]
+        self.nvml_error = None
 
     def _nvml_loop(self) -> bool:
         try:
             import pynvml as N
             N.nvmlInit()
             # CUDA_VISIBLE_DEVICES remapping: torch index -> NVML handle through the PCI bus id
-            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
             h = None
-            if bus is not None:
+            try:
+                bus = int(torch.cuda.get_device_properties(self.index).pci_bus_id)
                 for i in range(N.nvmlDeviceGetCount()):
                     hh = N.nvmlDeviceGetHandleByIndex(i)
-                    if int(N.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                    if int(N.nvmlDeviceGetPciInfo(hh).bus) == bus:
                         h = hh
                         break
+            except Exception:
+                h = None
             if h is None:
                 h = N.nvmlDeviceGetHandleByIndex(self.index)
             mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
@@ -89,7 +92,8 @@ class ClockSampler(threading.Thread):
                 self.rows.append([N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx] + [bool(r & b) for b in bits])
                 time.sleep(0.002)
             return True
-        except Exception:
+        except Exception as e:           # fall back to nvidia-smi; keep the reason for the record
+            self.nvml_error = f"{type(e).__name__}: {e}"
             return False
 
     def run(self):
@@ -110,7 +114,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "nvml_error": self.nvml_error}
         sm = sorted(r[0] for r in self.rows)
         reasons = [n for i, n in enumerate(self.NAMES) if any(r[2 + i] for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows)}
@@ -203,9 +207,12 @@ def main():
     w0 = ModelFactory.create_model(MODEL).get_model_weights()
     eng.set_global_weights(w0)
     host = [synthetic_client_data(MODEL, i) for i in eng.client_ids]
-    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
     sizes_all = [synthetic_num_samples(MODEL, i) for i in range(n_clients)]
-    eng.load_data([h[0] for h in host], [h[1] for h in host], sizes_all)
+    # the round's inputs as the caller holds them: this rank's clients back to back in pinned host memory
+    x_host = torch.cat([h[0].reshape(h[0].shape[0], -1) for h in host]).pin_memory()
+    y_host = torch.cat([h[1] for h in host]).to(torch.int32).pin_memory()
+    gw_host = torch.empty(eng.layout.P, dtype=torch.float32).pin_memory()
+    eng.load_packed(x_host, y_host, sizes_all)
     samples_round_local = eng.samples_per_round()
     samples_round = sum(sizes_all)
 
@@ -224,9 +231,9 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:
-                eng.load_data([h[0] for h in host], [h[1] for h in host], sizes_all)       # H2D from pinned memory
+                eng.load_packed(x_host, y_host, sizes_all)                                  # H2D from pinned memory
                 out = eng.run_round(read_metrics=True)                                      # D2H: losses / accuracies
-                gw = eng.global_row[:eng.layout.P].cpu()                                    # D2H: the aggregated model
+                gw_host.copy_(eng.global_row[:eng.layout.P], non_blocking=True)             # D2H: the aggregated model
             else:
                 eng.run_round(read_metrics=False)
             e1.record()
@@ -253,6 +260,7 @@ def main():
     ms_e2e = timed_rounds(args.steps, e2e=True)
     barrier()
     sampler.stop_flag = True          # clocks sampled across both timed regions (device-resident and end-to-end)
+    sampler.join(timeout=10)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

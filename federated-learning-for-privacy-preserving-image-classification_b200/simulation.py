@@ -121,6 +121,11 @@ class FederatedRoundEngine:
         self.trainer.load_data(xs, ys)
         self.num_samples_all = [int(n) for n in num_samples_all]
 
+    def load_packed(self, x_all: torch.Tensor, y_all: torch.Tensor, num_samples_all: Sequence[int]) -> None:
+        """This rank's clients concatenated (pinned host memory recommended): two H2D copies per round."""
+        self.trainer.load_packed(x_all, y_all, [int(num_samples_all[i]) for i in self.client_ids])
+        self.num_samples_all = [int(n) for n in num_samples_all]
+
     # ---- one round -----------------------------------------------------------------------------------------
     def fedavg_weights(self) -> List[float]:
         """n_k * E / sum(n * E) over ALL clients (fedavg.py:247-256 with num_samples = samples_processed)."""

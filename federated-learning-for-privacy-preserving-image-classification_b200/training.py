@@ -132,22 +132,44 @@ class BatchedClientTrainer:
                 raise L.FlbError(f"load_data: sample shape {tuple(x.shape[1:])} does not match {self.model_name}")
             if y.shape[0] != x.shape[0]:
                 raise L.FlbError("load_data: data / target length mismatch")
-        dev = self.device
-        total = sum(ns)
-        self.x = torch.empty((max(total, 1), self.sample_numel), dtype=torch.float32, device=dev)
-        self.y = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        self._reserve(ns)
         off = 0
-        offs = []
         for x, y, n in zip(xs, ys, ns):
-            offs.append(off)
             if n:
                 self.x[off:off + n].copy_(x.reshape(n, -1), non_blocking=True)
-                self.y[off:off + n].copy_(y.to(torch.int32), non_blocking=True)
+                self.y[off:off + n].copy_(y, non_blocking=True)          # dtype conversion (int64 -> int32) on the device
             off += n
-        self.sample_off = torch.tensor(offs, dtype=torch.int64).to(dev)
-        self.nsamples = torch.tensor(ns, dtype=torch.int32).to(dev)
-        self.n_host = ns
+
+    def _reserve(self, ns: Sequence[int]) -> None:
+        """Device sample store for these per-client counts; buffers (and therefore the captured graph) are reused
+        while the counts stay the same."""
+        ns = [int(n) for n in ns]
+        dev, total = self.device, sum(ns)
+        if self.x is None or self.x.shape[0] != max(total, 1):
+            self.x = torch.empty((max(total, 1), self.sample_numel), dtype=torch.float32, device=dev)
+            self.y = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        if ns != self.n_host:
+            offs = [0]
+            for n in ns[:-1]:
+                offs.append(offs[-1] + n)
+            self.sample_off = torch.tensor(offs, dtype=torch.int64).to(dev)
+            self.nsamples = torch.tensor(ns, dtype=torch.int32).to(dev)
+            self.n_host = ns
         self.h2d_bytes = total * (self.sample_numel * 4 + 4)
+
+    def load_packed(self, x_all: torch.Tensor, y_all: torch.Tensor, ns: Sequence[int]) -> None:
+        """Same as ``load_data`` for inputs that are already concatenated client after client: ``x_all`` [sum N, C*H*W]
+        (or [sum N, C, H, W]) fp32 and ``y_all`` [sum N] int32, ideally in pinned host memory -- two asynchronous
+        host -> device copies for the whole round instead of two per client."""
+        if len(ns) != self.K:
+            raise L.FlbError(f"load_packed: expected {self.K} clients, got {len(ns)}")
+        total = sum(int(n) for n in ns)
+        if x_all.shape[0] != total or y_all.shape[0] != total or x_all.numel() != total * self.sample_numel:
+            raise L.FlbError("load_packed: x_all / y_all do not match the per-client counts")
+        self._reserve(ns)
+        if total:
+            self.x[:total].copy_(x_all.reshape(total, -1), non_blocking=True)
+            self.y[:total].copy_(y_all, non_blocking=True)
 
     def configure_dp(self, mode: str = "none", max_grad_norm: float = 1.0, sigma: float = 0.0,
                      z: Optional[torch.Tensor] = None) -> None:
