@@ -57,10 +57,11 @@ __global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P,
 
 __device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, const TcConvTab& tab, int k, int bsz) {
     const int t = a.tcount[k] + 1;
-    float* W = a.W + (long long)k * a.ld;
-    float* G = a.G + (long long)k * a.ld;
-    float* M = a.M + (long long)k * a.ld;
-    float* V = a.V + (long long)k * a.ld;
+    // distinct buffers (rows of four different matrices): __restrict__ lets the loads of the next quad fly past the stores
+    float* __restrict__ W = a.W + (long long)k * a.ld;
+    float* __restrict__ G = a.G + (long long)k * a.ld;
+    float* __restrict__ M = a.M + (long long)k * a.ld;
+    float* __restrict__ V = a.V + (long long)k * a.ld;
     // scalars are formed in double and rounded to fp32 once, like Python floats entering fp32 tensor ops
     // (one thread per CTA: pow() in double is hundreds of instructions)
     __shared__ float s_sc[2];
@@ -75,8 +76,8 @@ __device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, c
     const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
     const float inv_b = 1.f / (float)bsz;
     const float* zrow = a.dp_z ? a.dp_z + (long long)k * a.ld : nullptr;
-    float* wt = tab.wt + (long long)k * tab.ldt;
-    const float* gt = tab.gt + (long long)k * tab.ldt;
+    float* __restrict__ wt = tab.wt + (long long)k * tab.ldt;
+    const float* __restrict__ gt = tab.gt + (long long)k * tab.ldt;
     const int P4 = (P + 3) >> 2;
     const bool adam = a.opt != 1;
     int tab_lo = 0x7fffffff, tab_hi = 0;
@@ -112,6 +113,10 @@ __device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, c
                 q[e] = p0 + e < P ? tc_tab_map(tab, p0 + e, layer) : -1;
                 if (q[e] >= 0 && tab.gt_live[layer]) g[e] = gt[q[e]];
             }
+        }
+        if (p0 < tab.g_zero_upto) {
+            if (whole) *reinterpret_cast<float4*>(G + p0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (int e = 0; e < 4 && p0 + e < P; ++e) G[p0 + e] = 0.f;
         }
         if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
             const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
@@ -215,6 +220,8 @@ extern "C" int flb_train_begin_epoch(const flb_train_args* a, void* stream) {
     begin_epoch_kernel<<<flb_cdiv(a->K, 256), 256, 0, (cudaStream_t)stream>>>(*a);
     const TcConvTab t = tab_of(*a);
     if (t.n) tc_repack_kernel<0><<<dim3(repack_blocks(*a, t), a->K), 256, 0, (cudaStream_t)stream>>>(*a, t);
+    if (a->model == 0)
+        if (int rc = simplecnn::begin_epoch_zero(*a, (cudaStream_t)stream)) return rc;
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
@@ -231,13 +238,13 @@ extern "C" int flb_train_advance(const flb_train_args* a, void* stream) {
     return FLB_OK;
 }
 
-static int fwd_bwd(const flb_train_args& a, cudaStream_t st) {
-    return a.model == 0 ? simplecnn::forward_backward(a, st) : cifar::forward_backward(a, st);
+static int fwd_bwd(const flb_train_args& a, cudaStream_t st, bool zero_first) {
+    return a.model == 0 ? simplecnn::forward_backward(a, st, zero_first) : cifar::forward_backward(a, st);
 }
 
 extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {
     if (int rc = check_args(a)) return rc;
-    if (int rc = fwd_bwd(*a, (cudaStream_t)stream)) return rc;
+    if (int rc = fwd_bwd(*a, (cudaStream_t)stream, true)) return rc;
     const TcConvTab t = tab_of(*a);          // the step proper never needs G in the reference layout; this entry does
     if (t.n) tc_repack_kernel<1><<<dim3(repack_blocks(*a, t), a->K), 256, 0, (cudaStream_t)stream>>>(*a, t);
     FLB_LAUNCH_CHECK();
@@ -247,7 +254,7 @@ extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream)
 extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     if (int rc = check_args(a)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = fwd_bwd(*a, st)) return rc;
+    if (int rc = fwd_bwd(*a, st, false)) return rc;      // accumulators are zero: begin_epoch + the optimizer keep them so
     const int P = num_params(*a);
     const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
     optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P, tab_of(*a));

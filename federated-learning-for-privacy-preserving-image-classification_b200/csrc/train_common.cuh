@@ -79,6 +79,11 @@ struct TcConvTab {
     int ldt = 0;
     float* wt = nullptr;             // [K, ldt]
     float* gt = nullptr;             // [K, ldt]
+    // Reference-layout gradients that are ACCUMULATED with atomics, G[0, g_zero_upto), are kept at zero between steps:
+    // the optimizer kernel clears what it has consumed, so no memset node sits on the step's critical path.
+    // (Gt is cleared by a memset on the weight-gradient side lane: clearing it from the optimizer's scattered
+    // tap-major accesses was measured 55 us slower.)  0 = the model's step zeroes its accumulators itself.
+    int g_zero_upto = 0;
 };
 // reference-layout offset p -> tap-major offset (or -1 when p is not a tensor-core conv weight)
 __device__ __forceinline__ int tc_tab_map(const TcConvTab& t, int p, int& layer) {
@@ -99,7 +104,8 @@ int num_params();
 long long ws_bytes(int K, int B);
 long long ws_offset(int K, int B, const char* name);
 int forward(const flb_train_args& a, cudaStream_t st);
-int forward_backward(const flb_train_args& a, cudaStream_t st);
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first);
+int begin_epoch_zero(const flb_train_args& a, cudaStream_t st);
 int step_launches(const flb_train_args& a);
 void tc_tab(const flb_train_args& a, TcConvTab* t);
 }

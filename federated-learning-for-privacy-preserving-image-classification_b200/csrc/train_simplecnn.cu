@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     for (int e = tid; e < nloc * 128; e += 256) {
         const int b = e >> 7, j = e & 127;
         const float pre = ws.hpre[kb * 128 + e] + W[Off::f1b + j];
+        ws.hpre[kb * 128 + e] = 0.f;                       // consumed: ready for the next step's split-K atomics
         float mult = pre > 0.f ? 1.f : 0.f;
         if (a.drop_p > 0.f) {
             bool keep;
@@ -456,8 +457,7 @@ constexpr int kLdt = 9 * 64 * 32;          // tap-major conv2 weights per client
 int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     const int K = a.K, B = a.B;
     const dim3 per_sample(B, K);
-    FLB_CUDA(cudaMemsetAsync(ws.hpre, 0, sizeof(float) * (size_t)K * B * 128, st));
-    MARK("begin");
+    MARK("begin");          // hpre (split-K accumulator of fc1) is kept at zero by its consumer, head_fwd_bwd_kernel
     conv1_fwd_pool_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
     MARK("conv1_fwd_pool");
     const int tcm = tc_mask_of(a);
@@ -484,13 +484,20 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     return FLB_OK;
 }
 
-int forward_backward(const flb_train_args& a, cudaStream_t st) {
+// gradients that are accumulated with atomics must start from zero: G[0, f1w) (everything except fc1.weight / fc2, which
+// are plain stores).  Inside an epoch the optimizer kernel re-zeroes them as it consumes them.
+int zero_accumulators(const flb_train_args& a, const SimpleCnnWs&, cudaStream_t st) {
+    FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, Off::f1w * sizeof(float), a.K, st));
+    return FLB_OK;
+}
+
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) {
     SimpleCnnWs ws;
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
     const int K = a.K, B = a.B;
     const dim3 per_sample(B, K);
-    // gradients that are accumulated with atomics start from zero: everything except fc1.weight/fc2 (plain stores)
-    FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, Off::f1w * sizeof(float), K, st));
+    if (zero_first)
+        if (int rc = zero_accumulators(a, ws, st)) return rc;
     if (a.dp_mode == 1) FLB_CUDA(cudaMemsetAsync(ws.norm2, 0, sizeof(float) * (size_t)K * B, st));
     if (int rc = forward(a, ws, st)) return rc;
 
@@ -518,7 +525,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st) {
         if (tcm & TC_CONV2_WGRAD) {
             if (coef) conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, 1);      // else: fused into unpool2
             if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
-            FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));
+            FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));       // side lane: off the critical path
             MARK("conv2_bias_grad");
             if (int rc = tc::conv_wgrad(a, kConv2, ws.a1p, ws.z2, ws.gt, kLdt, st)) return rc;
         } else {
@@ -608,7 +615,12 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
     return ::forward(a, ws, st);
 }
-int forward_backward(const flb_train_args& a, cudaStream_t st) { return ::forward_backward(a, st); }
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) { return ::forward_backward(a, st, zero_first); }
+int begin_epoch_zero(const flb_train_args& a, cudaStream_t st) {
+    SimpleCnnWs ws;
+    simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
+    return zero_accumulators(a, ws, st);
+}
 int step_launches(const flb_train_args& a) {
     const int m = tc_mask_of(a);
     int n = 12 - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less; conv2 bias gradient: fused into unpool2                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
@@ -617,6 +629,7 @@ int step_launches(const flb_train_args& a) {
 }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {
     const int m = tc_mask_of(a);
+    t->g_zero_upto = Off::f1w;
     if (!(m & (TC_CONV2_FWD | TC_CONV2_DGRAD | TC_CONV2_WGRAD))) return;
     SimpleCnnWs ws;
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
