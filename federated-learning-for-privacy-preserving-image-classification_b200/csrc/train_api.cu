@@ -256,7 +256,8 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = fwd_bwd(*a, st, false)) return rc;      // accumulators are zero: begin_epoch + the optimizer keep them so
     const int P = num_params(*a);
-    const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 8 + a->K - 1) / a->K));
+    // 4 CTAs per SM = one resident wave at 60 registers per thread (measured best of 2/4/8/16/32)
+    const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 4 + a->K - 1) / a->K));
     optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P, tab_of(*a));
     MARK("optimizer");
     FLB_LAUNCH_CHECK();
