@@ -96,6 +96,17 @@ fedavg_ptrs_kernel(const float* const* __restrict__ ptrs, const long long* __res
 // uint8 affine-quantised client rows (reference src/shared/compression.py:230-244 dequant rule
 // (float(q) - zp) * scale, per client and per layer), dequantised in registers and averaged in the
 // same pass: K bytes + 4 bytes of traffic per parameter instead of 4K + 4.
+// Each thread owns 16 consecutive parameters (one 16 B load per client row).  float(q) - zp is formed exactly in ONE
+// add through the 2^23 mantissa trick (as_float(0x4B000000 | q) = 2^23 + q; both q and zp are integers below 2^24),
+// the remaining fp32 multiply, multiply, add are rounded separately in the reference's order.
+__device__ __forceinline__ void q8_accum4(uint32_t word, float magic_z, float s, float wk, float* acc) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float qf = __uint_as_float(0x4B000000u | ((word >> (8 * e)) & 0xffu));       // 2^23 + q, exact
+        acc[e] = __fadd_rn(acc[e], __fmul_rn(wk, __fmul_rn(__fsub_rn(qf, magic_z), s)));   // (q - zp) * scale, then w * (.), then +=
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __restrict__ scale,
                  const float* __restrict__ zp, const long long* __restrict__ seg_off,
@@ -103,28 +114,39 @@ fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __re
     extern __shared__ long long s_off[];
     for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
     __syncthreads();
-    const long long P4 = (P + 3) >> 2;
+    const long long P16 = (P + 15) >> 4;
     const long long stride = (long long)gridDim.x * kThreads;
-    const bool vec_ok = (ldq & 3) == 0;
-    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < P4; c += stride) {
-        const long long p = c << 2;
-        int lo = 0, hi = L;
+    const bool vec_ok = (ldq & 15) == 0 && ((uintptr_t)q & 15) == 0;
+    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < P16; c += stride) {
+        const long long p = c << 4;
+        int lo = 0, hi = L;                       // largest l with s_off[l] <= p
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
-        const bool whole = vec_ok && (p + 3 < P) && (p + 3 < s_off[lo + 1]);
+        const bool whole = vec_ok && (p + 15 < P) && (p + 15 < s_off[lo + 1]);
         if (whole) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+#pragma unroll 2
             for (int k = 0; k < K; ++k) {
-                const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(q + (long long)k * ldq + p));
-                const float s = __ldg(&scale[(long long)k * L + lo]), z = __ldg(&zp[(long long)k * L + lo]);
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(q + (long long)k * ldq + p));
+                const float s = __ldg(&scale[(long long)k * L + lo]);
+                const float magic_z = 8388608.0f + __ldg(&zp[(long long)k * L + lo]);     // exact: zp is an integer < 2^16
                 const float wk = __ldg(&w[k]);
-                a0 = __fadd_rn(a0, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.x, z), s)));
-                a1 = __fadd_rn(a1, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.y, z), s)));
-                a2 = __fadd_rn(a2, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.z, z), s)));
-                a3 = __fadd_rn(a3, __fmul_rn(wk, __fmul_rn(__fsub_rn((float)v.w, z), s)));
+                q8_accum4(v.x, magic_z, s, wk, acc);
+                q8_accum4(v.y, magic_z, s, wk, acc + 4);
+                q8_accum4(v.z, magic_z, s, wk, acc + 8);
+                q8_accum4(v.w, magic_z, s, wk, acc + 12);
             }
-            out[p] = a0; out[p + 1] = a1; out[p + 2] = a2; out[p + 3] = a3;
+            float4* o4 = reinterpret_cast<float4*>(out + p);
+            if (((uintptr_t)out & 15) == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) out[p + e] = acc[e];
+            }
         } else {
-            for (long long e = p; e < min(p + 4, P); ++e) {
+            for (long long e = p; e < min(p + 16, P); ++e) {
                 int l = lo;
                 while (e >= s_off[l + 1]) ++l;
                 float a = 0.f;
@@ -181,7 +203,7 @@ extern "C" int flb_fedavg_weighted_sum_q8(const uint8_t* q, long long ldq, const
     FLB_CHECK_ARG(q && scale && zp && seg_off && w && out, "flb_fedavg_weighted_sum_q8: null pointer");
     FLB_CHECK_ARG(K >= 1 && L >= 1 && L <= 4096 && ldq >= P, "flb_fedavg_weighted_sum_q8: bad K/L/ldq");
     if (P == 0) return FLB_OK;
-    fedavg_q8_kernel<<<grid_for((P + 3) / 4), kThreads, (L + 1) * sizeof(long long), (cudaStream_t)stream>>>(
+    fedavg_q8_kernel<<<grid_for((P + 15) / 16), kThreads, (L + 1) * sizeof(long long), (cudaStream_t)stream>>>(
         q, ldq, scale, zp, seg_off, w, out, K, L, P);
     FLB_LAUNCH_CHECK();
     return FLB_OK;

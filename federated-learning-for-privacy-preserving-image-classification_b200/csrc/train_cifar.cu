@@ -777,34 +777,39 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     bn_bwd<128>(a, G6, ws.z6, nullptr, ws.d8a, ws.acc, 5, st);
     MARK("bn6_bwd");
     conv_wgrad(cx, G6, ws.y5, ws.d8a, 5);
+    MARK("conv6_wgrad");
     conv_dgrad(cx, G6, ws.d8a, ws.d8b, 5);
-    MARK("conv6_bwd");
+    MARK("conv6_dgrad");
     bn_bwd<128>(a, G5, ws.z5, ws.y5, ws.d8b, ws.acc, 4, st);
     MARK("bn5_bwd");
     conv_wgrad(cx, G5, ws.p2, ws.d8b, 4);
+    MARK("conv5_wgrad");
     conv_dgrad(cx, G5, ws.d8b, ws.d8p, 4);
-    MARK("conv5_bwd");
+    MARK("conv5_dgrad");
 
     // block 2 (16x16, 64 channels)
     unpool_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.d16a);
     bn_bwd<64>(a, G4, ws.z4, nullptr, ws.d16a, ws.acc, 3, st);
     MARK("bn4_bwd");
     conv_wgrad(cx, G4, ws.y3, ws.d16a, 3);
+    MARK("conv4_wgrad");
     conv_dgrad(cx, G4, ws.d16a, ws.d16b, 3);
-    MARK("conv4_bwd");
+    MARK("conv4_dgrad");
     bn_bwd<64>(a, G3, ws.z3, ws.y3, ws.d16b, ws.acc, 2, st);
     MARK("bn3_bwd");
     conv_wgrad(cx, G3, ws.p1, ws.d16b, 2);
+    MARK("conv3_wgrad");
     conv_dgrad(cx, G3, ws.d16b, ws.d16p, 2);
-    MARK("conv3_bwd");
+    MARK("conv3_dgrad");
 
     // block 1 (32x32, 32 channels)
     unpool_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.d32a);
     bn_bwd<32>(a, G2, ws.z2, nullptr, ws.d32a, ws.acc, 1, st);
     MARK("bn2_bwd");
     conv_wgrad(cx, G2, ws.y1, ws.d32a, 1);
+    MARK("conv2_wgrad");
     conv_dgrad(cx, G2, ws.d32a, ws.d32b, 1);
-    MARK("conv2_bwd");
+    MARK("conv2_dgrad");
     bn_bwd<32>(a, G1, ws.z1, ws.y1, ws.d32b, ws.acc, 0, st);
     MARK("bn1_bwd");
     conv1_wgrad_kernel<<<per_sample, 256, 0, st>>>(a, ws.d32b);
