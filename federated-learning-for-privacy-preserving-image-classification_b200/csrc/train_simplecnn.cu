@@ -27,6 +27,7 @@ int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, floa
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
 int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* pooled, uint8_t* idx, const float* wt,
                         long long ldt, int boff, cudaStream_t st);
+int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
@@ -271,6 +272,11 @@ __global__ void __launch_bounds__(64) conv2_bias_grad_kernel(flb_train_args a, S
     const float* a2 = ws.a2 + kb * 3136 + c * 49;
     float acc = 0.f;
     for (int pp = 0; pp < 49; ++pp) acc += a2[pp] > 0.f ? da2[pp] : 0.f;
+    if (use_coef == 2) {                       // per-sample DP norm pass: || db_b ||^2 joins the sample's squared gradient norm
+        float sq = flb_warp_sum(acc * acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&ws.norm2[kb], sq);
+        return;
+    }
     atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], acc * (use_coef ? ws.coef[kb] : 1.f));
 }
 
@@ -570,7 +576,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     // ---- per-sample clip coefficients (dp_mode 1) ----
     if (a.dp_mode == 1) {
         linear_ghost_norm_kernel<<<per_sample, 128, 0, st>>>(a, ws);
-        {
+        if (tcm & TC_CONV2_WGRAD) {          // per-sample conv2 gradient tiles live in TMEM only (tcgen05), squared on the way out
+            if (int rc = tc::conv_wgrad_norm_32_64(a, kConv2, ws.a1p, ws.z2, ws.norm2, st)) return rc;
+            conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, 2);
+        } else {
             ConvWgradNormProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.norm2_all = ws.norm2;
             simt::launch(p, 64, 289, 1, K * B, st);
         }
@@ -624,7 +633,7 @@ int begin_epoch_zero(const flb_train_args& a, cudaStream_t st) {
 int step_launches(const flb_train_args& a) {
     const int m = tc_mask_of(a);
     int n = 12 - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less; conv2 bias gradient: fused into unpool2                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
-    if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 2 : 0);
+    if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 3 : 0);
     return n;
 }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {

@@ -59,6 +59,20 @@ static int make_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_
 __device__ __forceinline__ int tap_shift(int tap, int Wp) { return (tap / 3 - 1) * Wp + (tap % 3 - 1); }
 
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of the function: set it once per (kernel, device)
+static int ensure_smem_attr(const void* fn, int smem) {
+    struct Seen { const void* fn; int dev; };
+    static thread_local Seen seen[64];
+    static thread_local int n = 0;
+    int dev = 0;
+    FLB_CUDA(cudaGetDevice(&dev));
+    for (int i = 0; i < n; ++i)
+        if (seen[i].fn == fn && seen[i].dev == dev) return FLB_OK;
+    FLB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (n < 64) seen[n++] = Seen{fn, dev};
+    return FLB_OK;
+}
+
 template <int N> struct Pow2Cols { static constexpr int value = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : (N <= 256 ? 256 : 512))); };
 
 // ---- conv forward: D[128 px, COUT] = sum_{tap, cin chunk} X[px + shift(tap), 32] * Wt[tap][COUT][32]^T ---------------
@@ -309,9 +323,13 @@ struct ConvDgradHaloT : ConvDgradT<CIN, COUT> {
 
 // ---- conv wgrad: Gt[tap][co][ci] += sum_px X[px + shift(tap)][ci] * dZ[px][co] ----------------------------------------
 // M = (tap, ci) in 32-row chunks, N = co, K = pixels (split over blockIdx.x); blockIdx.z selects MTC of the M tiles.
-template <int CIN, int COUT, int MTC>
+// NORM (north-star kernel 2, per-sample DP-SGD): one split per SAMPLE (kb_per_split = rows per image / 32), and the
+// epilogue does not write the [9*Cin, Cout] per-sample weight gradient anywhere -- it squares it straight out of TMEM,
+// reduces with warp shuffles and adds one float per warp to norm2[client, sample].
+template <int CIN, int COUT, int MTC, bool NORM = false>
 struct ConvWgradT {
-    struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* gt_all; long long ldt; int kb_per_split; };
+    struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* gt_all; long long ldt; int kb_per_split;
+                    float* norm2_all; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int CCH = CIN / 32, ACH = 9 * CCH, BCH = COUT / 32;
     static constexpr int A_BYTES = MTC * 4 * 4096, STAGE_BYTES = A_BYTES + BCH * 4096;
@@ -355,8 +373,27 @@ struct ConvWgradT {
                          smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
-        float* gt = p.gt_all + (long long)client * p.ldt;
         const int mtiles = (nch + 3) >> 2;
+        if (NORM) {
+            float sq = 0.f;
+#pragma unroll 1
+            for (int mt = 0; mt < mtiles; ++mt) {
+                const bool ok = ((mt * 128 + quarter * 32 + lane) >> 5) < nch;
+#pragma unroll 1
+                for (int c0 = 0; c0 < COUT; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + mt * COUT + c0, v);
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sq = fmaf(v[i], v[i], sq);
+                    }
+                }
+            }
+            sq = flb_warp_sum(sq);
+            if (lane == 0 && sq != 0.f) atomicAdd(&p.norm2_all[(long long)client * p.a.B + blockIdx.x], sq);     // blockIdx.x = sample
+            return;
+        }
+        float* gt = p.gt_all + (long long)client * p.ldt;
 #pragma unroll 1
         for (int mt = 0; mt < mtiles; ++mt) {
             const int row = mt * 128 + quarter * 32 + lane;          // row = local chunk * 32 + (cin within the slice)
@@ -512,11 +549,7 @@ template <class T>
 static int launch(const typename T::Params& p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = (size_t)T::STAGES * T::STAGE_BYTES + T::RESIDENT_BYTES + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        FLB_CUDA(cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&gemm_kernel<T>), (int)smem)) return rc;
     gemm_kernel<T><<<grid, THREADS, smem, st>>>(p);
     return FLB_OK;
 }
@@ -525,11 +558,7 @@ template <class T>
 static int launch_persistent(const typename T::Params& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)T::STAGES * T::STAGE_BYTES + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        FLB_CUDA(cudaFuncSetAttribute(gemm_persistent_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&gemm_persistent_kernel<T>), (int)smem)) return rc;
     const int tiles = T::num_tiles(p);
     const int grid = tiles < flb_num_sms() * T::MINB ? tiles : flb_num_sms() * T::MINB;
     gemm_persistent_kernel<T><<<grid, THREADS, smem, st>>>(p);
@@ -540,11 +569,7 @@ template <class T>
 static int launch_resident(const typename T::Params& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)T::W_BYTES + (size_t)T::STAGES * T::STAGE_BYTES + 1024;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        FLB_CUDA(cudaFuncSetAttribute(conv_resident_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_resident_kernel<T>), (int)smem)) return rc;
     const int tiles = T::num_tiles(p);
     const int grid = tiles < flb_num_sms() ? tiles : flb_num_sms();
     conv_resident_kernel<T><<<grid, THREADS, smem, st>>>(p);
@@ -598,7 +623,7 @@ static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float*
     typename T::Params p;
     if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 32, true)) return rc;
     if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 32, true)) return rc;
-    p.a = a; p.g = g; p.gt_all = gt; p.ldt = ldt;
+    p.a = a; p.g = g; p.gt_all = gt; p.ldt = ldt; p.norm2_all = nullptr;
     constexpr int groups = (T::ACH + MTC * 4 - 1) / (MTC * 4);
     const int total = (a.B * g.PP() + 31) / 32;
     int splits = flb_num_sms() / (a.K * groups);             // one wave of CTAs over the GPU (two waves measured slower)
@@ -606,6 +631,18 @@ static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float*
     p.kb_per_split = (total + splits - 1) / splits;
     splits = (total + p.kb_per_split - 1) / p.kb_per_split;
     return launch<T>(p, dim3(splits, a.K, groups), st);
+}
+
+// per-sample squared norms of the conv weight gradient (bias excluded): norm2[client, b] += || dW_b ||^2
+int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
+    using T = ConvWgradT<32, 64, 3, true>;
+    if (g.PP() % 32) { flb_set_error("conv_wgrad_norm_32_64: rows per image must be a multiple of 32"); return FLB_ERR_ARG; }
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32, true)) return rc;
+    p.a = a; p.g = g; p.gt_all = nullptr; p.ldt = 0; p.norm2_all = norm2;
+    p.kb_per_split = g.PP() / 32;                           // split index = sample index; finished samples drop out in setup()
+    return launch<T>(p, dim3(a.B, a.K, 1), st);
 }
 
 // ---- host entry points used by the step orchestrators ---------------------------------------------------------------------
