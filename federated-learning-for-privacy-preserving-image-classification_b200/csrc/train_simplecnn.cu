@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(112) pool2_kernel(flb_train_args a, SimpleCnnW
 // ------------------------------------------------------------------------------------------------
 // classifier head: fc1 bias + ReLU + dropout, fc2, softmax cross-entropy, dlogits, dh.
 // grid (K, HEAD_PARTS): each CTA owns a slice of the client's batch; the epoch accumulators take one atomic per CTA.
-constexpr int HEAD_PARTS = 4;
+constexpr int HEAD_PARTS = 8;
 __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, SimpleCnnWs ws) {
     const int k = blockIdx.x;
     const int bsz = flb_bsz(a, k);
@@ -181,13 +181,17 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     for (int e = tid; e < 1280; e += 256) sw2[e >> 7][e & 127] = W[Off::f2w + e];
     if (tid < 2) red[tid] = 0.f;
     __syncthreads();
-    for (int e = tid; e < nloc * 10; e += 256) {
-        const int b = e / 10, j = e % 10;
-        float acc = W[Off::f2b + j];
-#pragma unroll 8
-        for (int i = 0; i < 128; ++i) acc = fmaf(sh[b][i], sw2[j][i], acc);
-        slog[b][j] = acc;
-        ws.logits[kb * 10 + e] = acc;
+    for (int e = tid >> 5; e < nloc * 10; e += 8) {            // one warp per logit: 4 products per lane + shuffle reduce
+        const int b = e / 10, j = e % 10, l = tid & 31;
+        float acc = sh[b][l] * sw2[j][l];
+        acc = fmaf(sh[b][l + 32], sw2[j][l + 32], acc);
+        acc = fmaf(sh[b][l + 64], sw2[j][l + 64], acc);
+        acc = fmaf(sh[b][l + 96], sw2[j][l + 96], acc);
+        acc = flb_warp_sum(acc) + W[Off::f2b + j];
+        if (l == 0) {
+            slog[b][j] = acc;
+            ws.logits[kb * 10 + e] = acc;
+        }
     }
     __syncthreads();
     if (tid < nloc) {

@@ -79,12 +79,25 @@ template <int N> struct Pow2Cols { static constexpr int value = N <= 32 ? 32 : (
 // POOL (SimpleCNN conv2: 16-wide grid, 256 rows per image, so a 128-row tile is 8 whole grid rows): the epilogue applies
 // bias + ReLU + 2x2 max-pool (+argmax) with warp shuffles -- a warp's 32 accumulator rows are two adjacent grid rows --
 // and writes fc1's NCHW-flattened input directly; the pre-pool activation never goes to HBM.
-template <int CIN, int COUT, bool POOL = false>
+// NPART > 1: the k-loop is spread over NPART partial accumulators (column blocks NPART x COUT of TMEM) so that
+// consecutive MMAs do not form one dependent chain on a single accumulator; the epilogue adds the partials.
+template <int CIN, int COUT, bool POOL = false, int NPART = 1>
 struct ConvFwdT {
     struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff;
                     float* pool_out; uint8_t* pool_idx; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
-    static constexpr int ACC_COLS = COUT;
+    static constexpr int ACC_COLS = NPART * COUT;
+    // 32 accumulator columns [c0, c0 + 32) of this thread's row, partials summed
+    static __device__ __forceinline__ void ld_acc(uint32_t taddr, float* v) {
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int j = 1; j < NPART; ++j) {
+            float u[32];
+            tmem_ld32(taddr + j * COUT, u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += u[i];
+        }
+    }
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
         const int tpc = (p.a.B * p.g.PP() + 127) / 128;
@@ -137,7 +150,7 @@ struct ConvFwdT {
 #pragma unroll 1
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+                ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float x = v[i] + __ldg(&bias[c0 + i]);
@@ -161,7 +174,7 @@ struct ConvFwdT {
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+            ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -174,11 +187,21 @@ struct ConvFwdT {
 };
 
 // ---- conv dgrad: D[128 px, CIN] = sum_{tap, cout chunk} dZ[px - shift(tap), 32] * Wt[tap][32 cout][CIN] ---------------
-template <int CIN, int COUT>
+template <int CIN, int COUT, int NPART = 1>
 struct ConvDgradT {
     struct Params { CUtensorMap map_dz; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* dx_all; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
-    static constexpr int ACC_COLS = CIN;
+    static constexpr int ACC_COLS = NPART * CIN;
+    static __device__ __forceinline__ void ld_acc(uint32_t taddr, float* v) {
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int j = 1; j < NPART; ++j) {
+            float u[32];
+            tmem_ld32(taddr + j * CIN, u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += u[i];
+        }
+    }
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
         const int tpc = (p.a.B * p.g.PP() + 127) / 128;
@@ -226,7 +249,7 @@ struct ConvDgradT {
 #pragma unroll 1
         for (int c0 = 0; c0 < CIN; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+            ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dx + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -244,8 +267,8 @@ struct ConvDgradT {
 constexpr int HALO_A_BYTES = 200 * 128;       // up to 128 + 2*34 rows (33-wide CIFAR grid), padded to a 1024-byte multiple
 
 template <int CIN, int COUT, bool POOL = false>
-struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL> {
-    using Base = ConvFwdT<CIN, COUT, POOL>;
+struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL, 1> {         // one accumulator: this kernel is epilogue-bound (measured), partials only add TMEM loads
+    using Base = ConvFwdT<CIN, COUT, POOL, 1>;
     using Params = typename Base::Params;
     static constexpr int CH = CIN / 32, W_BYTES = CH * 9 * COUT * 128, STAGE_BYTES = HALO_A_BYTES;
     static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
@@ -282,8 +305,8 @@ struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL> {
 };
 
 template <int CIN, int COUT>
-struct ConvDgradHaloT : ConvDgradT<CIN, COUT> {
-    using Base = ConvDgradT<CIN, COUT>;
+struct ConvDgradHaloT : ConvDgradT<CIN, COUT, 3> {
+    using Base = ConvDgradT<CIN, COUT, 3>;
     using Params = typename Base::Params;
     static constexpr int CH = COUT / 32, NCH = CIN / 32, W_BYTES = CH * 9 * NCH * 4096, STAGE_BYTES = HALO_A_BYTES;
     static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
@@ -316,7 +339,8 @@ struct ConvDgradHaloT : ConvDgradT<CIN, COUT> {
             const uint32_t b_addr = wres + (uint32_t)((kb * 9 + tap) * NCH) * 4096u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (this->lead) mma_tf32(tmem, smem_desc_row(a_addr + k * 32), smem_desc_mn(b_addr + k * 1024, 4096, 512), id, kb > 0 || tap > 0 || k > 0);
+                if (this->lead) mma_tf32(tmem + (tap / 3) * CIN, smem_desc_row(a_addr + k * 32), smem_desc_mn(b_addr + k * 1024, 4096, 512), id,
+                                         kb > 0 || (tap % 3) > 0 || k > 0);
         }
     }
 };
