@@ -126,6 +126,13 @@ class FederatedRoundEngine:
         self.trainer.load_packed(x_all, y_all, [int(num_samples_all[i]) for i in self.client_ids])
         self.num_samples_all = [int(n) for n in num_samples_all]
 
+    def prefetch_packed(self, x_all: torch.Tensor, y_all: torch.Tensor) -> None:
+        """Start uploading the next round's samples (same client sizes) on the copy stream; see BatchedClientTrainer."""
+        self.trainer.prefetch_packed(x_all, y_all, self.trainer.n_host)
+
+    def use_prefetched(self) -> None:
+        self.trainer.use_prefetched()
+
     # ---- one round -----------------------------------------------------------------------------------------
     def fedavg_weights(self) -> List[float]:
         """n_k * E / sum(n * E) over ALL clients (fedavg.py:247-256 with num_samples = samples_processed)."""

@@ -121,3 +121,38 @@ def test_simulation_signature_and_result_dict(cuda_device):
 def test_smoke_entry(cuda_device):
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_prefetched_uploads_match_plain_loads(cuda_device):
+    """Double-buffered host -> device path (prefetch_packed / use_prefetched, two captured graphs) gives exactly the
+    rounds of the plain load_packed path, with different data every round."""
+    from flb200.simulation import FederatedRoundEngine
+    K, sizes = 3, [40, 33, 64]
+    w0 = OM.init_weights(MODEL, 3)
+    rounds = []
+    for r in range(4):
+        data = [OR.synthetic_client_data(MODEL, 10 * r + c, n=sizes[c]) for c in range(K)]
+        x = torch.cat([d[0].reshape(d[0].shape[0], -1) for d in data]).pin_memory()
+        y = torch.cat([d[1] for d in data]).to(torch.int32).pin_memory()
+        rounds.append((x, y))
+    outs = []
+    for mode in ("plain", "prefetch"):
+        eng = FederatedRoundEngine(MODEL, K, cuda_device, batch_size=8, learning_rate=1e-2, optimizer_type="sgd",
+                                   dp_mode="none", dropout_rate=0.0, precision="fp32")
+        eng.set_global_weights(w0)
+        eng.load_packed(rounds[0][0], rounds[0][1], sizes)
+        losses = []
+        for r in range(4):
+            if mode == "plain":
+                eng.load_packed(rounds[r][0], rounds[r][1], sizes)
+            else:
+                if r == 0:
+                    eng.prefetch_packed(rounds[0][0], rounds[0][1])
+                eng.use_prefetched()
+                if r + 1 < 4:
+                    eng.prefetch_packed(rounds[r + 1][0], rounds[r + 1][1])
+            losses.append(eng.run_round()["losses"])
+        outs.append((losses, eng.global_row.clone()))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5)          # split-K atomics reorder fp32 sums between runs
+    # atomics reorder fp32 sums between runs: same tolerance as two plain runs
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-6)
