@@ -219,9 +219,11 @@ __device__ __forceinline__ void bn_moments(const flb_train_args& a, const double
 // column sums over the real pixels of client k: MODE 0: (sum z, sum z^2) -> acc[0], acc[1];
 // MODE 1: g = relu-masked upstream gradient; (sum g * xhat, sum g) -> acc[2], acc[3].
 // thread = (channel quad, row lane): 16 B loads, two rows in flight per thread.
+// relu_gw >= 0 (MODE 1, layers whose dy comes from a dgrad): the ReLU mask is recomputed from z with the forward's own
+// arithmetic (z * alpha + beta > 0) instead of reading the activation tensor back.
 template <int C, int MODE>
 __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* dy_all,
-                                                        const float* y_all, double* acc, int coff) {
+                                                        double* acc, int coff, int relu_gw, int relu_gb) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
@@ -232,12 +234,16 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGe
     const long long base = (long long)k * a.B * PP * C;
     const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
     const float4* dy4 = MODE == 1 ? reinterpret_cast<const float4*>(dy_all + base) : nullptr;
-    const float4* y4 = (MODE == 1 && y_all) ? reinterpret_cast<const float4*>(y_all + base) : nullptr;
-    float mean[4] = {0.f, 0.f, 0.f, 0.f}, invstd[4] = {0.f, 0.f, 0.f, 0.f};
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, invstd[4] = {0.f, 0.f, 0.f, 0.f}, alpha[4], beta[4];
     if (MODE == 1) {
         float vb;
+        const float* W = a.W + (long long)k * a.ld;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) bn_moments(a, acc, k, coff + cq * 4 + e, bsz * g.H * g.W, mean[e], invstd[e], vb);
+        for (int e = 0; e < 4; ++e) {
+            bn_moments(a, acc, k, coff + cq * 4 + e, bsz * g.H * g.W, mean[e], invstd[e], vb);
+            alpha[e] = relu_gw >= 0 ? invstd[e] * W[relu_gw + cq * 4 + e] : 0.f;
+            beta[e] = relu_gw >= 0 ? W[relu_gb + cq * 4 + e] - mean[e] * alpha[e] : 0.f;
+        }
     }
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
     auto row = [&](int r) {
@@ -251,12 +257,10 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGe
         } else {
             const float4 gv4 = dy4[e];
             float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
-            if (y4) {
-                const float4 yv = y4[e];
-                if (!(yv.x > 0.f)) gv[0] = 0.f;
-                if (!(yv.y > 0.f)) gv[1] = 0.f;
-                if (!(yv.z > 0.f)) gv[2] = 0.f;
-                if (!(yv.w > 0.f)) gv[3] = 0.f;
+            if (relu_gw >= 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (!(__fadd_rn(__fmul_rn(zz[q], alpha[q]), beta[q]) > 0.f)) gv[q] = 0.f;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { s0[q] = fmaf(gv[q], (zz[q] - mean[q]) * invstd[q], s0[q]); s1[q] += gv[q]; }
@@ -386,44 +390,16 @@ __global__ void __launch_bounds__(256) bn_relu_pool_drop_kernel(flb_train_args a
     }
 }
 
-// backward of the kernel above up to (and including) the ReLU: dy on the fine grid (zeros on pads and non-argmax
-// positions).  dpool: gradient w.r.t. the pooled+dropped output (FLAT: [C*Ho*Wo], else the coarse padded grid).
-template <int C, bool FLAT>
-__global__ void __launch_bounds__(256) unpool_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
-                                                     const float* pooled_all, const uint8_t* idx_all, float* dy_all) {
-    const int b = blockIdx.x, k = blockIdx.y;
-    if (b >= flb_bsz(a, k)) return;
-    const long long kb = (long long)k * a.B + b;
-    const int Ho = g.H / 2, Wo = g.W / 2, npool = Ho * Wo;
-    const float* dpool = dpool_all + kb * (FLAT ? C * npool : go.PP() * C);
-    const float* pooled = pooled_all + kb * (FLAT ? C * npool : go.PP() * C);
-    const uint8_t* idx = idx_all + kb * npool * C;
-    float* dy = dy_all + kb * g.PP() * C;
-    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    const int total = g.PP() * C;
-    for (int e = threadIdx.x; e < total; e += 256) {
-        const int c = e % C, r = e / C, h = r / g.Wp, w = r - h * g.Wp;
-        float v = 0.f;
-        if (h < g.H && w < g.W) {
-            const int pp = (h >> 1) * Wo + (w >> 1);
-            const int src = FLAT ? c * npool + pp : ((h >> 1) * go.Wp + (w >> 1)) * C + c;
-            const int code = idx[FLAT ? c * npool + pp : pp * C + c];
-            if (code == ((h & 1) * 2 + (w & 1)) && pooled[src] > 0.f) v = dpool[src] * keep_scale;   // bit 2 set = dropped
-        }
-        dy[e] = v;
-    }
-}
-
 // dz = gamma * invstd * (g - dbeta/N - xhat * dgamma/N) in place over dy (zeros on pads); g = dy masked by y > 0 when
 // y_all is given.  CTA (0, k) writes dgamma / dbeta into G.
 template <int C>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, ConvGeom g, const float* z_all, const float* y_all,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, ConvGeom g, const float* z_all, int relu_mask,
                                                            float* dy_all, const double* acc, int coff, int gwoff, int gboff,
                                                            int conv_boff) {
     const int k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (bsz == 0) return;
-    __shared__ float s_mean[C], s_invstd[C], s_c0[C], s_c1[C], s_c2[C];
+    __shared__ float s_mean[C], s_invstd[C], s_c0[C], s_c1[C], s_c2[C], s_alpha[C], s_beta[C];
     const int tid = threadIdx.x;
     const int n_real = bsz * g.H * g.W;
     if (tid < C) {
@@ -433,6 +409,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
         const float dgamma = (float)A[0], dbeta = (float)A[BN_CH];
         const float gamma = a.W[(long long)k * a.ld + gwoff + tid];
         s_mean[tid] = mean; s_invstd[tid] = invstd;
+        s_alpha[tid] = invstd * gamma;                                  // forward: y = relu(z * alpha + beta)
+        s_beta[tid] = a.W[(long long)k * a.ld + gboff + tid] - mean * s_alpha[tid];
         s_c0[tid] = gamma * invstd;
         s_c1[tid] = dbeta / (float)n_real;
         s_c2[tid] = dgamma / (float)n_real;
@@ -448,7 +426,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
     constexpr int C4 = C / 4;
     float4* dy4 = reinterpret_cast<float4*>(dy_all + base);
     const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
-    const float4* y4 = y_all ? reinterpret_cast<const float4*>(y_all + base) : nullptr;
     const long long total = (long long)rows * C4;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};        // this thread always sees the same channel quad (256 % C4 == 0)
     const int c = (tid % C4) * 4;
@@ -459,12 +436,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
             const float4 gv4 = dy4[e], zv = z4[e];
             float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
             const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-            if (y4) {
-                const float4 yv = y4[e];
-                if (!(yv.x > 0.f)) gv[0] = 0.f;
-                if (!(yv.y > 0.f)) gv[1] = 0.f;
-                if (!(yv.z > 0.f)) gv[2] = 0.f;
-                if (!(yv.w > 0.f)) gv[3] = 0.f;
+            if (relu_mask) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (!(__fadd_rn(__fmul_rn(zz[q], s_alpha[c + q]), s_beta[c + q]) > 0.f)) gv[q] = 0.f;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -477,6 +452,120 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
     }
     if (conv_boff >= 0) {                     // conv bias gradient = column sums of dz (tensor-core path; the fp32 wgrad
         __shared__ float red[4][256];         // GEMM carries it as an extra column).  Exactly zero in exact arithmetic.
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[q][tid] = bsum[q];
+        __syncthreads();
+        if (tid < C) {
+            const int q = tid & 3, cq2 = tid >> 2;
+            float t = 0.f;
+            for (int i = 0; i < 256 / C4; ++i) t += red[q][i * C4 + cq2];
+            atomicAdd(&a.G[(long long)k * a.ld + conv_boff + tid], t);
+        }
+    }
+}
+
+// ---- BatchNorm backward of the POOLED layers (2, 4, 6) straight from the pooled-side arrays -----------------------------
+// Upstream of a max-pool the gradient is one value per 2x2 window, so the dense dy tensor is never materialised: the
+// reduction reads dpool / pooled / argmax (a quarter of the grid) and gathers z at the argmax positions; the apply kernel
+// forms dz = gamma * invstd * (g - dbeta/N - xhat * dgamma/N) for every grid position directly.
+template <int C, bool FLAT>
+__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
+                                                                 const float* pooled_all, const uint8_t* idx_all,
+                                                                 const float* z_all, double* acc, int coff) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (b >= bsz) return;
+    const int tid = threadIdx.x, c = tid % C;
+    const long long kb = (long long)k * a.B + b;
+    const int Wo = g.W / 2, npool = (g.H / 2) * Wo;
+    const float* dpool = dpool_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const float* pooled = pooled_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const uint8_t* idx = idx_all + kb * npool * C;
+    const float* z = z_all + kb * g.PP() * C;
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    float mean, invstd, vb;
+    bn_moments(a, acc, k, coff + c, bsz * g.H * g.W, mean, invstd, vb);
+    float s0 = 0.f, s1 = 0.f;
+    for (int e = tid; e < npool * C; e += 256) {              // e % C == c for every e of this thread (256 % C == 0)
+        const int pp = e / C, ph = pp / Wo, pw = pp - ph * Wo;
+        const int src = FLAT ? c * npool + pp : (ph * go.Wp + pw) * C + c;
+        if (!(pooled[src] > 0.f)) continue;                   // dropped, or ReLU inactive: no gradient through this window
+        const int code = idx[FLAT ? c * npool + pp : e] & 3;
+        const float gv = dpool[src] * keep_scale;
+        const float zv = z[((2 * ph + (code >> 1)) * g.Wp + 2 * pw + (code & 1)) * C + c];
+        s0 = fmaf(gv, (zv - mean) * invstd, s0);
+        s1 += gv;
+    }
+    __shared__ float red[2][256];
+    red[0][tid] = s0; red[1][tid] = s1;
+    __syncthreads();
+    if (tid < C) {
+        for (int i = 1; i < 256 / C; ++i) { s0 += red[0][tid + i * C]; s1 += red[1][tid + i * C]; }
+        double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
+        atomicAdd(A, (double)s0);
+        atomicAdd(A + BN_CH, (double)s1);
+    }
+}
+
+template <int C, bool FLAT>
+__global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
+                                                                const float* pooled_all, const uint8_t* idx_all, const float* z_all,
+                                                                float* dz_all, const double* acc, int coff, int gwoff, int gboff,
+                                                                int conv_boff) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (b >= bsz) return;
+    __shared__ float s_mean[C], s_invstd[C], s_c0[C], s_c1[C], s_c2[C];
+    const int tid = threadIdx.x;
+    const int n_real = bsz * g.H * g.W;
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, n_real, mean, invstd, vb);
+        const double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
+        const float dgamma = (float)A[0], dbeta = (float)A[BN_CH];
+        s_mean[tid] = mean; s_invstd[tid] = invstd;
+        s_c0[tid] = a.W[(long long)k * a.ld + gwoff + tid] * invstd;
+        s_c1[tid] = dbeta / (float)n_real;
+        s_c2[tid] = dgamma / (float)n_real;
+        if (b == 0) {
+            float* G = a.G + (long long)k * a.ld;
+            G[gwoff + tid] = dgamma;
+            G[gboff + tid] = dbeta;
+        }
+    }
+    __syncthreads();
+    const long long kb = (long long)k * a.B + b;
+    const int Wo = g.W / 2, npool = (g.H / 2) * Wo;
+    const float* dpool = dpool_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const float* pooled = pooled_all + kb * (FLAT ? C * npool : go.PP() * C);
+    const uint8_t* idx = idx_all + kb * npool * C;
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + kb * g.PP() * C);
+    float4* dz4 = reinterpret_cast<float4*>(dz_all + kb * g.PP() * C);
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    constexpr int C4 = C / 4;
+    const int c = (tid % C4) * 4;                          // fixed channel quad per thread (256 % C4 == 0)
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e = tid; e < g.PP() * C4; e += 256) {
+        const int r = e / C4, h = r / g.Wp, w = r - h * g.Wp;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (h < g.H && w < g.W) {
+            const int pp = (h >> 1) * Wo + (w >> 1), pos = (h & 1) * 2 + (w & 1);
+            const float4 zv = z4[e];
+            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int src = FLAT ? (c + q) * npool + pp : ((h >> 1) * go.Wp + (w >> 1)) * C + c + q;
+                const int code = idx[FLAT ? (c + q) * npool + pp : pp * C + c + q];
+                const float gv = (code == pos && pooled[src] > 0.f) ? dpool[src] * keep_scale : 0.f;     // bit 2 of code = dropped
+                const float xhat = (zz[q] - s_mean[c + q]) * s_invstd[c + q];
+                o[q] = s_c0[c + q] * (gv - s_c1[c + q] - xhat * s_c2[c + q]);
+                bsum[q] += o[q];
+            }
+        }
+        dz4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (conv_boff >= 0) {
+        __shared__ float red[4][256];
 #pragma unroll
         for (int q = 0; q < 4; ++q) red[q][tid] = bsum[q];
         __syncthreads();
@@ -635,14 +724,25 @@ __global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, Ci
 template <int C>
 void bn_stats(const flb_train_args& a, const ConvGeom& g, const float* z, double* acc, int coff, cudaStream_t st) {
     const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
-    bn_reduce_kernel<C, 0><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, nullptr, nullptr, acc, coff);
+    bn_reduce_kernel<C, 0><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, nullptr, acc, coff, -1, -1);
 }
+// layers whose upstream gradient is a dgrad output (1, 3, 5): dy is dense and still needs the ReLU mask
 template <int C>
-void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, const float* y, float* dy, double* acc, int layer, cudaStream_t st) {
+void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, float* dy, double* acc, int layer, cudaStream_t st) {
     const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
-    bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, y, acc, kNet.coff[layer]);
+    bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
     const int conv_boff = (a.precision == 1 && layer > 0) ? kNet.cb[layer] : -1;
-    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
+    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, 1, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
+}
+// pooled layers (2, 4, 6): straight from the pooled-side gradient
+template <int C, bool FLAT>
+void bn_pool_bwd(const flb_train_args& a, const ConvGeom& g, const ConvGeom& go, const float* dpool, const float* pooled,
+                 const uint8_t* idx, const float* z, float* dz, double* acc, int layer, cudaStream_t st) {
+    const dim3 per_sample(a.B, a.K);
+    bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
+    const int conv_boff = a.precision == 1 ? kNet.cb[layer] : -1;
+    bn_pool_bwd_apply_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, dz, acc, kNet.coff[layer],
+                                                                 kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
 template <int C>
 void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float* y, const double* acc, int layer, cudaStream_t st) {
@@ -773,14 +873,13 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     MARK("fc1_bwd");
 
     // block 3 (8x8, 128 channels)
-    unpool_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.da, ws.a, ws.i3, ws.d8a);
-    bn_bwd<128>(a, G6, ws.z6, nullptr, ws.d8a, ws.acc, 5, st);
+    bn_pool_bwd<128, true>(a, G6, G6, ws.da, ws.a, ws.i3, ws.z6, ws.d8a, ws.acc, 5, st);
     MARK("bn6_bwd");
     conv_wgrad(cx, G6, ws.y5, ws.d8a, 5);
     MARK("conv6_wgrad");
     conv_dgrad(cx, G6, ws.d8a, ws.d8b, 5);
     MARK("conv6_dgrad");
-    bn_bwd<128>(a, G5, ws.z5, ws.y5, ws.d8b, ws.acc, 4, st);
+    bn_bwd<128>(a, G5, ws.z5, ws.d8b, ws.acc, 4, st);
     MARK("bn5_bwd");
     conv_wgrad(cx, G5, ws.p2, ws.d8b, 4);
     MARK("conv5_wgrad");
@@ -788,14 +887,13 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     MARK("conv5_dgrad");
 
     // block 2 (16x16, 64 channels)
-    unpool_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.d16a);
-    bn_bwd<64>(a, G4, ws.z4, nullptr, ws.d16a, ws.acc, 3, st);
+    bn_pool_bwd<64, false>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.z4, ws.d16a, ws.acc, 3, st);
     MARK("bn4_bwd");
     conv_wgrad(cx, G4, ws.y3, ws.d16a, 3);
     MARK("conv4_wgrad");
     conv_dgrad(cx, G4, ws.d16a, ws.d16b, 3);
     MARK("conv4_dgrad");
-    bn_bwd<64>(a, G3, ws.z3, ws.y3, ws.d16b, ws.acc, 2, st);
+    bn_bwd<64>(a, G3, ws.z3, ws.d16b, ws.acc, 2, st);
     MARK("bn3_bwd");
     conv_wgrad(cx, G3, ws.p1, ws.d16b, 2);
     MARK("conv3_wgrad");
@@ -803,14 +901,13 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     MARK("conv3_dgrad");
 
     // block 1 (32x32, 32 channels)
-    unpool_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.d32a);
-    bn_bwd<32>(a, G2, ws.z2, nullptr, ws.d32a, ws.acc, 1, st);
+    bn_pool_bwd<32, false>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.z2, ws.d32a, ws.acc, 1, st);
     MARK("bn2_bwd");
     conv_wgrad(cx, G2, ws.y1, ws.d32a, 1);
     MARK("conv2_wgrad");
     conv_dgrad(cx, G2, ws.d32a, ws.d32b, 1);
     MARK("conv2_dgrad");
-    bn_bwd<32>(a, G1, ws.z1, ws.y1, ws.d32b, ws.acc, 0, st);
+    bn_bwd<32>(a, G1, ws.z1, ws.d32b, ws.acc, 0, st);
     MARK("bn1_bwd");
     conv1_wgrad_kernel<<<per_sample, 256, 0, st>>>(a, ws.d32b);
     MARK("conv1_wgrad");
@@ -840,7 +937,7 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     return forward_impl(a, ws, st);
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
-int step_launches(const flb_train_args&) { return 22 + 32; }
+int step_launches(const flb_train_args&) { return 22 + 29; }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {
     if (a.precision != 1) return;
     CifarWs ws;
