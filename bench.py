@@ -140,7 +140,7 @@ def cpu_baseline_run(n_clients: int, threads: int, rounds: int = 1, model: str =
     return n / dt, f"{rounds} round(s) x {n_clients} clients x 1 local epoch (batch 32, Adam) + update-level DP + FedAvg, {n} samples in {dt:.1f} s"
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,10 +161,20 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
+
+
+def _claim_stdout():
+    """Keep stdout to the ONE JSON line: libraries (NCCL's version banner, ...) that write to fd 1 are sent to stderr;
+    returns a file object on the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -179,7 +189,7 @@ def main():
     MODEL = wl["model"]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import flb200  # noqa: F401
     from flb200.models_pytorch import ModelFactory
@@ -344,7 +354,7 @@ def main():
                      else cpu_baseline_run(4, threads, 1, MODEL))
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
