@@ -13,6 +13,7 @@
 // no CTA spends time permuting weights; conv weight gradients are accumulated in the same layout (Gt).
 #include "tc_gemm.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -436,6 +437,98 @@ struct ConvWgradT {
     }
 };
 
+// ---- conv wgrad, halo variant ---------------------------------------------------------------------------------------------
+// The kernel above fetches nine shifted copies of every activation row (one TMA box per tap).  Here ONE box of
+// 32 + 2*(Wp+1) pixel rows is staged per 32-channel slice and k-block, and the M dimension is ordered (kernel row r,
+// slice c, tap-in-row j): for fixed (r, c) the three taps are the same rows shifted by one pixel, i.e. three 32-row M
+// chunks whose start addresses are 128 bytes apart -- a single MN-major descriptor with LBO = 128 (chunks overlap in
+// memory; the fourth chunk of the 128-row MMA tile is a don't-care).  L2 -> SM traffic per k-block drops from
+// 9 * 4 KB to (32 + 2*halo) * 128 B per slice.  RPC kernel rows per CTA (3, or 1 when 3 * Cin/32 * Cout > 512 TMEM columns).
+constexpr int WG_BOX_BYTES = 13 * 1024;       // up to 32 + 2*34 rows of 128 B, rounded up to a 1024-byte multiple
+
+template <int CIN, int COUT, int RPC, bool NORM = false>
+struct ConvWgradHaloT {
+    struct Params { CUtensorMap map_x; CUtensorMap map_dz; flb_train_args a; ConvGeom g; float* gt_all; long long ldt; int kb_per_split;
+                    float* norm2_all; };
+    bool lead = false;
+    static constexpr int CCH = CIN / 32, BCH = COUT / 32, TILES = RPC * CCH;
+    static constexpr int A_BYTES = CCH * WG_BOX_BYTES, STAGE_BYTES = A_BYTES + BCH * 4096;
+    static constexpr int STAGES = STAGE_BYTES * 4 <= 200 * 1024 ? 4 : (STAGE_BYTES * 3 <= 200 * 1024 ? 3 : 2), RESIDENT_BYTES = 0;
+    static constexpr int TMEM_COLS = Pow2Cols<TILES * COUT>::value, MINB = 1;
+    static_assert(TILES * COUT <= 512, "accumulators must fit TMEM");
+    int client, row0, kb0, rbase, total_rows, wp;
+    __device__ bool setup(const Params& p, int& num_kb) {
+        client = blockIdx.y;
+        const int bsz = flb_bsz(p.a, client);
+        total_rows = bsz * p.g.PP();
+        const int total = (total_rows + 31) / 32;
+        kb0 = blockIdx.x * p.kb_per_split;
+        if (kb0 >= total) return false;
+        num_kb = min(p.kb_per_split, total - kb0);
+        row0 = client * p.a.B * p.g.PP();
+        rbase = blockIdx.z * RPC;
+        wp = p.g.Wp;
+        return true;
+    }
+    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_dz); }
+    __device__ void stage_resident(const Params&, uint8_t*, int) {}
+    __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
+        const int px = row0 + (kb0 + kb) * 32, halo = p.g.Wp + 1;
+        if (this->lead) mbar_expect_tx(bar, CCH * (32 + 2 * halo) * 128 + BCH * 4096);
+#pragma unroll
+        for (int c = 0; c < CCH; ++c) if (this->lead) tma_load_2d(&p.map_x, stage + c * WG_BOX_BYTES, bar, c * 32, px - halo);
+#pragma unroll
+        for (int c = 0; c < BCH; ++c) if (this->lead) tma_load_2d(&p.map_dz, stage + A_BYTES + c * 4096, bar, c * 32, px);
+    }
+    __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
+        constexpr uint32_t id = idesc_tf32(128, COUT, true, true);
+        const int ksteps = min(4, (total_rows - (kb0 + kb) * 32) >> 3);      // rows per image are a multiple of 8
+        for (int k = 0; k < ksteps; ++k)
+#pragma unroll
+            for (int rl = 0; rl < RPC; ++rl)
+#pragma unroll
+                for (int c = 0; c < CCH; ++c) {
+                    // box row of tap (r, j = 0) for pixel 0 of the k-block: halo + shift = (Wp + 1) + (r - 1) * Wp - 1 = r * Wp
+                    const uint32_t a_addr = stage + c * WG_BOX_BYTES + (uint32_t)((rbase + rl) * wp + 8 * k) * 128u;
+                    if (this->lead) mma_tf32(tmem + (rl * CCH + c) * COUT, smem_desc_mn(a_addr, 128, 512),
+                                             smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
+                }
+    }
+    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
+        // accumulator row = (tap in kernel row j = quarter, cin within the slice = lane); quarter 3 is the don't-care chunk
+        if (NORM) {
+            float sq = 0.f;
+            if (quarter < 3) {
+#pragma unroll 1
+                for (int tl = 0; tl < TILES; ++tl)
+#pragma unroll 1
+                    for (int c0 = 0; c0 < COUT; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tl * COUT + c0, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sq = fmaf(v[i], v[i], sq);
+                    }
+            }
+            sq = flb_warp_sum(sq);
+            if (lane == 0 && sq != 0.f) atomicAdd(&p.norm2_all[(long long)client * p.a.B + blockIdx.x], sq);     // blockIdx.x = sample
+            return;
+        }
+        if (quarter >= 3) return;
+        float* gt = p.gt_all + (long long)client * p.ldt;
+#pragma unroll 1
+        for (int tl = 0; tl < TILES; ++tl) {
+            const int r = rbase + tl / CCH, c = tl % CCH, tap = 3 * r + quarter, ci = c * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + tl * COUT + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(&gt[((long long)tap * COUT + c0 + i) * CIN + ci], v[i]);   // lanes = consecutive ci
+            }
+        }
+    }
+};
+
 // ---- linear forward (swap-AB, split-K): D[128 out, B] += W[out, k] * act[b, k] --------------------------------------
 template <int IN, int OUT>
 struct FcFwdT {
@@ -659,10 +752,10 @@ static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float*
 
 // per-sample squared norms of the conv weight gradient (bias excluded): norm2[client, b] += || dW_b ||^2
 int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
-    using T = ConvWgradT<32, 64, 3, true>;
+    using T = ConvWgradHaloT<32, 64, 3, true>;
     if (g.PP() % 32) { flb_set_error("conv_wgrad_norm_32_64: rows per image must be a multiple of 32"); return FLB_ERR_ARG; }
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32 + 2 * (g.Wp + 1), true)) return rc;
     if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32, true)) return rc;
     p.a = a; p.g = g; p.gt_all = nullptr; p.ldt = 0; p.norm2_all = norm2;
     p.kb_per_split = g.PP() / 32;                           // split index = sample index; finished samples drop out in setup()
@@ -688,7 +781,30 @@ int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
     FLB_CONV_DISPATCH(conv_dgrad_t, a, g, dz, dx, wt, ldt, st)
 }
+template <int CIN, int COUT, int RPC>
+static int conv_wgrad_halo_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
+    using T = ConvWgradHaloT<CIN, COUT, RPC>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 32 + 2 * (g.Wp + 1), true)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 32, true)) return rc;
+    p.a = a; p.g = g; p.gt_all = gt; p.ldt = ldt; p.norm2_all = nullptr;
+    constexpr int groups = 3 / RPC;
+    const int total = (a.B * g.PP() + 31) / 32;
+    int splits = flb_num_sms() / (a.K * groups);             // one wave of CTAs over the GPU
+    splits = splits < 1 ? 1 : (splits > total ? total : splits);
+    p.kb_per_split = (total + splits - 1) / splits;
+    splits = (total + p.kb_per_split - 1) / p.kb_per_split;
+    return launch<T>(p, dim3(splits, a.K, groups), st);
+}
+
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
+    if (g.Wp + 1 <= 35 && !getenv("FLB_WGRAD_STREAMED")) {
+        if (g.Cin == 32 && g.Cout == 32) return conv_wgrad_halo_t<32, 32, 3>(a, g, xin, dz, gt, ldt, st);
+        if (g.Cin == 32 && g.Cout == 64) return conv_wgrad_halo_t<32, 64, 3>(a, g, xin, dz, gt, ldt, st);
+        if (g.Cin == 64 && g.Cout == 64) return conv_wgrad_halo_t<64, 64, 3>(a, g, xin, dz, gt, ldt, st);
+        if (g.Cin == 64 && g.Cout == 128) return conv_wgrad_halo_t<64, 128, 1>(a, g, xin, dz, gt, ldt, st);
+        if (g.Cin == 128 && g.Cout == 128) return conv_wgrad_halo_t<128, 128, 1>(a, g, xin, dz, gt, ldt, st);
+    }
     if (g.Cin == 32 && g.Cout == 32) return conv_wgrad_t<32, 32, 3>(a, g, xin, dz, gt, ldt, st);
     if (g.Cin == 32 && g.Cout == 64) return conv_wgrad_t<32, 64, 3>(a, g, xin, dz, gt, ldt, st);
     if (g.Cin == 64 && g.Cout == 64) return conv_wgrad_t<64, 64, 5>(a, g, xin, dz, gt, ldt, st);
