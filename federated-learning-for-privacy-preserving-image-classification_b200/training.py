@@ -172,7 +172,7 @@ class BatchedClientTrainer:
         with torch.cuda.device(self.device):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
-            if self._spare is None:
+            if self._spare is None or self._spare[0].shape != self.x.shape:
                 self._spare = (torch.empty_like(self.x), torch.empty_like(self.y))
             xs, ys = self._spare
             self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
