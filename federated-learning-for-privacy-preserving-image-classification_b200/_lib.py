@@ -37,6 +37,8 @@ SIGNATURES = {
     "flb_q8_dequantize": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
     "flb_update_stats": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_delta_norms": [_vp, _vp, _vp, _vp, _i, _ll, _vp],
+    "flb_gather_normalize_u8": [_vp, _ll, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp, _vp],
+    "flb_gather_labels": [_vp, _vp, _vp, _ll, _vp],
     "flb_topk_select": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "flb_topk_scatter": [_vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
     "flb_train_ws_bytes": [_i, _i, _i],

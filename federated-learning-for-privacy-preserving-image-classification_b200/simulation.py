@@ -126,6 +126,11 @@ class FederatedRoundEngine:
         self.trainer.load_packed(x_all, y_all, [int(num_samples_all[i]) for i in self.client_ids])
         self.num_samples_all = [int(n) for n in num_samples_all]
 
+    def attach_device_shards(self, x_dev: torch.Tensor, y_dev: torch.Tensor, num_samples_all: Sequence[int]) -> None:
+        """Device-resident packed store built by ``data_loader.DeviceShardBuilder`` for this rank's clients: used in place."""
+        self.trainer.attach(x_dev, y_dev, [int(num_samples_all[i]) for i in self.client_ids])
+        self.num_samples_all = [int(n) for n in num_samples_all]
+
     def prefetch_packed(self, x_all: torch.Tensor, y_all: torch.Tensor) -> None:
         """Start uploading the next round's samples (same client sizes) on the copy stream; see BatchedClientTrainer."""
         self.trainer.prefetch_packed(x_all, y_all, self.trainer.n_host)

@@ -150,14 +150,34 @@ class BatchedClientTrainer:
         if self.x is None or self.x.shape[0] != max(total, 1):
             self.x = torch.empty((max(total, 1), self.sample_numel), dtype=torch.float32, device=dev)
             self.y = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        self._reserve_meta(ns)
+
+    def _reserve_meta(self, ns: Sequence[int]) -> None:
+        ns = [int(n) for n in ns]
         if ns != self.n_host:
             offs = [0]
             for n in ns[:-1]:
                 offs.append(offs[-1] + n)
-            self.sample_off = torch.tensor(offs, dtype=torch.int64).to(dev)
-            self.nsamples = torch.tensor(ns, dtype=torch.int32).to(dev)
+            self.sample_off = torch.tensor(offs, dtype=torch.int64).to(self.device)
+            self.nsamples = torch.tensor(ns, dtype=torch.int32).to(self.device)
             self.n_host = ns
-        self.h2d_bytes = total * (self.sample_numel * 4 + 4)
+        self.h2d_bytes = sum(ns) * (self.sample_numel * 4 + 4)
+
+    def attach(self, x_dev: torch.Tensor, y_dev: torch.Tensor, ns: Sequence[int]) -> None:
+        """Use an already device-resident packed sample store (``DeviceShardBuilder.build``) in place: no copy."""
+        if len(ns) != self.K:
+            raise L.FlbError(f"attach: expected {self.K} clients, got {len(ns)}")
+        total = sum(int(n) for n in ns)
+        if not (x_dev.is_cuda and y_dev.is_cuda and x_dev.dtype == torch.float32 and y_dev.dtype == torch.int32
+                and x_dev.is_contiguous() and y_dev.is_contiguous()):
+            raise L.FlbError("attach: need contiguous CUDA tensors, x fp32 [sum N, C*H*W] and y int32 [sum N]")
+        if x_dev.shape[0] < max(total, 1) or x_dev[0].numel() != self.sample_numel or y_dev.shape[0] < max(total, 1):
+            raise L.FlbError("attach: x / y do not match the per-client counts or the model's sample shape")
+        self.x = self.y = None
+        self.n_host = []
+        self._spare = self._staged = None
+        self._reserve_meta(ns)
+        self.x, self.y = x_dev, y_dev
 
     def prefetch_packed(self, x_all: torch.Tensor, y_all: torch.Tensor, ns: Sequence[int]) -> None:
         """Upload the NEXT round's samples (same per-client counts as the current ones) into the spare device buffers on

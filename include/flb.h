@@ -73,6 +73,13 @@ int flb_update_stats(const float* const* ptrs, const long long* seg_off, float* 
 int flb_delta_norms(const float* const* new_ptrs, const float* const* old_ptrs, const long long* seg_off,
                     double* out, int L, long long P, void* stream);
 
+/* ---- device-resident shard builder: src/shared/data_loader.py:298-306,454-464 + training.py:186 ----
+ * out[j, c, h, w] = ((raw[idx[j]] / 255) - mean[c]) / std[c] (ToTensor + Normalize, fp32 step by step);
+ * raw is uint8 [n_raw, H, W, C] when hwc != 0 (CIFAR10.data) else [n_raw, C, H, W] (MNIST.data with C = 1). */
+int flb_gather_normalize_u8(const uint8_t* raw, long long n_raw, int H, int W, int C, int hwc, const long long* idx,
+                            long long M, const float* mean, const float* stdv, float* out, void* stream);
+int flb_gather_labels(const long long* labels, const long long* idx, int* out, long long M, void* stream);
+
 /* ---- top-k sparsification: src/shared/compression.py:327-365 (TopKSparsificationCompressor) ----------------
  * For every (client c, layer l): the kk[l] entries of largest |x| of x[c*ld + seg_off[l] .. seg_off[l+1]) as
  * (index relative to the layer start, value) pairs at [c*ldk + out_off[l] ..), in INDEX order; ties at the threshold keep

@@ -222,6 +222,32 @@ def main() -> None:
     digest("global", gm.model_weights, out)
     np.savez_compressed(os.path.join(OUT, "round_simple_cnn.npz"), **out)
 
+    # ---- 7. DataPartitioner (data side) ----------------------------------------
+    import random
+    from src.shared.data_loader import DataPartitioner
+
+    class _Labelled(torch.utils.data.Dataset):
+        def __init__(self, y):
+            self.y = y
+
+        def __len__(self):
+            return len(self.y)
+
+        def __getitem__(self, i):
+            return torch.zeros(1), int(self.y[i])
+
+    out = {}
+    y = np.random.default_rng(3).integers(0, 10, 3000)
+    out["labels"] = y
+    for strat in ("iid", "non_iid", "pathological"):
+        for nc in (7, 20):
+            random.seed(5)
+            np.random.seed(6)
+            part = DataPartitioner(_Labelled(y), nc, strat)
+            for cid, idx in part.client_indices.items():
+                out[f"{strat}/{nc}/{cid}"] = np.asarray(idx, dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "partition.npz"), **out)
+
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("# Golden vectors\n\nWritten by `python -m oracle.make_golden` from the unmodified reference "
                 f"(torch {meta['torch']}, 1 CPU thread, {meta['generated']}).\n"
