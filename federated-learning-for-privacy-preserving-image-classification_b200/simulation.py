@@ -181,6 +181,30 @@ class FederatedRoundEngine:
             self.history.append(out)
         return out
 
+    def evaluate_global(self, x: torch.Tensor, y: torch.Tensor, shards: int = 8) -> Dict[str, float]:
+        """Accuracy / mean batch loss of the CURRENT global model on a held-out set, through the forward kernels in eval
+        mode (no dropout, BatchNorm running statistics) -- what ``LocalTrainer.evaluate_model`` / ``_validate_epoch`` compute
+        (src/shared/training.py:214-242, 307-360), batched: the set is cut into ``shards`` pseudo-clients that all carry the
+        global weights, so one launch sequence evaluates ``shards x batch`` samples.  Uses its own small trainer; the
+        round state is untouched.  This is the number ``GlobalModel.accuracy_metrics`` is meant to hold (fedavg.py:106)."""
+        n = int(x.shape[0])
+        shards = max(1, min(shards, (n + self.trainer.B - 1) // self.trainer.B))
+        ev = getattr(self, "_evaluator", None)
+        if ev is None or ev.K != shards:
+            ev = BatchedClientTrainer(self.model_name, shards, self.device, self.trainer.B, 0.0, self.trainer.precision)
+            self._evaluator = ev
+        ev.set_global_row(self.global_row)
+        if ev.bn_running is not None:               # BatchNorm buffers are client-local upstream: use client 0's as the server's
+            ev.bn_running.copy_(self.trainer.bn_running[:1].expand(shards, -1))
+        per = (n + shards - 1) // shards
+        xs = [x[i * per:(i + 1) * per] for i in range(shards)]
+        ys = [y[i * per:(i + 1) * per] for i in range(shards)]
+        ev.load_data(xs, ys)
+        loss, acc, seen, _ = ev.evaluate()
+        tot = max(sum(seen), 1)
+        return {"accuracy": float(sum(a * s for a, s in zip(acc, seen)) / tot),
+                "loss": float(sum(l * s for l, s in zip(loss, seen)) / tot), "samples": int(sum(seen))}
+
     def samples_per_round(self) -> int:
         return sum(self.trainer.n_host) * self.local_epochs
 

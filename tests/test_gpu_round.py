@@ -156,3 +156,16 @@ def test_prefetched_uploads_match_plain_loads(cuda_device):
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5)          # split-K atomics reorder fp32 sums between runs
     # atomics reorder fp32 sums between runs: same tolerance as two plain runs
     torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-6)
+
+
+def test_evaluate_global_matches_oracle_forward(cuda_device):
+    """Held-out evaluation of the global model (training.py:307-360) through the batched forward kernels."""
+    from flb200.simulation import FederatedRoundEngine
+    w0 = OM.init_weights(MODEL, 9)
+    eng = FederatedRoundEngine(MODEL, 2, cuda_device, dp_mode="none", dropout_rate=0.25, precision="fp32")
+    eng.set_global_weights(w0)
+    x, y = OR.synthetic_client_data(MODEL, 77, n=203)
+    got = eng.evaluate_global(x, y, shards=3)
+    logits = OM.forward(MODEL, w0, x, train=False)
+    assert got["samples"] == 203
+    assert abs(got["accuracy"] - float((logits.argmax(1) == y).double().mean())) < 1e-12
