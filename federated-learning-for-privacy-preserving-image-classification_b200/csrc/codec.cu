@@ -99,7 +99,8 @@ q8_dequantize_kernel(const uint8_t* __restrict__ q, long long ldq, const long lo
 int chunks_for(long long P, int L, int K) {
     long long c = (P / L + (long long)kThreads * 8 - 1) / ((long long)kThreads * 8);    // ~8 elements per thread on an average layer
     if (c < 1) c = 1;
-    const long long cap = ((long long)flb_num_sms() * 16) / ((long long)L * K) + 1;
+    long long cap = ((long long)flb_num_sms() * 16) / ((long long)L * K) + 1;
+    if (cap < 8) cap = 8;            // layer sizes are very uneven (fc1 holds 70-95 % of the parameters): keep the big ones parallel
     if (c > cap) c = cap;
     return (int)(c > 1024 ? 1024 : c);
 }

@@ -781,6 +781,23 @@ int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
     FLB_CONV_DISPATCH(conv_dgrad_t, a, g, dz, dx, wt, ldt, st)
 }
+// Split-K factor of the wgrad kernels (one CTA per SM: they are shared-memory bound).  With `base` CTAs per split the
+// launch takes waves(s) = ceil(base * s / SMs) rounds, each costing 1/s of the k-loop (~0.5 us per 32-pixel k-block) plus
+// one accumulator flush (`flush_elems` fp32 reductions per CTA, ~0.2 ns each as 128-byte warp-wide REDs) -- calibrated on
+// B200 against 1/4/10/14/29 splits.  (SimpleCNN conv2, 10 clients: 14 splits; CIFAR conv2, 100 clients: ~10; conv6: 1-2.)
+static int wgrad_splits(int base, int total_kb, int flush_elems) {
+    const int sms = flb_num_sms();
+    const double work = 0.5 * total_kb, flush = 2e-4 * flush_elems;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 32 && s <= total_kb; ++s) {
+        const int waves = (base * s + sms - 1) / sms;
+        const double cost = waves * (work / s + flush);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
 template <int CIN, int COUT, int RPC>
 static int conv_wgrad_halo_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st) {
     using T = ConvWgradHaloT<CIN, COUT, RPC>;
@@ -790,8 +807,7 @@ static int conv_wgrad_halo_t(const flb_train_args& a, const ConvGeom& g, const f
     p.a = a; p.g = g; p.gt_all = gt; p.ldt = ldt; p.norm2_all = nullptr;
     constexpr int groups = 3 / RPC;
     const int total = (a.B * g.PP() + 31) / 32;
-    int splits = flb_num_sms() / (a.K * groups);             // one wave of CTAs over the GPU
-    splits = splits < 1 ? 1 : (splits > total ? total : splits);
+    int splits = wgrad_splits(a.K * groups, total, T::TILES * 96 * COUT);
     p.kb_per_split = (total + splits - 1) / splits;
     splits = (total + p.kb_per_split - 1) / p.kb_per_split;
     return launch<T>(p, dim3(splits, a.K, groups), st);
