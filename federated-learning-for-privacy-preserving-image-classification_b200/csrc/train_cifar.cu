@@ -116,18 +116,23 @@ size_t carve(void* base, int K, int B, CifarWs* ws) {
 }
 
 // ---- conv1 (Cin = 3): the input is the raw NCHW sample; K = 27 is too thin for a tensor-core tile -----------------
-// Direct 3->32 stencils (one CTA per sample): thread = (output channel, pixel lane); the 27 weights sit in registers,
-// the zero-haloed input planes in shared memory (every lane of a warp reads the same input pixel: broadcast).
+// Direct 3->32 stencils (one CTA per sample): thread = (output channel, strip lane); the 27 weights sit in registers,
+// the zero-haloed input planes in shared memory (row pitch 36 floats so that a 4-pixel strip's 6 inputs are one 16 B and
+// one 8 B load; every lane of a warp reads the same inputs: broadcast).  Each thread works on strips of 4 horizontally
+// adjacent pixels, so a (channel-in, kernel-row) pair costs 2 shared loads per 12 FMAs instead of 3 per 3.
+__device__ __forceinline__ void load_img3(float (*img)[34][36], const float* x, int tid) {
+    for (int i = tid; i < 3 * 34 * 36; i += 256) {
+        const int ci = i / (34 * 36), r = (i % (34 * 36)) / 36, c = i % 36;
+        img[ci][r][c] = (r >= 1 && r <= 32 && c >= 1 && c <= 32) ? x[ci * 1024 + (r - 1) * 32 + (c - 1)] : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float* z_all) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
-    __shared__ float img[3][34][35];
+    __shared__ __align__(16) float img[3][34][36];
     const int tid = threadIdx.x;
-    const float* x = a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072;
-    for (int i = tid; i < 3 * 34 * 34; i += 256) {
-        const int ci = i / 1156, r = (i % 1156) / 34, c = i % 34;
-        img[ci][r][c] = (r >= 1 && r <= 32 && c >= 1 && c <= 32) ? x[ci * 1024 + (r - 1) * 32 + (c - 1)] : 0.f;
-    }
+    load_img3(img, a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072, tid);
     const int c = tid & 31, g = tid >> 5;
     const float* W = a.W + (long long)k * a.ld;
     float w[27];
@@ -136,16 +141,23 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float*
     const float bias = W[kC1B + c];
     __syncthreads();
     float* z = z_all + ((long long)k * a.B + b) * PP32 * 32;
-    for (int p = g; p < 1024; p += 8) {
-        const int h = p >> 5, wc = p & 31;
-        float acc = bias;
+    for (int s = g; s < 256; s += 8) {                    // strip = 4 pixels (h, w0 .. w0 + 3)
+        const int h = s >> 3, w0 = (s & 7) * 4;
+        float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r) {
+                const float4 p0 = *reinterpret_cast<const float4*>(&img[ci][h + r][w0]);
+                const float2 p1 = *reinterpret_cast<const float2*>(&img[ci][h + r][w0 + 4]);
+                const float in[6] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y};
 #pragma unroll
-                for (int q = 0; q < 3; ++q) acc = fmaf(w[ci * 9 + r * 3 + q], img[ci][h + r][wc + q], acc);
-        z[(h * 33 + wc) * 32 + c] = acc;
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[ci * 9 + r * 3 + q], in[j + q], acc[j]);
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[(h * 33 + w0 + j) * 32 + c] = acc[j];
     }
 }
 
@@ -153,30 +165,34 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float*
 __global__ void __launch_bounds__(256) conv1_wgrad_kernel(flb_train_args a, const float* dz_all) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
-    __shared__ float img[3][34][35];
+    __shared__ __align__(16) float img[3][34][36];
     __shared__ float part[8][32][29];
     const int tid = threadIdx.x;
-    const float* x = a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072;
-    for (int i = tid; i < 3 * 34 * 34; i += 256) {
-        const int ci = i / 1156, r = (i % 1156) / 34, c = i % 34;
-        img[ci][r][c] = (r >= 1 && r <= 32 && c >= 1 && c <= 32) ? x[ci * 1024 + (r - 1) * 32 + (c - 1)] : 0.f;
-    }
+    load_img3(img, a.x + (a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b) * 3072, tid);
     __syncthreads();
     const int c = tid & 31, g = tid >> 5;
     const float* dz = dz_all + ((long long)k * a.B + b) * PP32 * 32;
     float acc[28];
 #pragma unroll
     for (int i = 0; i < 28; ++i) acc[i] = 0.f;
-    for (int p = g; p < 1024; p += 8) {
-        const int h = p >> 5, wc = p & 31;
-        const float gv = dz[(h * 33 + wc) * 32 + c];
+    for (int s = g; s < 256; s += 8) {
+        const int h = s >> 3, w0 = (s & 7) * 4;
+        float gv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gv[j] = dz[(h * 33 + w0 + j) * 32 + c];
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r) {
+                const float4 p0 = *reinterpret_cast<const float4*>(&img[ci][h + r][w0]);
+                const float2 p1 = *reinterpret_cast<const float2*>(&img[ci][h + r][w0 + 4]);
+                const float in[6] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y};
 #pragma unroll
-                for (int q = 0; q < 3; ++q) acc[ci * 9 + r * 3 + q] = fmaf(gv, img[ci][h + r][wc + q], acc[ci * 9 + r * 3 + q]);
-        acc[27] += gv;
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[ci * 9 + r * 3 + q] = fmaf(gv[j], in[j + q], acc[ci * 9 + r * 3 + q]);
+            }
+        acc[27] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
     }
 #pragma unroll
     for (int i = 0; i < 28; ++i) part[g][c][i] = acc[i];
