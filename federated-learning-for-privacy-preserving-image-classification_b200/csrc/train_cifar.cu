@@ -558,25 +558,39 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(flb_train_args a
     const float4* z4 = reinterpret_cast<const float4*>(z_all + kb * g.PP() * C);
     float4* dz4 = reinterpret_cast<float4*>(dz_all + kb * g.PP() * C);
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    constexpr int C4 = C / 4;
-    const int c = (tid % C4) * 4;                          // fixed channel quad per thread (256 % C4 == 0)
+    constexpr int C4 = C / 4, LANES = 256 / C4;
+    const int c = (tid % C4) * 4, pl = tid / C4;           // fixed channel quad per thread, pixel lane
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int e = tid; e < g.PP() * C4; e += 256) {
-        const int r = e / C4, h = r / g.Wp, w = r - h * g.Wp;
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        if (h < g.H && w < g.W) {
-            const int pp = (h >> 1) * Wo + (w >> 1), pos = (h & 1) * 2 + (w & 1);
-            const float4 zv = z4[e];
-            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+    // REAL pixels only (H, W are powers of two: no divisions): this kernel is the only writer of its dz buffer, whose pad
+    // positions therefore keep the zeros of the workspace initialisation
+    const int wshift = 31 - __clz(g.W);
+    for (int p = pl; p < g.H * g.W; p += LANES) {
+        const int h = p >> wshift, w = p & (g.W - 1), e = (h * g.Wp + w) * C4 + (c >> 2);
+        const int pp = (h >> 1) * Wo + (w >> 1), pos = (h & 1) * 2 + (w & 1);
+        const float4 zv = z4[e];
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+        float gq[4];
+        if (FLAT) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int src = FLAT ? (c + q) * npool + pp : ((h >> 1) * go.Wp + (w >> 1)) * C + c + q;
-                const int code = idx[FLAT ? (c + q) * npool + pp : pp * C + c + q];
-                const float gv = (code == pos && pooled[src] > 0.f) ? dpool[src] * keep_scale : 0.f;     // bit 2 of code = dropped
-                const float xhat = (zz[q] - s_mean[c + q]) * s_invstd[c + q];
-                o[q] = s_c0[c + q] * (gv - s_c1[c + q] - xhat * s_c2[c + q]);
-                bsum[q] += o[q];
+                const int src = (c + q) * npool + pp;
+                gq[q] = (idx[src] == pos && pooled[src] > 0.f) ? dpool[src] * keep_scale : 0.f;     // bit 2 of the code = dropped
             }
+        } else {
+            const int src = ((h >> 1) * go.Wp + (w >> 1)) * C + c;
+            const uchar4 code = *reinterpret_cast<const uchar4*>(idx + pp * C + c);
+            const float4 pv = *reinterpret_cast<const float4*>(pooled + src), dv = *reinterpret_cast<const float4*>(dpool + src);
+            gq[0] = (code.x == pos && pv.x > 0.f) ? dv.x * keep_scale : 0.f;
+            gq[1] = (code.y == pos && pv.y > 0.f) ? dv.y * keep_scale : 0.f;
+            gq[2] = (code.z == pos && pv.z > 0.f) ? dv.z * keep_scale : 0.f;
+            gq[3] = (code.w == pos && pv.w > 0.f) ? dv.w * keep_scale : 0.f;
+        }
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xhat = (zz[q] - s_mean[c + q]) * s_invstd[c + q];
+            o[q] = s_c0[c + q] * (gq[q] - s_c1[c + q] - xhat * s_c2[c + q]);
+            bsum[q] += o[q];
         }
         dz4[e] = make_float4(o[0], o[1], o[2], o[3]);
     }
