@@ -214,6 +214,18 @@ __device__ __forceinline__ bool real_px(const ConvGeom& g, int r) {       // r =
     return h < g.H && (rr - h * g.Wp) < g.W;
 }
 
+// row (within the client's [B * PP] rows) of the q-th REAL pixel, q in [0, bsz * H * W): shifts only (H, W powers of two)
+__device__ __forceinline__ int real_row(const ConvGeom& g, int q, int hw_shift, int w_shift) {
+    const int b = q >> hw_shift, p = q & ((1 << hw_shift) - 1);
+    return b * g.PP() + (p >> w_shift) * g.Wp + (p & (g.W - 1));
+}
+// row of the j-th PAD position of a client, j in [0, bsz * (PP - H*W)): the pad column of every image row, then the tail rows
+__device__ __forceinline__ int pad_row(const ConvGeom& g, int j) {
+    const int npad = g.PP() - g.H * g.W, b = j / npad, t = j - b * npad;
+    const int rr = t < g.H * (g.Wp - g.W) ? (t / (g.Wp - g.W)) * g.Wp + g.W + t % (g.Wp - g.W) : g.H * g.Wp + (t - g.H * (g.Wp - g.W));
+    return b * g.PP() + rr;
+}
+
 // per-channel mean / invstd of client k for this step (train) or from the running buffers (eval)
 __device__ __forceinline__ void bn_moments(const flb_train_args& a, const double* acc, int k, int ch, int n_real,
                                            float& mean, float& invstd, float& var_b) {
@@ -245,8 +257,9 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGe
     if (bsz == 0) return;
     constexpr int C4 = C / 4, RL = 256 / C4;
     const int tid = threadIdx.x, cq = tid % C4, rl = tid / C4;
-    const int PP = g.PP(), rows = bsz * PP;
-    const int per = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+    const int PP = g.PP(), nreal = bsz * g.H * g.W;
+    const int hw_shift = 31 - __clz(g.H * g.W), w_shift = 31 - __clz(g.W);
+    const int per = (nreal + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(nreal, r0 + per);
     const long long base = (long long)k * a.B * PP * C;
     const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
     const float4* dy4 = MODE == 1 ? reinterpret_cast<const float4*>(dy_all + base) : nullptr;
@@ -262,9 +275,9 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(flb_train_args a, ConvGe
         }
     }
     float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-    auto row = [&](int r) {
-        if (r >= r1 || !real_px(g, r)) return;
-        const long long e = (long long)r * C4 + cq;
+    auto row = [&](int q_) {                               // q_: index of a real pixel
+        if (q_ >= r1) return;
+        const long long e = (long long)real_row(g, q_, hw_shift, w_shift) * C4 + cq;
         const float4 zv = z4[e];
         const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
         if (MODE == 0) {
@@ -323,22 +336,25 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(flb_train_args a, Co
         }
     }
     __syncthreads();
-    const int PP = g.PP(), rows = bsz * PP;
+    const int PP = g.PP();
     const long long base = (long long)k * a.B * PP * C;
     const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
     float4* y4 = reinterpret_cast<float4*>(y_all + base);
-    constexpr int C4 = C / 4;
-    const long long total = (long long)rows * C4;
-    for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
-        const int r = (int)(e / C4), c = (int)(e % C4) * 4;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (real_px(g, r)) {
-            const float4 v = z4[e];
-            o.x = fmaxf(__fadd_rn(__fmul_rn(v.x, s_scale[c]), s_beta[c]), 0.f);
-            o.y = fmaxf(__fadd_rn(__fmul_rn(v.y, s_scale[c + 1]), s_beta[c + 1]), 0.f);
-            o.z = fmaxf(__fadd_rn(__fmul_rn(v.z, s_scale[c + 2]), s_beta[c + 2]), 0.f);
-            o.w = fmaxf(__fadd_rn(__fmul_rn(v.w, s_scale[c + 3]), s_beta[c + 3]), 0.f);
-        }
+    constexpr int C4 = C / 4, RL = 256 / C4;
+    // real pixels only: this kernel is y's only writer, so the pads keep the zeros the workspace was created with.
+    // thread = (channel quad, pixel lane): its scale / shift live in registers, rows come from shifts
+    const int cq = tid % C4, rl = tid / C4, c = cq * 4;
+    const int hw_shift = 31 - __clz(g.H * g.W), w_shift = 31 - __clz(g.W);
+    const float sc[4] = {s_scale[c], s_scale[c + 1], s_scale[c + 2], s_scale[c + 3]};
+    const float sb[4] = {s_beta[c], s_beta[c + 1], s_beta[c + 2], s_beta[c + 3]};
+    for (int q = blockIdx.x * RL + rl; q < n_real; q += gridDim.x * RL) {
+        const long long e = (long long)real_row(g, q, hw_shift, w_shift) * C4 + cq;
+        const float4 v = z4[e];
+        float4 o;
+        o.x = fmaxf(__fadd_rn(__fmul_rn(v.x, sc[0]), sb[0]), 0.f);
+        o.y = fmaxf(__fadd_rn(__fmul_rn(v.y, sc[1]), sb[1]), 0.f);
+        o.z = fmaxf(__fadd_rn(__fmul_rn(v.z, sc[2]), sb[2]), 0.f);
+        o.w = fmaxf(__fadd_rn(__fmul_rn(v.w, sc[3]), sb[3]), 0.f);
         y4[e] = o;
     }
 }
@@ -437,35 +453,41 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
         }
     }
     __syncthreads();
-    const int PP = g.PP(), rows = bsz * PP;
+    const int PP = g.PP();
     const long long base = (long long)k * a.B * PP * C;
-    constexpr int C4 = C / 4;
+    constexpr int C4 = C / 4, RL = 256 / C4;
     float4* dy4 = reinterpret_cast<float4*>(dy_all + base);
     const float4* z4 = reinterpret_cast<const float4*>(z_all + base);
-    const long long total = (long long)rows * C4;
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};        // this thread always sees the same channel quad (256 % C4 == 0)
-    const int c = (tid % C4) * 4;
-    for (long long e = (long long)blockIdx.x * 256 + tid; e < total; e += (long long)gridDim.x * 256) {
-        const int r = (int)(e / C4);
-        float o[4] = {0.f, 0.f, 0.f, 0.f};
-        if (real_px(g, r)) {
-            const float4 gv4 = dy4[e], zv = z4[e];
-            float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
-            const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
-            if (relu_mask) {
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};        // thread = (channel quad, pixel lane)
+    const int cq = tid % C4, rl = tid / C4, c = cq * 4;
+    const int hw_shift = 31 - __clz(g.H * g.W), w_shift = 31 - __clz(g.W);
+    float k_al[4], k_be[4], k_c0[4], k_c1[4], k_mi[4], k_m2[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (!(__fadd_rn(__fmul_rn(zz[q], s_alpha[c + q]), s_beta[c + q]) > 0.f)) gv[q] = 0.f;
-            }
+    for (int q = 0; q < 4; ++q) {
+        k_al[q] = s_alpha[c + q]; k_be[q] = s_beta[c + q]; k_c0[q] = s_c0[c + q]; k_c1[q] = s_c1[c + q];
+        k_mi[q] = s_mean[c + q]; k_m2[q] = s_invstd[c + q] * s_c2[c + q];
+    }
+    for (int px = blockIdx.x * RL + rl; px < n_real; px += gridDim.x * RL) {
+        const long long e = (long long)real_row(g, px, hw_shift, w_shift) * C4 + cq;
+        const float4 gv4 = dy4[e], zv = z4[e];
+        float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w}, o[4];
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+        if (relu_mask) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float xhat = (zz[q] - s_mean[c + q]) * s_invstd[c + q];
-                o[q] = s_c0[c + q] * (gv[q] - s_c1[c + q] - xhat * s_c2[c + q]);
-                bsum[q] += o[q];
-            }
+            for (int q = 0; q < 4; ++q)
+                if (!(__fadd_rn(__fmul_rn(zz[q], k_al[q]), k_be[q]) > 0.f)) gv[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o[q] = k_c0[q] * (gv[q] - k_c1[q] - (zz[q] - k_mi[q]) * k_m2[q]);
+            bsum[q] += o[q];
         }
         dy4[e] = make_float4(o[0], o[1], o[2], o[3]);
     }
+    // the producer (a dgrad GEMM over the whole padded grid) leaves values on the pads: zero them for the next GEMMs
+    const int n_pad = bsz * (PP - g.H * g.W);
+    for (int j = blockIdx.x * RL + rl; j < n_pad; j += gridDim.x * RL)
+        dy4[(long long)pad_row(g, j) * C4 + cq] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (conv_boff >= 0) {                     // conv bias gradient = column sums of dz (tensor-core path; the fp32 wgrad
         __shared__ float red[4][256];         // GEMM carries it as an extra column).  Exactly zero in exact arithmetic.
 #pragma unroll
