@@ -107,6 +107,10 @@ __device__ __forceinline__ void q8_accum4(uint32_t word, float magic_z, float s,
     }
 }
 
+// EPT = parameters per thread: 16 (one 16 B load per client row) for long rows; 4 (one 4 B load, a warp still reads whole
+// 128 B lines) when P / 16 threads would leave most of the machine idle -- the client loop cannot be split, its adds
+// must stay in client order to remain bit-exact.
+template <int EPT>
 __global__ void __launch_bounds__(kThreads)
 fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __restrict__ scale,
                  const float* __restrict__ zp, const long long* __restrict__ seg_off,
@@ -114,39 +118,43 @@ fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __re
     extern __shared__ long long s_off[];
     for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
     __syncthreads();
-    const long long P16 = (P + 15) >> 4;
+    const long long PV = (P + EPT - 1) / EPT;
     const long long stride = (long long)gridDim.x * kThreads;
-    const bool vec_ok = (ldq & 15) == 0 && ((uintptr_t)q & 15) == 0;
-    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < P16; c += stride) {
-        const long long p = c << 4;
+    const bool vec_ok = (ldq & (EPT - 1)) == 0 && ((uintptr_t)q & (EPT - 1)) == 0;
+    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < PV; c += stride) {
+        const long long p = c * EPT;
         int lo = 0, hi = L;                       // largest l with s_off[l] <= p
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
-        const bool whole = vec_ok && (p + 15 < P) && (p + 15 < s_off[lo + 1]);
+        const bool whole = vec_ok && (p + EPT - 1 < P) && (p + EPT - 1 < s_off[lo + 1]);
         if (whole) {
-            float acc[16];
+            float acc[EPT];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-#pragma unroll 2
+            for (int e = 0; e < EPT; ++e) acc[e] = 0.f;
+#pragma unroll(EPT == 16 ? 2 : 8)
             for (int k = 0; k < K; ++k) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(q + (long long)k * ldq + p));
                 const float s = __ldg(&scale[(long long)k * L + lo]);
                 const float magic_z = 8388608.0f + __ldg(&zp[(long long)k * L + lo]);     // exact: zp is an integer < 2^16
                 const float wk = __ldg(&w[k]);
-                q8_accum4(v.x, magic_z, s, wk, acc);
-                q8_accum4(v.y, magic_z, s, wk, acc + 4);
-                q8_accum4(v.z, magic_z, s, wk, acc + 8);
-                q8_accum4(v.w, magic_z, s, wk, acc + 12);
+                if (EPT == 16) {
+                    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(q + (long long)k * ldq + p));
+                    q8_accum4(v.x, magic_z, s, wk, acc);
+                    q8_accum4(v.y, magic_z, s, wk, acc + 4);
+                    q8_accum4(v.z, magic_z, s, wk, acc + 8);
+                    q8_accum4(v.w, magic_z, s, wk, acc + 12);
+                } else {
+                    q8_accum4(__ldcs(reinterpret_cast<const uint32_t*>(q + (long long)k * ldq + p)), magic_z, s, wk, acc);
+                }
             }
             float4* o4 = reinterpret_cast<float4*>(out + p);
             if (((uintptr_t)out & 15) == 0) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+                for (int e = 0; e < EPT / 4; ++e) o4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
             } else {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) out[p + e] = acc[e];
+                for (int e = 0; e < EPT; ++e) out[p + e] = acc[e];
             }
         } else {
-            for (long long e = p; e < min(p + 16, P); ++e) {
+            for (long long e = p; e < min(p + EPT, P); ++e) {
                 int l = lo;
                 while (e >= s_off[l + 1]) ++l;
                 float a = 0.f;
@@ -203,8 +211,11 @@ extern "C" int flb_fedavg_weighted_sum_q8(const uint8_t* q, long long ldq, const
     FLB_CHECK_ARG(q && scale && zp && seg_off && w && out, "flb_fedavg_weighted_sum_q8: null pointer");
     FLB_CHECK_ARG(K >= 1 && L >= 1 && L <= 4096 && ldq >= P, "flb_fedavg_weighted_sum_q8: bad K/L/ldq");
     if (P == 0) return FLB_OK;
-    fedavg_q8_kernel<<<grid_for((P + 15) / 16), kThreads, (L + 1) * sizeof(long long), (cudaStream_t)stream>>>(
-        q, ldq, scale, zp, seg_off, w, out, K, L, P);
+    const size_t smem = (L + 1) * sizeof(long long);
+    if ((P + 15) / 16 >= (long long)flb_num_sms() * 1536)        // enough 16-parameter threads to fill the machine
+        fedavg_q8_kernel<16><<<grid_for((P + 15) / 16), kThreads, smem, (cudaStream_t)stream>>>(q, ldq, scale, zp, seg_off, w, out, K, L, P);
+    else
+        fedavg_q8_kernel<4><<<grid_for((P + 3) / 4), kThreads, smem, (cudaStream_t)stream>>>(q, ldq, scale, zp, seg_off, w, out, K, L, P);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

@@ -37,14 +37,18 @@ __device__ __forceinline__ float flb_u01(uint32_t x) {
     return fminf(u, 0.99999994f);
 }
 
-// four standard normals for one Philox block
+// four standard normals for one Philox block.  The clip + noise kernel is ALU-bound on this function (Philox is ~100
+// integer instructions per block), so the transcendental part uses the hardware approximations: lg2.approx (absolute
+// error < 2^-22 in log2 u), x * rsqrt(x) for the square root, and sin/cos.approx on an argument reduced to [-pi, pi)
+// (absolute error < 2^-20.9); the results agree with the double-precision transform of oracle/philox.py to ~2e-6.
 __device__ __forceinline__ float4 flb_normal4(unsigned long long seed, unsigned long long stream,
                                               unsigned long long block) {
     const flb_u4 r = flb_philox_block(seed, stream, block);
-    const float r0 = sqrtf(-2.0f * logf(flb_u01(r.x)));
-    const float r1 = sqrtf(-2.0f * logf(flb_u01(r.z)));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * flb_u01(r.y), &s0, &c0);
-    sincospif(2.0f * flb_u01(r.w), &s1, &c1);
-    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+    // -2 ln u = -2 ln2 * log2 u; clamped away from 0 (u < 1, but the approximation may return +0 next to 1)
+    const float x0 = fmaxf(-1.3862943611198906f * __log2f(flb_u01(r.x)), 1e-30f);
+    const float x1 = fmaxf(-1.3862943611198906f * __log2f(flb_u01(r.z)), 1e-30f);
+    const float r0 = -(x0 * rsqrtf(x0)), r1 = -(x1 * rsqrtf(x1));       // minus: the angle below is shifted by pi
+    const float t0 = fmaf(flb_u01(r.y), 6.283185307179586f, -3.141592653589793f);
+    const float t1 = fmaf(flb_u01(r.w), 6.283185307179586f, -3.141592653589793f);
+    return make_float4(r0 * __cosf(t0), r0 * __sinf(t0), r1 * __cosf(t1), r1 * __sinf(t1));
 }
