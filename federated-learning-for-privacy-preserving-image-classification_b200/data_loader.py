@@ -28,6 +28,26 @@ MNIST_MEAN_STD = ((0.1307,), (0.3081,))                                        #
 CIFAR10_MEAN_STD = ((0.4914, 0.4822, 0.4465), (0.2023, 0.1994, 0.2010))        # data_loader.py:454-464
 
 
+class FederatedDataset(torch.utils.data.Dataset):
+    """One client's view of the base dataset (src/shared/data_loader.py:22-62): an index list, no copy."""
+
+    def __init__(self, base_dataset, client_id: str, indices: List[int]):
+        self.base_dataset, self.client_id, self.indices = base_dataset, client_id, indices
+
+    def __len__(self) -> int:
+        return len(self.indices)
+
+    def __getitem__(self, idx: int):
+        return self.base_dataset[self.indices[idx]]
+
+    def get_statistics(self) -> Dict[str, Any]:
+        counts: Dict[int, int] = defaultdict(int)
+        for i in self.indices:
+            counts[int(self.base_dataset[i][1])] += 1
+        return {"client_id": self.client_id, "total_samples": len(self.indices), "class_distribution": dict(counts),
+                "num_classes": len(counts)}
+
+
 class DataPartitioner:
     """src/shared/data_loader.py:65-264.  ``dataset`` is anything indexable as ``dataset[i] -> (x, label)``; pass
     ``labels=`` to skip the per-item label extraction (:101-107) for large datasets."""
@@ -118,6 +138,11 @@ class DataPartitioner:
                 if available:
                     client_indices[cid].extend(random.sample(available, min(need, len(available))))
         return dict(client_indices)
+
+    def get_client_dataset(self, client_id: int) -> FederatedDataset:
+        if client_id not in self.client_indices:
+            raise ValueError(f"Client {client_id} not found")
+        return FederatedDataset(self.dataset, str(client_id), self.client_indices[client_id])
 
     def get_partition_statistics(self) -> Dict[str, Any]:
         stats = {"num_clients": self.num_clients, "partition_strategy": self.partition_strategy,

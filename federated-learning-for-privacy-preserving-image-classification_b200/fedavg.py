@@ -307,3 +307,32 @@ class AdaptiveFedAvg(FedAvgAggregator):
 
 def create_fedavg_aggregator(aggregator_type: str = "standard", **kwargs) -> FedAvgAggregator:
     return AdaptiveFedAvg(**kwargs) if aggregator_type == "adaptive" else FedAvgAggregator(**kwargs)
+
+
+def benchmark_aggregation_performance(num_clients_list: List[int] = (5, 10, 25, 50), model_size: int = 1000000,
+                                      device=None) -> Dict[str, Any]:
+    """Same report as the reference's helper (src/aggregation/fedavg.py:487-546: four equal random layers per client, random
+    sample counts, `validate_updates=False`) with the client tensors on the CUDA device; `aggregation_time` is the wall
+    clock around `aggregate_updates` + a device synchronize.  bench.py / scripts/fedavg_sweep.py are the measured versions."""
+    import time
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    results: Dict[str, Any] = {}
+    for n in num_clients_list:
+        try:
+            updates = [ModelUpdate(client_id=f"client_{i}", round_number=1,
+                                   model_weights={f"layer{j}": torch.randn(model_size // 4, device=dev) for j in range(1, 5)},
+                                   num_samples=int(np.random.randint(100, 1000)), training_loss=float(np.random.uniform(0.1, 2.0)),
+                                   privacy_budget_used=0.1, compression_ratio=0.8, timestamp=datetime.now()) for i in range(n)]
+            agg = FedAvgAggregator(validate_updates=False)
+            torch.cuda.synchronize(dev)
+            t0 = time.time()
+            model = agg.aggregate_updates(updates)
+            torch.cuda.synchronize(dev)
+            dt = time.time() - t0
+            results[f"{n}_clients"] = {"aggregation_time": dt, "throughput": n / dt,
+                                       "memory_usage": sum(w.numel() * w.element_size() for w in model.model_weights.values()),
+                                       "participating_clients": len(model.participating_clients)}
+        except Exception as e:
+            logger.error(f"Benchmark failed for {n} clients: {str(e)}")
+            results[f"{n}_clients"] = {"error": str(e)}
+    return results

@@ -613,3 +613,42 @@ class FederatedTrainingConfig:
     @classmethod
     def from_dict(cls, config_dict: Dict[str, Any]) -> "FederatedTrainingConfig":
         return cls(**config_dict)
+
+
+def create_adaptive_config(client_capabilities: Dict[str, Any]) -> FederatedTrainingConfig:
+    """Per-client hyper-parameters from its declared capabilities (src/shared/training.py:455-501): host logic only.
+    Note the kernels take batches of at most 32 samples; a 'high' power client's batch of 64/128 must be split by the caller."""
+    power = client_capabilities.get("compute_power", "medium")
+    bandwidth = client_capabilities.get("network_bandwidth", 10)
+    samples = client_capabilities.get("available_samples", 1000)
+    epochs, batch, lr = {"high": (10, 64, 0.001), "medium": (5, 32, 0.001)}.get(power, (3, 16, 0.0005))
+    if samples < 500:
+        batch = min(batch, 16)
+    elif samples > 5000:
+        batch = min(batch * 2, 128)
+    if bandwidth < 5:                       # slow uplink: more local work per round
+        epochs = max(epochs + 2, 7)
+    return FederatedTrainingConfig(local_epochs=epochs, batch_size=batch, learning_rate=lr, optimizer_type="adam",
+                                   early_stopping_patience=None, save_checkpoints=True, validation_split=0.1)
+
+
+def validate_training_data(train_loader) -> Dict[str, Any]:
+    """Pre-flight check of a loader (src/shared/training.py:504-560): never raises, returns {'valid': ...}."""
+    try:
+        if len(train_loader) == 0:
+            raise ValueError("Training data loader is empty")
+        batch = next(iter(train_loader))
+        if len(batch) != 2:
+            raise ValueError("Expected (data, targets) tuple from data loader")
+        data, targets = batch
+        if not isinstance(data, torch.Tensor):
+            raise ValueError("Data must be a torch.Tensor")
+        if not isinstance(targets, torch.Tensor):
+            raise ValueError("Targets must be a torch.Tensor")
+        if data.dim() != 4:
+            raise ValueError(f"Expected 4D data tensor, got shape {data.shape}")
+        return {"valid": True, "num_batches": len(train_loader), "batch_size": data.shape[0], "data_shape": tuple(data.shape[1:]),
+                "num_classes": len(torch.unique(targets)), "data_type": str(data.dtype), "targets_type": str(targets.dtype)}
+    except Exception as e:
+        logger.error(f"Training data validation failed: {str(e)}")
+        return {"valid": False, "error": str(e)}

@@ -45,10 +45,52 @@ def seeded_batches(model, seed, n, bs):
     return x, y, [(x[i:i + bs], y[i:i + bs]) for i in range(0, n, bs)]
 
 
+def convergence_sequence(seed: int = 21, rounds: int = 8):
+    """Seeded sequence of global models with shrinking steps (SimpleCNN shapes): [(weights, accuracy_metrics)]."""
+    from oracle import models as OM
+    g = torch.Generator().manual_seed(seed)
+    w = OM.init_weights("simple_cnn", seed)
+    seq = []
+    for r in range(rounds):
+        w = {k: v + (0.05 * 0.35 ** r) * torch.randn(v.shape, generator=g) for k, v in w.items()}
+        seq.append((w, {"test_accuracy": min(0.8, 0.5 + 0.08 * r) - (0.03 if r == 5 else 0.0), "train_loss": 1.5 * 0.7 ** r + (0.2 if r == 6 else 0.0)}))
+    return seq
+
+
+def convergence_golden(out_dir: str) -> None:
+    """---- 8. ConvergenceDetector: the unmodified reference on the seeded sequence ----"""
+    from src.aggregation.convergence import create_convergence_detector
+    from src.shared.models import GlobalModel
+    out = {}
+    for kind in ("standard", "adaptive"):
+        det = create_convergence_detector(kind, patience=3)
+        prev, rows, stops = None, [], []
+        for r, (w, accm) in enumerate(convergence_sequence()):
+            cur = GlobalModel(round_number=r, model_weights=w, accuracy_metrics=accm, participating_clients=["c0"],
+                              convergence_score=0.0, created_at=datetime.now())
+            m = det.calculate_convergence_metrics(cur, prev)
+            rows.append([m.weight_change_norm, m.relative_weight_change, m.accuracy_change, m.loss_change, m.convergence_score,
+                         float(m.is_converged), m.confidence, det.convergence_threshold])
+            stops.append(det.should_stop_early()[1])
+            prev = cur
+        out[f"{kind}/rows"] = np.asarray(rows, dtype=np.float64)
+        out[f"{kind}/stop_reasons"] = np.asarray(stops)
+        out[f"{kind}/trend"] = np.asarray(det.get_convergence_summary()["recent_performance"]["convergence_trend"])
+    np.savez_compressed(os.path.join(out_dir, "convergence.npz"), **out)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--only-convergence", action="store_true", help="write tests/golden/convergence.npz only")
     args = ap.parse_args()
+    if args.only_convergence:
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, args.ref)
+        torch.set_num_threads(1)
+        convergence_golden(OUT)
+        print("convergence golden written to", OUT)
+        return
     sys.dont_write_bytecode = True
     sys.path.insert(0, args.ref)
     sys.modules.setdefault("lz4", types.ModuleType("lz4"))
@@ -247,6 +289,8 @@ def main() -> None:
             for cid, idx in part.client_indices.items():
                 out[f"{strat}/{nc}/{cid}"] = np.asarray(idx, dtype=np.int64)
     np.savez_compressed(os.path.join(OUT, "partition.npz"), **out)
+
+    convergence_golden(OUT)
 
     with open(os.path.join(OUT, "README.md"), "w") as f:
         f.write("# Golden vectors\n\nWritten by `python -m oracle.make_golden` from the unmodified reference "

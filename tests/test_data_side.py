@@ -30,6 +30,23 @@ def test_partitioner_matches_reference_golden(strategy, num_clients):
         DataPartitioner(None, 3, "sorted", labels=labels)
 
 
+def test_client_dataset_view():
+    from flb200.data_loader import DataPartitioner, FederatedDataset
+    y = [i % 5 for i in range(200)]
+    base = [(torch.full((1,), float(i)), y[i]) for i in range(200)]
+    random.seed(1)
+    part = DataPartitioner(base, 4, "iid")
+    ds = part.get_client_dataset(2)
+    assert isinstance(ds, FederatedDataset) and ds.client_id == "2" and len(ds) == len(part.client_indices[2])
+    x0, y0 = ds[0]
+    assert int(x0.item()) == part.client_indices[2][0] and y0 == y[part.client_indices[2][0]]
+    st = ds.get_statistics()
+    assert st["total_samples"] == len(ds) and sum(st["class_distribution"].values()) == len(ds)
+    assert st == part.get_partition_statistics()["client_statistics"][2]
+    with pytest.raises(ValueError, match="Client 9 not found"):
+        part.get_client_dataset(9)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["mnist", "cifar"])
 def test_device_shard_builder_is_totensor_normalize(cuda_device, kind):

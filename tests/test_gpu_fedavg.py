@@ -141,3 +141,16 @@ def test_full_size_linearity_property(cuda_device):
     cols = torch.randint(0, P, (1000,), generator=torch.Generator().manual_seed(2))
     ref = OF.weighted_average_flat(theta[:, cols.to(cuda_device)].cpu().numpy(), w)
     assert np.array_equal(base[cols.to(cuda_device)].cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_benchmark_helper_report_shape(cuda_device):
+    """fedavg.py:487-546: same keys per client count, memory = 4 layers x (size // 4) fp32."""
+    from flb200.fedavg import benchmark_aggregation_performance
+    r = benchmark_aggregation_performance([3, 6], model_size=40000, device=cuda_device)
+    assert sorted(r) == ["3_clients", "6_clients"]
+    for n in (3, 6):
+        row = r[f"{n}_clients"]
+        assert row["participating_clients"] == n and row["memory_usage"] == 40000 * 4
+        assert row["aggregation_time"] > 0 and abs(row["throughput"] * row["aggregation_time"] - n) < 1e-9
+    assert "error" in benchmark_aggregation_performance([1], model_size=400, device=cuda_device)["1_clients"]     # < min_clients
