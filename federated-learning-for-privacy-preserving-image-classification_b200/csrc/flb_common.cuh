@@ -51,6 +51,18 @@ int flb_num_sms();   // SM count of the current device (148 on B200), cached
 
 static inline int flb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// CTAs of `kernel` that are resident at once on the whole device (occupancy API x SM count).  Grid-stride kernels whose
+// CTAs live for the whole launch are sized to AT MOST this many: a few CTAs beyond one wave double the duration.
+template <class F>
+static inline int flb_resident_ctas(F kernel, int threads, size_t dyn_smem = 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    return per_sm * flb_num_sms();
+}
+
 __device__ __forceinline__ float flb_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -143,9 +143,11 @@ __global__ void philox_raw_kernel(uint32_t* __restrict__ out, long long nblocks,
     }
 }
 
-int blocks_per_client(long long P, int K) {
+// grid.x of a (blocks, K) launch of a grid-stride kernel: whole waves of its resident CTA count (flb_resident_ctas) --
+// one wave when the clients fit, else two; never a fraction of a wave beyond
+int blocks_per_client(long long P, int K, int resident) {
     const long long want = (P / 4 + kThreads - 1) / kThreads;
-    long long cap = ((long long)flb_num_sms() * 8 + K - 1) / K;      // ~8 CTAs per SM over all clients
+    long long cap = resident / K;
     if (cap < 1) cap = 1;
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
@@ -160,7 +162,8 @@ extern "C" int flb_dp_sumsq(const float* local, long long ld, const float* globa
     FLB_CUDA(cudaMemsetAsync(norm2, 0, sizeof(double) * K, st));
     if (P == 0) return FLB_OK;
     const bool vec = (ld % 4 == 0) && ((uintptr_t)local % 16 == 0) && (!global_w || (uintptr_t)global_w % 16 == 0);
-    dim3 grid(blocks_per_client(P, K), K);
+    static const int resident = flb_resident_ctas(dp_sumsq_kernel<true>, kThreads);
+    dim3 grid(blocks_per_client(P, K, resident), K);
     if (vec) dp_sumsq_kernel<true><<<grid, kThreads, 0, st>>>(local, ld, global_w, norm2, P);
     else dp_sumsq_kernel<false><<<grid, kThreads, 0, st>>>(local, ld, global_w, norm2, P);
     FLB_LAUNCH_CHECK();
@@ -178,7 +181,8 @@ extern "C" int flb_dp_clip_noise(const float* local, long long ld, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (ld % 4 == 0) && ((uintptr_t)local % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      (!global_w || (uintptr_t)global_w % 16 == 0) && (!z_in || (uintptr_t)z_in % 16 == 0);
-    dim3 grid(blocks_per_client(P, K), K);
+    static const int resident = flb_resident_ctas(dp_clip_noise_kernel<true>, kThreads);
+    dim3 grid(blocks_per_client(P, K, resident), K);
     if (vec) dp_clip_noise_kernel<true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
     else dp_clip_noise_kernel<false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
     FLB_LAUNCH_CHECK();
@@ -190,7 +194,8 @@ extern "C" int flb_dp_add_noise(const float* x, long long ld, const float* z_in,
     FLB_CHECK_ARG(x && out, "flb_dp_add_noise: null pointer");
     FLB_CHECK_ARG(K >= 1 && K <= 65535 && P >= 0 && ld >= P && sigma >= 0.0, "flb_dp_add_noise: bad K/P/ld/sigma");
     if (P == 0) return FLB_OK;
-    dim3 grid(blocks_per_client(P, K), K);
+    static const int resident = flb_resident_ctas(dp_add_noise_kernel, kThreads);
+    dim3 grid(blocks_per_client(P, K, resident), K);
     dp_add_noise_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, ld, z_in, out, (float)sigma, seed, stream_base, P);
     FLB_LAUNCH_CHECK();
     return FLB_OK;

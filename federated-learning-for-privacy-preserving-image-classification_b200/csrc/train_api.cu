@@ -30,129 +30,190 @@ __global__ void __launch_bounds__(256) tc_repack_kernel(flb_train_args a, TcConv
     }
 }
 
-__device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, const TcConvTab& tab, int k, int bsz);
+// Scalars of one optimizer step of one client: formed in double and rounded to fp32 once, like Python floats entering
+// fp32 tensor ops.
+struct OptScalars {
+    float step_size, inv_bc2_sqrt, lr, omb1, b2, omb2, eps, decay, mu, inv_b, sigma;
+    int t;
+};
 
-// grid (blocks, K).  Also advances the minibatch counter and the clients' optimizer step counts (what
+__device__ __forceinline__ float sqrt_fast(float x) {        // <= 1 ulp, exact 0 -> 0 (v can be exactly zero)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// One element.  OPT: 0 Adam, 1 SGD(momentum), 2 AdamW.  DP: g is the sum of clipped per-sample gradients, z a standard normal.
+template <int OPT, bool DP>
+__device__ __forceinline__ void opt_update(const OptScalars& c, float g, float z, float& w, float& m, float& v) {
+    if (DP) g = (g + c.sigma * z) * c.inv_b;                // (sum clipped + N(0, sigma^2)) / B
+    if (OPT == 1) {                                         // SGD with momentum, dampening 0
+        const float buf = c.t == 1 ? g : fmaf(c.mu, m, g);
+        m = buf;
+        w = w - c.lr * buf;
+    } else {
+        if (OPT == 2) w = w * c.decay;                      // AdamW decoupled decay
+        m = m + (g - m) * c.omb1;                           // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * c.b2 + c.omb2 * g * g;                      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        // denom = sqrt(v) / sqrt(1 - b2^t) + eps; param.addcdiv_(m, denom, -step_size).  Square root and division use
+        // the hardware approximations (<= 2 ulp): Adam trajectories are compared at +-lr granularity anyway
+        // (conftest.adam_trajectory_check) and the IEEE forms made this kernel instruction-bound (ncu).
+        const float denom = fmaf(sqrt_fast(v), c.inv_bc2_sqrt, c.eps);
+        w = w - c.step_size * __fdividef(m, denom);
+    }
+}
+
+// grid (blocks, K).  One specialisation per (optimizer, DP mode, tensor-core weight table) so that the loop body is
+// straight-line code; the quad of the NEXT iteration is loaded before the current one is processed (the kernel is a
+// single wave of ~7 iterations per thread: without the prefetch every iteration exposes a full DRAM round trip -- ncu
+// showed 35 % of the DRAM peak).  Also advances the minibatch counter and the clients' optimizer step counts (what
 // flb_train_advance does on its own for the forward-only path).
-__global__ void __launch_bounds__(256) optimizer_kernel(flb_train_args a, int P, TcConvTab tab) {
-    const int k = blockIdx.y;
+template <int OPT, bool DP, bool TAB>
+__global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int P, TcConvTab tab) {
+    const int k = blockIdx.y, tid = threadIdx.x;
     const int bsz = flb_bsz(a, k);
-    if (bsz > 0) optimizer_body(a, P, tab, k, bsz);
+    __shared__ OptScalars s_c;
+    if (bsz > 0) {
+        // distinct buffers (rows of four different matrices; rows are 128 B aligned: ld % 32 == 0)
+        float* __restrict__ W = a.W + (long long)k * a.ld;
+        float* __restrict__ G = a.G + (long long)k * a.ld;
+        float* __restrict__ M = a.M + (long long)k * a.ld;
+        float* __restrict__ V = a.V + (long long)k * a.ld;
+        const float* __restrict__ zrow = (DP && a.dp_z) ? a.dp_z + (long long)k * a.ld : nullptr;
+        const int t = a.tcount[k] + 1;
+        const int nq = P >> 2, stride = gridDim.x * 256;
+        const bool need_m = OPT != 1 || t > 1;
+        int c4 = blockIdx.x * 256 + tid;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = g4, m4 = g4, v4 = g4, z4 = g4;
+        auto load = [&](int c, float4& g, float4& w, float4& m, float4& v, float4& z) {
+            g = reinterpret_cast<const float4*>(G)[c];
+            w = reinterpret_cast<const float4*>(W)[c];
+            if (need_m) m = reinterpret_cast<const float4*>(M)[c];
+            if (OPT != 1) v = reinterpret_cast<const float4*>(V)[c];
+            if (DP && zrow) z = reinterpret_cast<const float4*>(zrow)[c];
+        };
+        bool have = c4 < nq;
+        if (have) load(c4, g4, w4, m4, v4, z4);             // in flight while thread 0 forms the scalars (pow in double)
+        if (tid == 0) {
+            OptScalars c;
+            // beta^t by binary exponentiation (<= 2 log2 t dependent double multiplies; libm pow() is hundreds of
+            // instructions on one thread while the CTA waits at the barrier below)
+            double p1 = 1.0, p2 = 1.0, q1 = a.beta1, q2 = a.beta2;
+            for (int e = t; e > 0; e >>= 1) {
+                if (e & 1) { p1 *= q1; p2 *= q2; }
+                q1 *= q1; q2 *= q2;
+            }
+            const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+            c.step_size = (float)(a.lr / bc1);
+            c.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+            c.lr = (float)a.lr; c.omb1 = (float)(1.0 - a.beta1); c.b2 = (float)a.beta2; c.omb2 = (float)(1.0 - a.beta2);
+            c.eps = (float)a.eps; c.decay = (float)(1.0 - a.lr * a.weight_decay); c.mu = (float)a.momentum;
+            c.inv_b = 1.f / (float)bsz; c.sigma = a.dp_sigma; c.t = t;
+            s_c = c;
+        }
+        __syncthreads();
+        const OptScalars c = s_c;
+        float* __restrict__ wt = tab.wt + (long long)k * tab.ldt;
+        const float* __restrict__ gt = tab.gt + (long long)k * tab.ldt;
+        int tab_lo = 0x7fffffff, tab_hi = 0;
+        if (TAB)
+            for (int i = 0; i < tab.n; ++i) {
+                tab_lo = min(tab_lo, tab.woff[i]);
+                tab_hi = max(tab_hi, tab.woff[i] + tab.cout[i] * tab.cin[i] * 9);
+            }
+        while (have) {
+            const int nxt = c4 + stride;
+            const bool have_n = nxt < nq;
+            float4 gn = make_float4(0.f, 0.f, 0.f, 0.f), wn = gn, mn = gn, vn = gn, zn = gn;
+            if (have_n) load(nxt, gn, wn, mn, vn, zn);
+            const int p0 = c4 * 4;
+            float g[4] = {g4.x, g4.y, g4.z, g4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w},
+                  v[4] = {v4.x, v4.y, v4.z, v4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
+            int q[4] = {-1, -1, -1, -1};
+            const bool mapped = TAB && p0 + 3 >= tab_lo && p0 < tab_hi;     // quad touches a tensor-core conv weight range
+            if (mapped) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int layer = 0;
+                    q[e] = tc_tab_map(tab, p0 + e, layer);
+                    if (q[e] >= 0 && tab.gt_live[layer]) g[e] = gt[q[e]];
+                }
+            }
+            if (p0 < tab.g_zero_upto) reinterpret_cast<float4*>(G)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (DP && c.sigma > 0.f && !zrow) {
+                const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
+                z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) opt_update<OPT, DP>(c, g[e], z[e], w[e], m[e], v[e]);
+            reinterpret_cast<float4*>(W)[c4] = make_float4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<float4*>(M)[c4] = make_float4(m[0], m[1], m[2], m[3]);
+            if (OPT != 1) reinterpret_cast<float4*>(V)[c4] = make_float4(v[0], v[1], v[2], v[3]);
+            if (mapped) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (q[e] >= 0) wt[q[e]] = w[e];
+            }
+            c4 = nxt; have = have_n;
+            g4 = gn; w4 = wn; m4 = mn; v4 = vn; z4 = zn;
+        }
+        if (blockIdx.x == 0 && tid == 0) {                 // the P % 4 parameters after the last whole quad
+            for (int p = nq * 4; p < P; ++p) {
+                float g = G[p], w = W[p], m = M[p], v = V[p], z = 0.f;
+                int layer = 0;
+                const int q = TAB ? tc_tab_map(tab, p, layer) : -1;
+                if (q >= 0 && tab.gt_live[layer]) g = gt[q];
+                if (p < tab.g_zero_upto) G[p] = 0.f;
+                if (DP) {
+                    if (zrow) z = zrow[p];
+                    else if (c.sigma > 0.f) {
+                        const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + (p >> 2));
+                        const float za[4] = {zz.x, zz.y, zz.z, zz.w};
+                        z = za[p & 3];
+                    }
+                }
+                opt_update<OPT, DP>(c, g, z, w, m, v);
+                W[p] = w; M[p] = m;
+                if (OPT != 1) V[p] = v;
+                if (q >= 0) wt[q] = w;
+            }
+        }
+    }
     // The last CTA to finish advances the step: every CTA has read *step_ctr / tcount before it takes its ticket.
     __shared__ int s_last;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         __threadfence();
         const int ticket = atomicAdd(&a.step_ctr[1], 1);
         s_last = ticket == (int)(gridDim.x * gridDim.y) - 1;
     }
     __syncthreads();
     if (s_last) {
-        for (int c = threadIdx.x; c < a.K; c += blockDim.x)
+        for (int c = tid; c < a.K; c += blockDim.x)
             if (flb_bsz(a, c) > 0) a.tcount[c] += 1;
         __syncthreads();
-        if (threadIdx.x == 0) { a.step_ctr[0] += 1; a.step_ctr[1] = 0; __threadfence(); }
+        if (tid == 0) { a.step_ctr[0] += 1; a.step_ctr[1] = 0; __threadfence(); }
     }
 }
 
-__device__ __forceinline__ void optimizer_body(const flb_train_args& a, int P, const TcConvTab& tab, int k, int bsz) {
-    const int t = a.tcount[k] + 1;
-    // distinct buffers (rows of four different matrices): __restrict__ lets the loads of the next quad fly past the stores
-    float* __restrict__ W = a.W + (long long)k * a.ld;
-    float* __restrict__ G = a.G + (long long)k * a.ld;
-    float* __restrict__ M = a.M + (long long)k * a.ld;
-    float* __restrict__ V = a.V + (long long)k * a.ld;
-    // scalars are formed in double and rounded to fp32 once, like Python floats entering fp32 tensor ops
-    // (one thread per CTA: pow() in double is hundreds of instructions)
-    __shared__ float s_sc[2];
-    if (threadIdx.x == 0) {
-        const double bc1d = 1.0 - pow(a.beta1, (double)t), bc2d = 1.0 - pow(a.beta2, (double)t);
-        s_sc[0] = (float)(a.lr / bc1d);
-        s_sc[1] = (float)(1.0 / sqrt(bc2d));
-    }
-    __syncthreads();
-    const float step_size = s_sc[0], inv_bc2_sqrt = s_sc[1];
-    const float lr = (float)a.lr, omb1 = (float)(1.0 - a.beta1), b2 = (float)a.beta2, omb2 = (float)(1.0 - a.beta2);
-    const float eps = (float)a.eps, decay = (float)(1.0 - a.lr * a.weight_decay), mu = (float)a.momentum;
-    const float inv_b = 1.f / (float)bsz;
-    const float* zrow = a.dp_z ? a.dp_z + (long long)k * a.ld : nullptr;
-    float* __restrict__ wt = tab.wt + (long long)k * tab.ldt;
-    const float* __restrict__ gt = tab.gt + (long long)k * tab.ldt;
-    const int P4 = (P + 3) >> 2;
-    const bool adam = a.opt != 1;
-    int tab_lo = 0x7fffffff, tab_hi = 0;
-    for (int i = 0; i < tab.n; ++i) {
-        tab_lo = min(tab_lo, tab.woff[i]);
-        tab_hi = max(tab_hi, tab.woff[i] + tab.cout[i] * tab.cin[i] * 9);
-    }
-#pragma unroll 2
-    for (int c4 = blockIdx.x * 256 + threadIdx.x; c4 < P4; c4 += gridDim.x * 256) {
-        const int p0 = c4 * 4;
-        const bool whole = p0 + 3 < P;           // rows are 128 B aligned (ld % 32 == 0): 16 B vector access per quad
-        float g[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
-        float z[4] = {0.f, 0.f, 0.f, 0.f};
-        int q[4] = {-1, -1, -1, -1};
-        if (whole) {
-            const float4 g4 = *reinterpret_cast<const float4*>(G + p0), w4 = *reinterpret_cast<const float4*>(W + p0);
-            g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
-            w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
-            if (adam || t > 1) { const float4 m4 = *reinterpret_cast<const float4*>(M + p0); m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w; }
-            if (adam) { const float4 v4 = *reinterpret_cast<const float4*>(V + p0); v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w; }
-            if (a.dp_mode == 1 && zrow) { const float4 z4 = *reinterpret_cast<const float4*>(zrow + p0); z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w; }
-        } else {
-            for (int e = 0; e < 4 && p0 + e < P; ++e) {
-                g[e] = G[p0 + e]; w[e] = W[p0 + e]; m[e] = M[p0 + e]; v[e] = V[p0 + e];
-                if (a.dp_mode == 1 && zrow) z[e] = zrow[p0 + e];
-            }
-        }
-        const bool mapped = tab.n && p0 + 3 >= tab_lo && p0 < tab_hi;     // quad touches a tensor-core conv weight range
-        if (mapped) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                int layer = 0;
-                q[e] = p0 + e < P ? tc_tab_map(tab, p0 + e, layer) : -1;
-                if (q[e] >= 0 && tab.gt_live[layer]) g[e] = gt[q[e]];
-            }
-        }
-        if (p0 < tab.g_zero_upto) {
-            if (whole) *reinterpret_cast<float4*>(G + p0) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (int e = 0; e < 4 && p0 + e < P; ++e) G[p0 + e] = 0.f;
-        }
-        if (a.dp_mode == 1 && a.dp_sigma > 0.f && !zrow) {
-            const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
-            z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (a.dp_mode == 1) g[e] = (g[e] + a.dp_sigma * z[e]) * inv_b;     // (sum clipped + N(0, sigma^2)) / B
-            if (!adam) {                                    // SGD with momentum, dampening 0
-                const float buf = t == 1 ? g[e] : fmaf(mu, m[e], g[e]);
-                m[e] = buf;
-                w[e] = w[e] - lr * buf;
-            } else {
-                if (a.opt == 2) w[e] = w[e] * decay;        // AdamW decoupled decay
-                m[e] = m[e] + (g[e] - m[e]) * omb1;         // exp_avg.lerp_(grad, 1 - beta1)
-                v[e] = v[e] * b2 + omb2 * g[e] * g[e];      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-                // denom = sqrt(v) / sqrt(1 - b2^t) + eps; param.addcdiv_(m, denom, -step_size).  The two divisions use the
-                // fast reciprocal forms (<= 2 ulp): Adam trajectories are compared at +-lr granularity anyway
-                // (conftest.adam_trajectory_check) and IEEE division made this kernel instruction-bound (ncu).
-                const float denom = fmaf(__fsqrt_rn(v[e]), inv_bc2_sqrt, eps);
-                w[e] = w[e] - step_size * __fdividef(m[e], denom);
-            }
-        }
-        if (whole) {
-            *reinterpret_cast<float4*>(W + p0) = make_float4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<float4*>(M + p0) = make_float4(m[0], m[1], m[2], m[3]);
-            if (adam) *reinterpret_cast<float4*>(V + p0) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-            for (int e = 0; e < 4 && p0 + e < P; ++e) { W[p0 + e] = w[e]; M[p0 + e] = m[e]; if (adam) V[p0 + e] = v[e]; }
-        }
-        if (mapped) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (q[e] >= 0) wt[q[e]] = w[e];
-        }
-    }
+// at most ONE resident wave: every CTA lives for the whole kernel, so a handful of CTAs beyond the resident set would
+// double its duration (ncu: 600 CTAs on 592 slots cost +6 us of a 24 us launch)
+template <int OPT, bool DP, bool TAB>
+void launch_optimizer_k(const flb_train_args& a, int P, const TcConvTab& tab, cudaStream_t st) {
+    static const int resident = flb_resident_ctas(optimizer_kernel<OPT, DP, TAB>, 256);
+    const int blocks = max(1, min(flb_cdiv(P / 4, 256), resident / a.K));
+    optimizer_kernel<OPT, DP, TAB><<<dim3(blocks, a.K), 256, 0, st>>>(a, P, tab);
+}
+template <int OPT, bool DP>
+void launch_optimizer_tab(const flb_train_args& a, int P, const TcConvTab& tab, cudaStream_t st) {
+    if (tab.n) launch_optimizer_k<OPT, DP, true>(a, P, tab, st);
+    else launch_optimizer_k<OPT, DP, false>(a, P, tab, st);
+}
+void launch_optimizer(const flb_train_args& a, int P, const TcConvTab& tab, cudaStream_t st) {
+    const bool dp = a.dp_mode == 1;
+    if (a.opt == 0) { if (dp) launch_optimizer_tab<0, true>(a, P, tab, st); else launch_optimizer_tab<0, false>(a, P, tab, st); }
+    else if (a.opt == 1) { if (dp) launch_optimizer_tab<1, true>(a, P, tab, st); else launch_optimizer_tab<1, false>(a, P, tab, st); }
+    else { if (dp) launch_optimizer_tab<2, true>(a, P, tab, st); else launch_optimizer_tab<2, false>(a, P, tab, st); }
 }
 
 __global__ void advance_kernel(flb_train_args a) {
@@ -256,9 +317,7 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = fwd_bwd(*a, st, false)) return rc;      // accumulators are zero: begin_epoch + the optimizer keep them so
     const int P = num_params(*a);
-    // 4 CTAs per SM = one resident wave at 60 registers per thread (measured best of 2/4/8/16/32)
-    const int blocks = max(1, min(flb_cdiv(P / 4, 256), (flb_num_sms() * 4 + a->K - 1) / a->K));
-    optimizer_kernel<<<dim3(blocks, a->K), 256, 0, st>>>(*a, P, tab_of(*a));
+    launch_optimizer(*a, P, tab_of(*a), st);
     MARK("optimizer");
     FLB_LAUNCH_CHECK();
     return FLB_OK;

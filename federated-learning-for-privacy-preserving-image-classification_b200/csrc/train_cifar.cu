@@ -775,16 +775,18 @@ __global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, Ci
 // ---- orchestration ------------------------------------------------------------------------------------------------------
 template <int C>
 void bn_stats(const flb_train_args& a, const ConvGeom& g, const float* z, double* acc, int coff, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
+    static const int resident = flb_resident_ctas(bn_reduce_kernel<C, 0>, 256);
+    const int chunks = max(1, min(64, resident / a.K));                  // one resident wave (flb_resident_ctas)
     bn_reduce_kernel<C, 0><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, nullptr, acc, coff, -1, -1);
 }
 // layers whose upstream gradient is a dgrad output (1, 3, 5): dy is dense and still needs the ReLU mask
 template <int C>
 void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, float* dy, double* acc, int layer, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
+    static const int resident_r = flb_resident_ctas(bn_reduce_kernel<C, 1>, 256), resident_a = flb_resident_ctas(bn_bwd_apply_kernel<C>, 256);
+    const int chunks = max(1, min(64, resident_r / a.K)), chunks_a = max(1, min(64, resident_a / a.K));
     bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
     const int conv_boff = (a.precision == 1 && layer > 0) ? kNet.cb[layer] : -1;
-    bn_bwd_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, 1, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
+    bn_bwd_apply_kernel<C><<<dim3(chunks_a, a.K), 256, 0, st>>>(a, g, z, 1, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
 // pooled layers (2, 4, 6): straight from the pooled-side gradient
 template <int C, bool FLAT>
@@ -798,7 +800,8 @@ void bn_pool_bwd(const flb_train_args& a, const ConvGeom& g, const ConvGeom& go,
 }
 template <int C>
 void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float* y, const double* acc, int layer, cudaStream_t st) {
-    const int chunks = max(1, min(64, (flb_num_sms() * 8 + a.K - 1) / a.K));
+    static const int resident = flb_resident_ctas(bn_relu_apply_kernel<C>, 256);
+    const int chunks = max(1, min(64, resident / a.K));
     bn_relu_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
 }
 
