@@ -345,7 +345,11 @@ __global__ void __launch_bounds__(256) unpool2_kernel(flb_train_args a, SimpleCn
 // dp_mode 0 (per_sample = 0): two CTAs per sample (pooled rows 0-6 / 7-13) atomically add their halves into G.
 // dp_mode 1 (norm pass, per_sample = 1): one CTA per sample; the values are stored per sample in g1ps and their squared
 // norm added to norm2; the clipped sum is formed later by conv1_ps_reduce_kernel.
-__global__ void __launch_bounds__(256) conv1_bwd_kernel(flb_train_args a, SimpleCnnWs ws, int per_sample) {
+// Registers are capped for 5 CTAs per SM (48, no spills; 123 uncapped): at 10 clients the 640 half-sample CTAs are then one
+// resident wave instead of 2.2 (measured 22.8 -> 16.4 us; a cap of 3 CTAs gives 18.4 us).
+template <bool PS>
+__global__ void __launch_bounds__(256, PS ? 2 : 5) conv1_bwd_kernel(flb_train_args a, SimpleCnnWs ws) {
+    constexpr int per_sample = PS ? 1 : 0;
     const int nhalf = per_sample ? 1 : 2;
     const int b = blockIdx.x / nhalf, half = blockIdx.x % nhalf, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
@@ -365,18 +369,18 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(flb_train_args a, Simple
     const uint8_t* idx = ws.idx1 + kb * (196 * 32);
     const int pp0 = per_sample ? 0 : half * 98, npp = per_sample ? 196 : 98;
     // all of this thread's gradient values first (independent loads in flight together), then the stencil updates
-    constexpr int MAXIT = 25;
+    constexpr int MAXIT = PS ? 25 : 13;            // ceil(196 / 8) or ceil(98 / 8) pooled positions per thread
     float gvv[MAXIT];
-    int sel[MAXIT];
+    unsigned long long sel = 0;                    // 2-bit argmax of every iteration
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
         const int pl = g + it * 8;
-        gvv[it] = 0.f; sel[it] = 0;
+        gvv[it] = 0.f;
         if (pl < npp) {
             const int pp = pp0 + pl, o = ((pp / 14) * WP2 + pp % 14) * 32 + c;
             const float av = a1[o], dv = da1[o];
             gvv[it] = av > 0.f ? dv : 0.f;
-            sel[it] = idx[pp * 32 + c];
+            sel |= (unsigned long long)(idx[pp * 32 + c] & 3) << (2 * it);
         }
     }
     __syncthreads();
@@ -389,7 +393,8 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(flb_train_args a, Simple
         if (pl < npp) {
             const int pp = pp0 + pl, ph = pp / 14, pw = pp % 14;
             const float gv = gvv[it];
-            const int y0 = 2 * ph + (sel[it] >> 1), x0 = 2 * pw + (sel[it] & 1);     // top-left of the 3x3 window in img (halo 1)
+            const int si = (int)(sel >> (2 * it)) & 3;
+            const int y0 = 2 * ph + (si >> 1), x0 = 2 * pw + (si & 1);     // top-left of the 3x3 window in img (halo 1)
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -587,7 +592,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
             ConvWgradNormProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.norm2_all = ws.norm2;
             simt::launch(p, 64, 289, 1, K * B, st);
         }
-        conv1_bwd_kernel<<<per_sample, 256, 0, st>>>(a, ws, 1);
+        conv1_bwd_kernel<true><<<per_sample, 256, 0, st>>>(a, ws);
         clip_coef_kernel<<<flb_cdiv(K * B, 256), 256, 0, st>>>(a, ws);
         coef = ws.coef;
         MARK("per_sample_norms");
@@ -599,7 +604,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
         if (int rc = wgrads_conv2(st)) return rc;
     }
     if (a.dp_mode == 1) conv1_ps_reduce_kernel<<<K, 320, 0, st>>>(a, ws);
-    else conv1_bwd_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws, 0);
+    else conv1_bwd_kernel<false><<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
     MARK("conv1_wgrad");
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
