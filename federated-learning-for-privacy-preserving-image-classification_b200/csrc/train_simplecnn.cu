@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     const int nloc = max(0, min(bsz, b0 + per) - b0);          // live samples of this slice
     __shared__ float sh[32][129];
     __shared__ float sw2[10][129];
+    __shared__ float sb2[10];
     __shared__ float slog[32][10];
     __shared__ float sdl[32][10];
     __shared__ float red[2];
@@ -153,33 +154,49 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
     for (int e = nloc * 128 + tid; e < min(per, a.B - b0) * 128; e += 256) ws.dh[kb * 128 + e] = 0.f;
     if (nloc == 0) return;
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    const int step = *a.step_ctr;
-    // h = dropout(relu(hpre + b1)); the multiplier (0 or 1/(1-p), and 0 where ReLU is inactive) is kept in dh's
-    // slot until the backward part below overwrites it
-    for (int e = tid; e < nloc * 128; e += 256) {
-        const int b = e >> 7, j = e & 127;
-        const float pre = ws.hpre[kb * 128 + e] + W[Off::f1b + j];
-        ws.hpre[kb * 128 + e] = 0.f;                       // consumed: ready for the next step's split-K atomics
-        float mult = pre > 0.f ? 1.f : 0.f;
+    // This kernel is a chain of four short dependent phases: every global load whose address is known up front is
+    // issued here, before the first barrier (labels, fc2 weights / bias), so that only hpre's latency is exposed.
+    int label = 0;                                             // of sample tid >> 4 (the softmax phase's mapping)
+    if (tid < 16 * nloc) label = a.y[a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b0 + (tid >> 4)];
+    for (int e = tid; e < 1280; e += 256) sw2[e >> 7][e & 127] = W[Off::f2w + e];
+    if (tid < 10) sb2[tid] = W[Off::f2b + tid];
+    if (tid < 2) red[tid] = 0.f;
+    // h = dropout(relu(hpre + b1)); the multiplier (0 or 1/(1-p), and 0 where ReLU is inactive) stays in registers for the
+    // backward part below.  A thread owns 4 consecutive elements = one Philox block and one 16 B access (the kernel is
+    // bound by instruction latency at 8 warps per SM, so instructions per warp are what counts: ncu, 18 cycles each).
+    constexpr int QUADS = (32 / HEAD_PARTS) * 128 / 4;         // B <= 32 samples over gridDim.y = HEAD_PARTS slices
+    static_assert(32 % HEAD_PARTS == 0 && QUADS <= 256, "one quad per thread");
+    float mult_r[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool own = tid < nloc * 32;
+    if (own) {
+        const int e = tid * 4, b = e >> 7, j = e & 127;
+        const float4 pre4 = *reinterpret_cast<const float4*>(ws.hpre + kb * 128 + e);
+        const float4 b4 = *reinterpret_cast<const float4*>(W + Off::f1b + j);
+        *reinterpret_cast<float4*>(ws.hpre + kb * 128 + e) = make_float4(0.f, 0.f, 0.f, 0.f);   // consumed: ready for the next step's split-K atomics
+        const float pre[4] = {pre4.x + b4.x, pre4.y + b4.y, pre4.z + b4.z, pre4.w + b4.w};
+        bool keep[4] = {true, true, true, true};
         if (a.drop_p > 0.f) {
-            bool keep;
-            if (a.drop_keep) keep = a.drop_keep[kb * 128 + e] != 0;
-            else {
+            if (a.drop_keep) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) keep[i] = a.drop_keep[kb * 128 + e + i] != 0;
+            } else {
                 const int eg = b0 * 128 + e;                   // element index within the client's [B, 128] block
                 const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
                                                   ((unsigned long long)a.tcount[k] << 12) + (eg >> 2));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-                keep = flb_u01(rr[eg & 3]) >= a.drop_p;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) keep[i] = flb_u01(rr[i]) >= a.drop_p;
             }
-            mult = keep ? mult * keep_scale : 0.f;
         }
-        const float hv = pre * mult;
-        sh[b][j] = hv;
-        ws.h[kb * 128 + e] = hv;
-        ws.dh[kb * 128 + e] = mult;
+        float hv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            mult_r[i] = (pre[i] > 0.f && keep[i]) ? keep_scale : 0.f;
+            hv[i] = pre[i] * mult_r[i];
+            sh[b][j + i] = hv[i];
+        }
+        *reinterpret_cast<float4*>(ws.h + kb * 128 + e) = make_float4(hv[0], hv[1], hv[2], hv[3]);
     }
-    for (int e = tid; e < 1280; e += 256) sw2[e >> 7][e & 127] = W[Off::f2w + e];
-    if (tid < 2) red[tid] = 0.f;
     __syncthreads();
     for (int e = tid >> 5; e < nloc * 10; e += 8) {            // one warp per logit: 4 products per lane + shuffle reduce
         const int b = e / 10, j = e % 10, l = tid & 31;
@@ -187,30 +204,39 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
         acc = fmaf(sh[b][l + 32], sw2[j][l + 32], acc);
         acc = fmaf(sh[b][l + 64], sw2[j][l + 64], acc);
         acc = fmaf(sh[b][l + 96], sw2[j][l + 96], acc);
-        acc = flb_warp_sum(acc) + W[Off::f2b + j];
+        acc = flb_warp_sum(acc) + sb2[j];
         if (l == 0) {
             slog[b][j] = acc;
             ws.logits[kb * 10 + e] = acc;
         }
     }
     __syncthreads();
-    if (tid < nloc) {
-        const int y = a.y[a.sample_off[k] + (long long)step * a.B + b0 + tid];
-        float mx = slog[tid][0];
-        int am = 0;
-        for (int j = 1; j < 10; ++j) if (slog[tid][j] > mx) { mx = slog[tid][j]; am = j; }
-        float se = 0.f;
-        for (int j = 0; j < 10; ++j) se += expf(slog[tid][j] - mx);
-        const float lse = logf(se) + mx;
-        const float gs = a.dp_mode == 1 ? 1.f : 1.f / (float)bsz;          // mean reduction (training.py:90)
-        for (int j = 0; j < 10; ++j) {
-            const float p = expf(slog[tid][j] - lse);
-            const float d = (p - (j == y ? 1.f : 0.f)) * gs;
-            sdl[tid][j] = d;
-            ws.dlog[kb * 10 + tid * 10 + j] = d;
+    // softmax cross-entropy: 16 lanes per sample (10 live), reductions by width-16 shuffles
+    if (tid < 16 * (32 / HEAD_PARTS)) {
+        const int b = tid >> 4, j = tid & 15;
+        const bool live = b < nloc && j < 10;
+        const int bb = b < nloc ? b : 0;
+        const float v = live ? slog[bb][j] : -INFINITY;
+        float mx = v;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, 16));
+        int am = (live && v == mx) ? j : 99;                   // first index of the maximum, like the sequential scan
+        float ex = live ? expf(v - mx) : 0.f, se = ex;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            am = min(am, __shfl_xor_sync(0xffffffffu, am, o, 16));
+            se += __shfl_xor_sync(0xffffffffu, se, o, 16);
         }
-        atomicAdd(&red[0], lse - slog[tid][y]);
-        atomicAdd(&red[1], am == y ? 1.f : 0.f);
+        const float lse = logf(se) + mx;
+        const int y = label;
+        const float gs = a.dp_mode == 1 ? 1.f : 1.f / (float)bsz;          // mean reduction (training.py:90)
+        if (live) {
+            const float d = (expf(v - lse) - (j == y ? 1.f : 0.f)) * gs;
+            sdl[b][j] = d;
+            ws.dlog[kb * 10 + b * 10 + j] = d;
+            if (j == y) atomicAdd(&red[0], lse - v);
+            if (j == 0) atomicAdd(&red[1], am == y ? 1.f : 0.f);
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -221,12 +247,16 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
             a.nseen[k] += bsz;
         }
     }
-    for (int e = tid; e < nloc * 128; e += 256) {
-        const int b = e >> 7, j = e & 127;
-        float acc = 0.f;
+    if (own) {
+        const int e = tid * 4, b = e >> 7, j = e & 127;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 10; ++c) acc = fmaf(sdl[b][c], sw2[c][j], acc);
-        ws.dh[kb * 128 + e] = acc * ws.dh[kb * 128 + e];
+        for (int c = 0; c < 10; ++c) {
+            const float d = sdl[b][c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(d, sw2[c][j + i], acc[i]);
+        }
+        *reinterpret_cast<float4*>(ws.dh + kb * 128 + e) = make_float4(acc[0] * mult_r[0], acc[1] * mult_r[1], acc[2] * mult_r[2], acc[3] * mult_r[3]);
     }
 }
 
