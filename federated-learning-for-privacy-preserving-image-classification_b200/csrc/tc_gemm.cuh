@@ -134,6 +134,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Column sums of a warp's 32 x 32 register tile (lane = row, v[i] = column i): returns in lane j the sum over all lanes
+// of v[j].  Transposing butterfly: every step exchanges half of the still-live columns, 31 shuffles in all.  v is clobbered.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// optional Traits::finish(p, lane): called once by every epilogue warp after its last tile (persistent skeletons)
+template <class T, class P>
+__device__ __forceinline__ auto call_finish(T& t, const P& p, int lane, int) -> decltype(t.finish(p, lane), void()) { t.finish(p, lane); }
+template <class T, class P>
+__device__ __forceinline__ void call_finish(T&, const P&, int, long) {}
+
 // byte offset of element (row, k) inside a K-major SW128 tile whose rows are 128 B (32 fp32) and dense
 __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
     return (uint32_t)row * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)row & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
@@ -291,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             ++nt;
         }
+        call_finish(t, p, lane, 0);
     }
     tc_fence_before();
     __syncthreads();
@@ -397,6 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             ++nt;
         }
+        call_finish(t, p, lane, 0);
     }
     tc_fence_before();
     __syncthreads();

@@ -17,7 +17,9 @@
 #include <string.h>
 
 namespace tc {
-int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st);
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st,
+             double* bn_acc = nullptr, int bn_coff = 0, int bn_stride = 0);
+bool conv_fwd_fuses_stats(int cin, int cout);
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
@@ -807,11 +809,18 @@ void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float*
 
 struct Ctx { const flb_train_args& a; const CifarWs& ws; cudaStream_t st; int rc = FLB_OK; bool tc; bool tc_wgrad; };
 
-void conv_fwd(Ctx& c, const ConvGeom& g, const float* xin, float* z, int layer) {
+// returns true when the launch also accumulated the layer's BatchNorm statistics (sum z, sum z^2) into ws.acc
+bool conv_fwd(Ctx& c, const ConvGeom& g, const float* xin, float* z, int layer, bool want_stats) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) { if (int rc = tc::conv_fwd(a, g, xin, z, c.ws.wt + kNet.toff[layer], kNet.ldt, kNet.cb[layer], st)) c.rc = rc; return; }
+    if (c.tc) {
+        const bool fuse = want_stats && tc::conv_fwd_fuses_stats(g.Cin, g.Cout);
+        if (int rc = tc::conv_fwd(a, g, xin, z, c.ws.wt + kNet.toff[layer], kNet.ldt, kNet.cb[layer], st,
+                                  fuse ? c.ws.acc : nullptr, kNet.coff[layer], BN_CH)) c.rc = rc;
+        return fuse;
+    }
     ConvFwdProb p{}; p.a = a; p.g = g; p.xin_all = xin; p.z_all = z; p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
     simt::launch(p, a.B * g.PP(), g.Cout, 1, a.K, st);
+    return false;
 }
 void conv_dgrad(Ctx& c, const ConvGeom& g, const float* dz, float* dx, int layer) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
@@ -865,29 +874,29 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     if (stats) bn_stats<32>(a, G1, ws.z1, ws.acc, kNet.coff[0], st);
     bn_apply<32>(a, G1, ws.z1, ws.y1, ws.acc, 0, st);
     MARK("bn1");
-    conv_fwd(cx, G2, ws.y1, ws.z2, 1);
+    const bool fused1 = conv_fwd(cx, G2, ws.y1, ws.z2, 1, stats);
     MARK("conv2_fwd");
-    if (stats) bn_stats<32>(a, G2, ws.z2, ws.acc, kNet.coff[1], st);
+    if (stats && !fused1) bn_stats<32>(a, G2, ws.z2, ws.acc, kNet.coff[1], st);
     bn_relu_pool_drop_kernel<32, false><<<per_sample, 256, 0, st>>>(a, G2, G3, ws.z2, ws.p1, ws.i1, ws.acc, kNet.coff[1], kNet.bw[1], kNet.bb[1], 0, 0);
     MARK("bn2_pool");
-    conv_fwd(cx, G3, ws.p1, ws.z3, 2);
+    const bool fused2 = conv_fwd(cx, G3, ws.p1, ws.z3, 2, stats);
     MARK("conv3_fwd");
-    if (stats) bn_stats<64>(a, G3, ws.z3, ws.acc, kNet.coff[2], st);
+    if (stats && !fused2) bn_stats<64>(a, G3, ws.z3, ws.acc, kNet.coff[2], st);
     bn_apply<64>(a, G3, ws.z3, ws.y3, ws.acc, 2, st);
     MARK("bn3");
-    conv_fwd(cx, G4, ws.y3, ws.z4, 3);
+    const bool fused3 = conv_fwd(cx, G4, ws.y3, ws.z4, 3, stats);
     MARK("conv4_fwd");
-    if (stats) bn_stats<64>(a, G4, ws.z4, ws.acc, kNet.coff[3], st);
+    if (stats && !fused3) bn_stats<64>(a, G4, ws.z4, ws.acc, kNet.coff[3], st);
     bn_relu_pool_drop_kernel<64, false><<<per_sample, 256, 0, st>>>(a, G4, G5, ws.z4, ws.p2, ws.i2, ws.acc, kNet.coff[3], kNet.bw[3], kNet.bb[3], 1, 8192);
     MARK("bn4_pool");
-    conv_fwd(cx, G5, ws.p2, ws.z5, 4);
+    const bool fused4 = conv_fwd(cx, G5, ws.p2, ws.z5, 4, stats);
     MARK("conv5_fwd");
-    if (stats) bn_stats<128>(a, G5, ws.z5, ws.acc, kNet.coff[4], st);
+    if (stats && !fused4) bn_stats<128>(a, G5, ws.z5, ws.acc, kNet.coff[4], st);
     bn_apply<128>(a, G5, ws.z5, ws.y5, ws.acc, 4, st);
     MARK("bn5");
-    conv_fwd(cx, G6, ws.y5, ws.z6, 5);
+    const bool fused5 = conv_fwd(cx, G6, ws.y5, ws.z6, 5, stats);
     MARK("conv6_fwd");
-    if (stats) bn_stats<128>(a, G6, ws.z6, ws.acc, kNet.coff[5], st);
+    if (stats && !fused5) bn_stats<128>(a, G6, ws.z6, ws.acc, kNet.coff[5], st);
     bn_relu_pool_drop_kernel<128, true><<<per_sample, 256, 0, st>>>(a, G6, G6, ws.z6, ws.a, ws.i3, ws.acc, kNet.coff[5], kNet.bw[5], kNet.bb[5], 2, 8192 + 4096);
     MARK("bn6_pool");
     lin_fwd(cx, ws.a, ws.hpre1, 2048, 512, kNet.f1w, 8);
@@ -992,7 +1001,8 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     return forward_impl(a, ws, st);
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
-int step_launches(const flb_train_args&) { return 22 + 29; }
+// forward 22 + backward 29 launches; on the tensor-core path three BatchNorm statistic passes ride in the conv epilogues
+int step_launches(const flb_train_args& a) { return 22 + 29 - (a.precision == 1 ? 3 : 0); }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {
     if (a.precision != 1) return;
     CifarWs ws;

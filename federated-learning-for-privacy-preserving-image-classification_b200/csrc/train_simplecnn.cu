@@ -22,7 +22,8 @@
 #include <string.h>
 
 namespace tc {
-int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st);
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st,
+             double* bn_acc = nullptr, int bn_coff = 0, int bn_stride = 0);
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
 int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, float* pooled, uint8_t* idx, const float* wt,

@@ -84,8 +84,10 @@ template <int N> struct Pow2Cols { static constexpr int value = N <= 32 ? 32 : (
 // consecutive MMAs do not form one dependent chain on a single accumulator; the epilogue adds the partials.
 template <int CIN, int COUT, bool POOL = false, int NPART = 1>
 struct ConvFwdT {
+    // bn_acc (optional): per-client BatchNorm accumulators [K][4][bn_stride] in double; the epilogue adds the column sums
+    // and sums of squares of z over the real pixels of the live samples to rows 0 / 1 at channel offset bn_coff
     struct Params { CUtensorMap map_x; CUtensorMap map_w; flb_train_args a; ConvGeom g; float* z_all; int boff;
-                    float* pool_out; uint8_t* pool_idx; };
+                    float* pool_out; uint8_t* pool_idx; double* bn_acc; int bn_coff, bn_stride; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static constexpr int ACC_COLS = NPART * COUT;
     // 32 accumulator columns [c0, c0 + 32) of this thread's row, partials summed
@@ -105,7 +107,8 @@ struct ConvFwdT {
         client = tile / tpc;
         const int bsz = flb_bsz(p.a, client);
         m0 = (tile - client * tpc) * 128;
-        if (m0 >= bsz * p.g.PP()) return false;
+        live_rows = bsz * p.g.PP();
+        if (m0 >= live_rows) return false;
         row0 = client * p.a.B * p.g.PP();
         num_kb = NKB;
         return true;
@@ -113,11 +116,39 @@ struct ConvFwdT {
     static constexpr int CH = CIN / 32, NKB = 9 * CH, A_BYTES = 128 * 128, B_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = COUT > 64 ? 3 : 4, RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<COUT>::value, MINB = 2;
-    int client, m0, row0;
+    int client, m0, row0, live_rows = 0;
+    // fused BatchNorm statistics: lane j of every epilogue warp carries the partial (sum, sum of squares) of column
+    // 32 * chunk + j over the rows that warp has seen for client `bclient`
+    // ROWACC (COUT = 32): the sums stay per ROW LANE (2 x 32 registers) across tiles and are transposed only when they are
+    // flushed -- the epilogue of the 32 -> 32 layer is as long as its MMAs, two butterflies per tile would make it the limiter
+    static constexpr bool ROWACC = COUT == 32;
+    float bs0[COUT / 32] = {}, bs1[COUT / 32] = {};
+    float rs0[ROWACC ? 32 : 1] = {}, rs1[ROWACC ? 32 : 1] = {};
+    int bclient = -1;
+    __device__ void bn_flush(const Params& p, int lane) {
+        if (bclient < 0) return;
+        if (ROWACC) {
+            bs0[0] = warp_colsum32(reinterpret_cast<float (&)[32]>(rs0), lane);
+            bs1[0] = warp_colsum32(reinterpret_cast<float (&)[32]>(rs1), lane);
+#pragma unroll
+            for (int i = 0; i < (ROWACC ? 32 : 1); ++i) { rs0[i] = 0.f; rs1[i] = 0.f; }
+        }
+        double* A = p.bn_acc + (long long)bclient * 4 * p.bn_stride + p.bn_coff + lane;
+#pragma unroll
+        for (int ch = 0; ch < COUT / 32; ++ch) {
+            atomicAdd(A + ch * 32, (double)bs0[ch]);
+            atomicAdd(A + p.bn_stride + ch * 32, (double)bs1[ch]);
+            bs0[ch] = 0.f; bs1[ch] = 0.f;
+        }
+    }
+    __device__ void finish(const Params& p, int lane) {
+        if (!POOL && p.bn_acc) bn_flush(p, lane);
+    }
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
         const int bsz = flb_bsz(p.a, client);
         m0 = blockIdx.x * 128;
+        live_rows = bsz * p.g.PP();
         if (m0 >= bsz * p.g.PP()) return false;
         row0 = client * p.a.B * p.g.PP();
         num_kb = NKB;
@@ -172,16 +203,36 @@ struct ConvFwdT {
         }
         float* z = p.z_all + ((long long)row0 + m) * COUT;
         const bool ok = m < p.a.B * p.g.PP();
-#pragma unroll 1
+        const bool stats = p.bn_acc != nullptr;
+        bool counted = false;                    // this row is a real pixel of a live sample
+        if (stats) {
+            if (client != bclient) { bn_flush(p, lane); bclient = client; }
+            if (m < live_rows) {
+                const int rr = m % p.g.PP(), h = rr / p.g.Wp;
+                counted = h < p.g.H && (rr - h * p.g.Wp) < p.g.W;
+            }
+        }
+#pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
             float v[32];
             ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
-            if (ok) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-                    *reinterpret_cast<float4*>(z + c0 + i) = make_float4(v[i] + bv.x, v[i + 1] + bv.y, v[i + 2] + bv.z, v[i + 3] + bv.w);
+            for (int i = 0; i < 32; i += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+                v[i] += bv.x; v[i + 1] += bv.y; v[i + 2] += bv.z; v[i + 3] += bv.w;
+                if (ok) *reinterpret_cast<float4*>(z + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            if (stats && ROWACC) {
+                if (counted) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { rs0[ROWACC ? i : 0] += v[i]; rs1[ROWACC ? i : 0] = fmaf(v[i], v[i], rs1[ROWACC ? i : 0]); }
                 }
+            } else if (stats) {
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { v[i] = counted ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+                bs0[c0 / 32] += warp_colsum32(v, lane);
+                bs1[c0 / 32] += warp_colsum32(sq, lane);
             }
         }
     }
@@ -702,13 +753,15 @@ static int make_wt_map(CUtensorMap* m, const float* wt, long long ldt, int cin, 
 }
 
 template <int CIN, int COUT>
-static int conv_fwd_t(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st) {
+static int conv_fwd_t(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff,
+                      double* bn_acc, int bn_coff, int bn_stride, cudaStream_t st) {
     constexpr bool HALO = CIN * COUT * 36 <= 150 * 1024;          // the whole weight tensor stays resident in shared memory
     using T = typename std::conditional<HALO, ConvFwdHaloT<(HALO ? CIN : 32), (HALO ? COUT : 32)>, ConvFwdT<CIN, COUT>>::type;
     typename T::Params p;
     if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, HALO ? 128 + 2 * (g.Wp + 1) : 128)) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, CIN, COUT, a.K, COUT, false)) return rc;
     p.a = a; p.g = g; p.z_all = z; p.boff = boff; p.pool_out = nullptr; p.pool_idx = nullptr;
+    p.bn_acc = HALO ? bn_acc : nullptr; p.bn_coff = bn_coff; p.bn_stride = bn_stride;
     if constexpr (HALO) return launch_resident<T>(p, st);
     else return launch_persistent<T>(p, st);
 }
@@ -721,6 +774,7 @@ int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float*
     if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 128 + 2 * (g.Wp + 1))) return rc;
     if (int rc = make_wt_map(&p.map_w, wt, ldt, 32, 64, a.K, 64, false)) return rc;
     p.a = a; p.g = g; p.z_all = nullptr; p.boff = boff; p.pool_out = pooled; p.pool_idx = idx;
+    p.bn_acc = nullptr; p.bn_coff = 0; p.bn_stride = 0;
     return launch_resident<T>(p, st);
 }
 template <int CIN, int COUT>
@@ -775,8 +829,11 @@ bool conv_supported(int cin, int cout) {
     flb_set_error("tensor-core conv: unsupported channels %d -> %d", g.Cin, g.Cout);          \
     return FLB_ERR_UNSUPPORTED;
 
-int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st) {
-    FLB_CONV_DISPATCH(conv_fwd_t, a, g, xin, z, wt, ldt, boff, st)
+// the resident-weight (halo) forward kernels can add the BatchNorm statistics of their output in the epilogue
+bool conv_fwd_fuses_stats(int cin, int cout) { return conv_supported(cin, cout) && cin * cout * 36 <= 150 * 1024; }
+int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float* z, const float* wt, long long ldt, int boff, cudaStream_t st,
+             double* bn_acc, int bn_coff, int bn_stride) {
+    FLB_CONV_DISPATCH(conv_fwd_t, a, g, xin, z, wt, ldt, boff, bn_acc, bn_coff, bn_stride, st)
 }
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st) {
     FLB_CONV_DISPATCH(conv_dgrad_t, a, g, dz, dx, wt, ldt, st)
