@@ -129,7 +129,9 @@ __device__ __forceinline__ void load_img3(float (*img)[34][36], const float* x, 
     }
 }
 
-__global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float* z_all) {
+// bn_acc (optional): the sample's per-channel (sum z, sum z^2) are added to the client's BatchNorm accumulators (rows 0 / 1
+// of [K][4][BN_CH], layer offset 0), which saves the separate statistics pass over z1.
+__global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float* z_all, double* bn_acc) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     __shared__ __align__(16) float img[3][34][36];
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float*
     const float bias = W[kC1B + c];
     __syncthreads();
     float* z = z_all + ((long long)k * a.B + b) * PP32 * 32;
+    float s0 = 0.f, s1 = 0.f;
     for (int s = g; s < 256; s += 8) {                    // strip = 4 pixels (h, w0 .. w0 + 3)
         const int h = s >> 3, w0 = (s & 7) * 4;
         float acc[4] = {bias, bias, bias, bias};
@@ -159,7 +162,25 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float*
                     for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[ci * 9 + r * 3 + q], in[j + q], acc[j]);
             }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) z[(h * 33 + w0 + j) * 32 + c] = acc[j];
+        for (int j = 0; j < 4; ++j) {
+            z[(h * 33 + w0 + j) * 32 + c] = acc[j];
+            s0 += acc[j];
+            s1 = fmaf(acc[j], acc[j], s1);
+        }
+    }
+    if (bn_acc) {
+        __syncthreads();                                   // img is dead: reuse it for the cross-warp reduction
+        float (*red)[8][32] = reinterpret_cast<float (*)[8][32]>(&img[0][0][0]);
+        red[0][g][c] = s0;
+        red[1][g][c] = s1;
+        __syncthreads();
+        if (tid < 64) {
+            const int which = tid >> 5;
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += red[which][i][c];
+            atomicAdd(bn_acc + (long long)k * 4 * BN_CH + which * BN_CH + c, (double)t);
+        }
     }
 }
 
@@ -869,9 +890,9 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     MARK("begin");
     const bool stats = !a.eval_mode;
     Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
-    conv1_fwd_kernel<<<per_sample, 256, 0, st>>>(a, ws.z1);
+    static_assert(kNet.coff[0] == 0, "conv1_fwd_kernel adds its statistics at channel offset 0");
+    conv1_fwd_kernel<<<per_sample, 256, 0, st>>>(a, ws.z1, stats ? ws.acc : nullptr);
     MARK("conv1_fwd");
-    if (stats) bn_stats<32>(a, G1, ws.z1, ws.acc, kNet.coff[0], st);
     bn_apply<32>(a, G1, ws.z1, ws.y1, ws.acc, 0, st);
     MARK("bn1");
     const bool fused1 = conv_fwd(cx, G2, ws.y1, ws.z2, 1, stats);
@@ -1001,8 +1022,9 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     return forward_impl(a, ws, st);
 }
 int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
-// forward 22 + backward 29 launches; on the tensor-core path three BatchNorm statistic passes ride in the conv epilogues
-int step_launches(const flb_train_args& a) { return 22 + 29 - (a.precision == 1 ? 3 : 0); }
+// forward 21 + backward 29 launches (conv1 carries its own BatchNorm statistics); on the tensor-core path three more
+// statistic passes ride in the conv epilogues
+int step_launches(const flb_train_args& a) { return 21 + 29 - (a.precision == 1 ? 3 : 0); }
 void tc_tab(const flb_train_args& a, TcConvTab* t) {
     if (a.precision != 1) return;
     CifarWs ws;
