@@ -298,21 +298,28 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(flb_train_args a, Simpl
 
 // conv2 bias gradient (tensor-core path; the fp32 path gets it as an extra GEMM column): every pooling window routes
 // its upstream gradient to exactly one conv2 output, so sum_px dz2[px][c] = sum_pp [a2 > 0] * da2[c*49 + pp].
-__global__ void __launch_bounds__(64) conv2_bias_grad_kernel(flb_train_args a, SimpleCnnWs ws, int use_coef) {
+// 256 threads: thread = (channel, quarter of the 49 windows); all 13 load pairs of a thread are independent.
+__global__ void __launch_bounds__(256) conv2_bias_grad_kernel(flb_train_args a, SimpleCnnWs ws, int use_coef) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     const long long kb = (long long)k * a.B + b;
-    const int c = threadIdx.x;
+    const int c = threadIdx.x >> 2, q = threadIdx.x & 3;
     const float* da2 = ws.da2 + kb * 3136 + c * 49;
     const float* a2 = ws.a2 + kb * 3136 + c * 49;
     float acc = 0.f;
-    for (int pp = 0; pp < 49; ++pp) acc += a2[pp] > 0.f ? da2[pp] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int pp = q + 4 * i;
+        if (pp < 49) acc += a2[pp] > 0.f ? da2[pp] : 0.f;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (use_coef == 2) {                       // per-sample DP norm pass: || db_b ||^2 joins the sample's squared gradient norm
-        float sq = flb_warp_sum(acc * acc);
+        float sq = flb_warp_sum(q == 0 ? acc * acc : 0.f);
         if ((threadIdx.x & 31) == 0) atomicAdd(&ws.norm2[kb], sq);
         return;
     }
-    atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], acc * (use_coef ? ws.coef[kb] : 1.f));
+    if (q == 0) atomicAdd(&a.G[(long long)k * a.ld + Off::c2b + c], acc * (use_coef ? ws.coef[kb] : 1.f));
 }
 
 // dp_mode 1, tensor-core wgrads: TMA cannot scale an operand in flight, so the activation gradients are scaled by
@@ -569,7 +576,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     };
     auto wgrads_conv2 = [&](cudaStream_t st) -> int {
         if (tcm & TC_CONV2_WGRAD) {
-            if (coef) conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, 1);      // else: fused into unpool2
+            if (coef) conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, 1);      // else: fused into unpool2
             if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.z2, coef, PP2 * 64);
             FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kLdt, st));       // side lane: off the critical path
             MARK("conv2_bias_grad");
@@ -618,7 +625,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
         linear_ghost_norm_kernel<<<per_sample, 128, 0, st>>>(a, ws);
         if (tcm & TC_CONV2_WGRAD) {          // per-sample conv2 gradient tiles live in TMEM only (tcgen05), squared on the way out
             if (int rc = tc::conv_wgrad_norm_32_64(a, kConv2, ws.a1p, ws.z2, ws.norm2, st)) return rc;
-            conv2_bias_grad_kernel<<<per_sample, 64, 0, st>>>(a, ws, 2);
+            conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, 2);
         } else {
             ConvWgradNormProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.norm2_all = ws.norm2;
             simt::launch(p, 64, 289, 1, K * B, st);
