@@ -621,7 +621,15 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     MARK("conv2_dgrad");
 
     // ---- per-sample clip coefficients (dp_mode 1) ----
+    // The four norm kernels only meet in norm2 (atomics), and the weight-gradient GEMMs only need the clip coefficients:
+    // both groups are split over the main stream and a side stream (fork / join by events, capturable).
+    SideLane* lane_ps = (a.dp_mode == 1 && !g_prof.on && !getenv("FLB_NO_SIDE_LANE")) ? flb_side_lane() : nullptr;
     if (a.dp_mode == 1) {
+        if (lane_ps) {
+            FLB_CUDA(cudaEventRecord(lane_ps->ev[0], st));
+            FLB_CUDA(cudaStreamWaitEvent(lane_ps->s, lane_ps->ev[0], 0));
+        }
+        conv1_bwd_kernel<true><<<per_sample, 256, 0, lane_ps ? lane_ps->s : st>>>(a, ws);
         linear_ghost_norm_kernel<<<per_sample, 128, 0, st>>>(a, ws);
         if (tcm & TC_CONV2_WGRAD) {          // per-sample conv2 gradient tiles live in TMEM only (tcgen05), squared on the way out
             if (int rc = tc::conv_wgrad_norm_32_64(a, kConv2, ws.a1p, ws.z2, ws.norm2, st)) return rc;
@@ -630,14 +638,22 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
             ConvWgradNormProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.norm2_all = ws.norm2;
             simt::launch(p, 64, 289, 1, K * B, st);
         }
-        conv1_bwd_kernel<true><<<per_sample, 256, 0, st>>>(a, ws);
+        if (lane_ps) {
+            FLB_CUDA(cudaEventRecord(lane_ps->ev[1], lane_ps->s));
+            FLB_CUDA(cudaStreamWaitEvent(st, lane_ps->ev[1], 0));
+        }
         clip_coef_kernel<<<flb_cdiv(K * B, 256), 256, 0, st>>>(a, ws);
         coef = ws.coef;
         MARK("per_sample_norms");
     }
 
     // ---- weight gradients ----
-    if (!lane) {
+    if (lane_ps) {
+        FLB_CUDA(cudaEventRecord(lane_ps->ev[2], st));
+        FLB_CUDA(cudaStreamWaitEvent(lane_ps->s, lane_ps->ev[2], 0));
+        if (int rc = wgrads_head_fc1(lane_ps->s)) return rc;
+        if (int rc = wgrads_conv2(st)) return rc;
+    } else if (!lane) {
         if (int rc = wgrads_head_fc1(st)) return rc;
         if (int rc = wgrads_conv2(st)) return rc;
     }
@@ -647,6 +663,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
         FLB_CUDA(cudaStreamWaitEvent(st, lane->ev[2], 0));
+    }
+    if (lane_ps) {
+        FLB_CUDA(cudaEventRecord(lane_ps->ev[3], lane_ps->s));
+        FLB_CUDA(cudaStreamWaitEvent(st, lane_ps->ev[3], 0));
     }
     FLB_LAUNCH_CHECK();
     return FLB_OK;
