@@ -143,9 +143,19 @@ class FederatedRoundEngine:
         """n_k * E / sum(n * E) over ALL clients (fedavg.py:247-256 with num_samples = samples_processed)."""
         return global_fedavg_weights(self.num_samples_all, self.client_ids)
 
-    def run_round(self, read_metrics: bool = True) -> Dict[str, Any]:
+    def run_round(self, read_metrics: bool = True, model_out: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        """One FedAvg round.  ``model_out``: optional pinned host buffer [>= P] that receives the aggregated model (the
+        copy is enqueued before the round's single synchronisation, so metrics and model arrive together)."""
+        self.start_round()
+        return self.finish_round(read_metrics, model_out)
+
+    def start_round(self) -> None:
+        """Enqueue the whole round (local epochs, DP, FedAvg, all-reduce) on the current stream; does not synchronise.
+        Host work that should overlap the round goes between ``start_round`` and ``finish_round``.  (Issue
+        ``prefetch_packed`` BEFORE ``start_round``: a copy submitted behind an already enqueued captured epoch only starts
+        when that epoch has drained -- measured with scripts/dbg_e2e.py.)"""
         tr, lay = self.trainer, self.layout
-        t0 = time.time()
+        self._t0 = time.time()
         tr.set_global_row(self.global_row)
         tr._fill_args(self.lr, self.optimizer_type, train=True)
         tr.M.zero_(); tr.V.zero_(); tr.tcount.zero_()
@@ -172,12 +182,19 @@ class FederatedRoundEngine:
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.pg)
         self.global_row[:lay.P].copy_(partial)
         self.round_number += 1
+        self._round_w = w
+
+    def finish_round(self, read_metrics: bool = True, model_out: Optional[torch.Tensor] = None) -> Dict[str, Any]:
+        tr, lay = self.trainer, self.layout
         out: Dict[str, Any] = {"round": self.round_number, "clients": len(self.client_ids)}
+        if model_out is not None:
+            model_out[:lay.P].copy_(self.global_row[:lay.P], non_blocking=True)
         if read_metrics:
-            loss, acc, seen = tr.epoch_metrics()          # the round's single device -> host read
+            loss, acc, seen = tr.epoch_metrics()          # the round's single synchronisation (covers model_out too)
+            w = self._round_w
             out.update(losses=loss.tolist(), accuracies=acc.tolist(),
                        samples=[int(s) * self.local_epochs for s in seen.tolist()],
-                       avg_loss=float(sum(l * wi for l, wi in zip(loss.tolist(), w))), wall_s=time.time() - t0)
+                       avg_loss=float(sum(l * wi for l, wi in zip(loss.tolist(), w))), wall_s=time.time() - self._t0)
             self.history.append(out)
         return out
 

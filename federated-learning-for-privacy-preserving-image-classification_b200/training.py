@@ -88,10 +88,11 @@ class BatchedClientTrainer:
         self.V = lay.new_rows(K, dev)
         self.tcount = torch.zeros(K, dtype=torch.int32, device=dev)
         self.step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.loss_sum = torch.zeros(K, dtype=torch.float32, device=dev)
-        self.correct = torch.zeros(K, dtype=torch.int32, device=dev)
-        self.nbatch = torch.zeros(K, dtype=torch.int32, device=dev)
-        self.nseen = torch.zeros(K, dtype=torch.int32, device=dev)
+        # epoch accumulators in ONE buffer ([4, K] 32-bit words) so that they reach the host in one copy
+        self._metrics = torch.zeros((4, K), dtype=torch.int32, device=dev)
+        self.loss_sum = self._metrics[0].view(torch.float32)
+        self.correct, self.nbatch, self.nseen = self._metrics[1], self._metrics[2], self._metrics[3]
+        self._metrics_host = torch.zeros((4, K), dtype=torch.int32).pin_memory()
         self.ws_bytes = L.call_ll("flb_train_ws_bytes", self.model_id, K, self.B)
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=dev)      # pads of the NHWC grids stay zero forever
         nbn = L.call_ll("flb_train_bn_floats", self.model_id)
@@ -182,7 +183,8 @@ class BatchedClientTrainer:
     def prefetch_packed(self, x_all: torch.Tensor, y_all: torch.Tensor, ns: Sequence[int]) -> None:
         """Upload the NEXT round's samples (same per-client counts as the current ones) into the spare device buffers on
         a copy stream, so the host -> device transfer overlaps the round that is running; ``use_prefetched()`` swaps
-        them in.  The copy waits for the work already queued on the compute stream (the spare buffers' last reader)."""
+        them in.  The copy waits only for the spare buffers' last reader (the work queued before the swap that freed them),
+        not for a round enqueued since -- so it may be issued right after ``start_round`` and still overlap that round."""
         ns = [int(n) for n in ns]
         if self.x is None or ns != self.n_host:
             raise L.FlbError("prefetch_packed: call load_packed once with these per-client counts first")
@@ -192,10 +194,15 @@ class BatchedClientTrainer:
         with torch.cuda.device(self.device):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(self.device)
+            free_ev = getattr(self, "_spare_free_ev", None)
             if self._spare is None or self._spare[0].shape != self.x.shape:
                 self._spare = (torch.empty_like(self.x), torch.empty_like(self.y))
+                free_ev = None
             xs, ys = self._spare
-            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            if free_ev is not None:
+                self._copy_stream.wait_event(free_ev)
+            else:
+                self._copy_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._copy_stream):
                 xs[:total].copy_(x_all.reshape(total, -1), non_blocking=True)
                 ys[:total].copy_(y_all, non_blocking=True)
@@ -209,7 +216,10 @@ class BatchedClientTrainer:
         if self._staged is None:
             raise L.FlbError("use_prefetched: nothing was prefetched")
         xs, ys, ev = self._staged
-        torch.cuda.current_stream(self.device).wait_event(ev)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        self._spare_free_ev = torch.cuda.Event()          # everything that read the old buffers is queued before this point
+        self._spare_free_ev.record(cur)
         self._spare, self._staged = (self.x, self.y), None
         self.x, self.y = xs, ys
 
@@ -335,10 +345,20 @@ class BatchedClientTrainer:
 
     def epoch_metrics(self):
         """The one device->host read of an epoch: mean of batch-mean losses, accuracy, samples (training.py:209-212)."""
-        stats = torch.stack([self.loss_sum.double(), self.correct.double(), self.nbatch.double(),
-                             self.nseen.double()]).cpu()
-        nb, ns = stats[2].clamp(min=1), stats[3].clamp(min=1)
-        return stats[0] / nb, stats[1] / ns, stats[3].long()
+        self.enqueue_metrics_read()
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.metrics_from_host()
+
+    def enqueue_metrics_read(self) -> None:
+        """Async copy of the accumulators into pinned host memory (current stream); pair with metrics_from_host()."""
+        self._metrics_host.copy_(self._metrics, non_blocking=True)
+
+    def metrics_from_host(self):
+        """Per-client (mean batch loss, accuracy, samples) from the pinned copy; the copy must have completed."""
+        h = self._metrics_host
+        loss_sum = h[0].view(torch.float32).double()
+        nb, ns = h[2].double().clamp(min=1), h[3].double().clamp(min=1)
+        return loss_sum / nb, h[1].double() / ns, h[3].long()
 
     # ---- single-step entries used by tests / evaluation ---------------------------------------------------
     def forward_backward(self, learning_rate: float = 0.001, optimizer_type: str = "adam") -> None:

@@ -141,6 +141,7 @@ def test_prefetched_uploads_match_plain_loads(cuda_device):
                                    dp_mode="none", dropout_rate=0.0, precision="fp32")
         eng.set_global_weights(w0)
         eng.load_packed(rounds[0][0], rounds[0][1], sizes)
+        model_host = torch.zeros(eng.layout.P, dtype=torch.float32).pin_memory()
         losses = []
         for r in range(4):
             if mode == "plain":
@@ -149,8 +150,13 @@ def test_prefetched_uploads_match_plain_loads(cuda_device):
                 if r == 0:
                     eng.prefetch_packed(rounds[0][0], rounds[0][1])
                 eng.use_prefetched()
+                eng.start_round()                      # the split form: the next upload is issued while the round runs
                 if r + 1 < 4:
                     eng.prefetch_packed(rounds[r + 1][0], rounds[r + 1][1])
+                out = eng.finish_round(model_out=model_host)
+                assert torch.equal(model_host[:eng.layout.P], eng.global_row[:eng.layout.P].cpu())
+                losses.append(out["losses"])
+                continue
             losses.append(eng.run_round()["losses"])
         outs.append((losses, eng.global_row.clone()))
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5)          # split-K atomics reorder fp32 sums between runs
