@@ -42,8 +42,9 @@ WORKLOADS = {
 GEMM_FLOPS = {
     "simple_cnn": {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288,
                    "fc1_fwd": 2 * 3136 * 128, "fc1_dgrad": 2 * 3136 * 128, "fc1_wgrad": 2 * 3136 * 128},
-    "cifar10_cnn": {f"conv{i}_fwd": 2 * hw * ci * 9 * co for i, (hw, ci, co) in
-                    enumerate([(1024, 3, 32), (1024, 32, 32), (256, 32, 64), (256, 64, 64), (64, 64, 128), (64, 128, 128)], start=1)},
+    "cifar10_cnn": {f"conv{i}_{kind}": 2 * hw * ci * 9 * co for i, (hw, ci, co) in
+                    enumerate([(1024, 3, 32), (1024, 32, 32), (256, 32, 64), (256, 64, 64), (64, 64, 128), (64, 128, 128)], start=1)
+                    for kind in ("fwd", "dgrad", "wgrad") if not (i == 1 and kind == "dgrad")},
 }
 
 
@@ -90,7 +91,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append([N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx] + [bool(r & b) for b in bits])
-                time.sleep(0.002)
+                time.sleep(0.005)
             return True
         except Exception as e:           # fall back to nvidia-smi; keep the reason for the record
             self.nvml_error = f"{type(e).__name__}: {e}"
@@ -291,11 +292,12 @@ def main():
     from flb200 import _lib as L
     L.call("flb_train_begin_epoch", C.byref(tr.args), L.stream_ptr(dev))
     tr.profile_step()
-    acc = {}
-    reps = 5
+    samples = {}
+    reps = 7
     for _ in range(reps):
         for k, v in tr.profile_step().items():
-            acc[k] = acc.get(k, 0.0) + v / reps
+            samples.setdefault(k, []).append(v)
+    acc = {k: sorted(v)[len(v) // 2] for k, v in samples.items()}          # median: one preempted launch must not pick the kernel
     step_ms = sum(acc.values())
     top = max(acc, key=acc.get)
     pk = peaks()
@@ -326,7 +328,7 @@ def main():
         roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": traffic}
     roof["share_of_step"] = acc[top] / step_ms
     roof["how"] = ("CUDA events after every kernel of one training step, launched eagerly on the launch stream right after the "
-                   "timed region (the timed rounds replay a CUDA graph, which cannot be instrumented per kernel); mean of 5 steps")
+                   "timed region (the timed rounds replay a CUDA graph, which cannot be instrumented per kernel); median of 7 steps")
     roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in acc.items()}
     # the other kernels against their own rooflines, for the record
     others = {}
