@@ -568,6 +568,69 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(flb_train_args 
     }
 }
 
+// The same reduction for the NHWC pooled layout (layers 2, 4), vectorised: thread = (channel quad, pooled-position lane);
+// 16 B loads of the pooled-side arrays, the four argmax codes as one 32-bit word, and all four window positions of z as
+// 16 B loads (a warp fetches those sectors anyway, whichever position each channel picks); shifts instead of divisions.
+// (Measured and dropped: the same scheme for the NCHW-flattened layer 6, and CTAs that walk several samples -- both slower.)
+template <int C>
+__global__ void __launch_bounds__(256) bn_pool_bwd_reduce_vec_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
+                                                                     const float* pooled_all, const uint8_t* idx_all,
+                                                                     const float* z_all, double* acc, int coff) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (b >= bsz) return;
+    constexpr int C4 = C / 4, PL = 256 / C4;
+    const int tid = threadIdx.x, cq = tid % C4, pl = tid / C4;
+    __shared__ float s_mean[C], s_invstd[C];
+    __shared__ float red[8][256];
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, bsz * g.H * g.W, mean, invstd, vb);
+        s_mean[tid] = mean; s_invstd[tid] = invstd;
+    }
+    __syncthreads();
+    const long long kb = (long long)k * a.B + b;
+    const int Wo = g.W / 2, npool = (g.H / 2) * Wo, wshift = 31 - __clz(Wo);
+    const float4* dpool4 = reinterpret_cast<const float4*>(dpool_all + kb * go.PP() * C);
+    const float4* pooled4 = reinterpret_cast<const float4*>(pooled_all + kb * go.PP() * C);
+    const uint32_t* idx32 = reinterpret_cast<const uint32_t*>(idx_all + kb * npool * C);
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + kb * g.PP() * C);
+    const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
+    float mean[4], invstd[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { mean[q] = s_mean[cq * 4 + q]; invstd[q] = s_invstd[cq * 4 + q]; }
+    for (int pp = pl; pp < npool; pp += PL) {
+        const int ph = pp >> wshift, pw = pp & (Wo - 1);
+        const int src = (ph * go.Wp + pw) * C4 + cq;
+        const float4 p4 = pooled4[src], d4 = dpool4[src];
+        const uint32_t codes = idx32[pp * C4 + cq];
+        const int r00 = (2 * ph * g.Wp + 2 * pw) * C4 + cq;
+        const float4 za = z4[r00], zb = z4[r00 + C4], zc = z4[r00 + g.Wp * C4], zd = z4[r00 + (g.Wp + 1) * C4];
+        const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float zz[4][4] = {{za.x, za.y, za.z, za.w}, {zb.x, zb.y, zb.z, zb.w}, {zc.x, zc.y, zc.z, zc.w}, {zd.x, zd.y, zd.z, zd.w}};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!(pv[q] > 0.f)) continue;                     // dropped, or ReLU inactive: no gradient through this window
+            const int code = (codes >> (8 * q)) & 3;
+            const float zv = code == 0 ? zz[0][q] : (code == 1 ? zz[1][q] : (code == 2 ? zz[2][q] : zz[3][q]));
+            const float gv = dv[q] * keep_scale;
+            s0[q] = fmaf(gv, (zv - mean[q]) * invstd[q], s0[q]);
+            s1[q] += gv;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { red[q][tid] = s0[q]; red[4 + q][tid] = s1[q]; }
+    __syncthreads();
+    if (tid < C) {
+        const int q = tid & 3, cq2 = tid >> 2;
+        float t0 = 0.f, t1 = 0.f;
+        for (int i = 0; i < PL; ++i) { t0 += red[q][i * C4 + cq2]; t1 += red[4 + q][i * C4 + cq2]; }
+        double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
+        atomicAdd(A, (double)t0);
+        atomicAdd(A + BN_CH, (double)t1);
+    }
+}
+
 template <int C, bool FLAT>
 __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
                                                                 const float* pooled_all, const uint8_t* idx_all, const float* z_all,
@@ -816,7 +879,8 @@ template <int C, bool FLAT>
 void bn_pool_bwd(const flb_train_args& a, const ConvGeom& g, const ConvGeom& go, const float* dpool, const float* pooled,
                  const uint8_t* idx, const float* z, float* dz, double* acc, int layer, cudaStream_t st) {
     const dim3 per_sample(a.B, a.K);
-    bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
+    if constexpr (FLAT) bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
+    else bn_pool_bwd_reduce_vec_kernel<C><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
     const int conv_boff = a.precision == 1 ? kNet.cb[layer] : -1;
     bn_pool_bwd_apply_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, dz, acc, kNet.coff[layer],
                                                                  kNet.bw[layer], kNet.bb[layer], conv_boff);
