@@ -392,6 +392,21 @@ __device__ __forceinline__ bool drop_keep(const flb_train_args& a, int k, int b,
     return flb_u01(rr[e & 3]) >= a.drop_p;
 }
 
+// the same decision for 4 consecutive elements e_nchw0 .. e_nchw0 + 3 (e_nchw0 % 4 == 0): ONE Philox block instead of four
+__device__ __forceinline__ void drop_keep4(const flb_train_args& a, int k, int b, int layer, int layer_off, int per_sample, int e_nchw0,
+                                           bool (&keep)[4]) {
+    if (a.drop_keep) {
+        const uchar4 m = *reinterpret_cast<const uchar4*>(a.drop_keep + ((long long)k * a.B + b) * DROP_PER_SAMPLE + layer_off + e_nchw0);
+        keep[0] = m.x != 0; keep[1] = m.y != 0; keep[2] = m.z != 0; keep[3] = m.w != 0;
+        return;
+    }
+    const unsigned long long e = (unsigned long long)b * per_sample + e_nchw0;
+    const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
+                                      ((unsigned long long)a.tcount[k] << 24) + ((unsigned long long)layer << 20) + (e >> 2));
+    keep[0] = flb_u01(r.x) >= a.drop_p; keep[1] = flb_u01(r.y) >= a.drop_p;
+    keep[2] = flb_u01(r.z) >= a.drop_p; keep[3] = flb_u01(r.w) >= a.drop_p;
+}
+
 // relu(bn(z)) -> 2x2 max-pool (+argmax) -> dropout.  One CTA per (sample, client).  FLAT: the output is fc1's
 // NCHW-flattened input [C * Ho * Wo]; otherwise the next resolution's padded NHWC grid.  Also updates running stats.
 template <int C, bool FLAT>
@@ -424,24 +439,51 @@ __global__ void __launch_bounds__(256) bn_relu_pool_drop_kernel(flb_train_args a
     float* out = out_all + kb * (FLAT ? C * npool : go.PP() * C);
     uint8_t* idx = idx_all + kb * npool * C;
     const float keep_scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-    for (int e = tid; e < npool * C; e += 256) {
-        const int c = e % C, pp = e / C, ph = pp / Wo, pw = pp - ph * Wo;
-        float best = -INFINITY;
-        int bi = 0;
+    // thread = (channel, group): 4 consecutive pooled positions of one channel per iteration (same pooled row: Wo % 4 == 0) --
+    // their dropout decisions are one Philox block, the window rows are 2 x 8 loads that coalesce over the channel lanes,
+    // and the indices come from shifts
+    constexpr int GROUPS = 256 / C;
+    const int c = tid % C, grp = tid / C, wshift = 31 - __clz(Wo);
+    const float sc = s_scale[c], sb = s_beta[c];
+    for (int qd = grp; qd < npool / 4; qd += GROUPS) {
+        const int pp0 = qd * 4, ph = pp0 >> wshift, pw0 = pp0 & (Wo - 1);
+        float zt[2][8];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float v = __fadd_rn(__fmul_rn(z[((2 * ph + i) * g.Wp + 2 * pw + j) * C + c], s_scale[c]), s_beta[c]);
-                if (v > best) { best = v; bi = i * 2 + j; }
+            for (int j = 0; j < 8; ++j) zt[i][j] = z[((2 * ph + i) * g.Wp + 2 * pw0 + j) * C + c];
+        bool keep[4] = {true, true, true, true};
+        if (a.drop_p > 0.f) drop_keep4(a, k, b, drop_layer, drop_off, npool * C, c * npool + pp0, keep);
+        float vo[4];
+        uint8_t bo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float best = -INFINITY;
+            int bi = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float v = __fadd_rn(__fmul_rn(zt[i][2 * t + j], sc), sb);
+                    if (v > best) { best = v; bi = i * 2 + j; }
+                }
+            float v = fmaxf(best, 0.f);
+            if (a.drop_p > 0.f) {
+                if (keep[t]) v *= keep_scale;
+                else { v = 0.f; bi |= 4; }
             }
-        float v = fmaxf(best, 0.f);
-        if (a.drop_p > 0.f) {
-            if (drop_keep(a, k, b, drop_layer, drop_off, npool * C, c * npool + pp)) v *= keep_scale;
-            else { v = 0.f; bi |= 4; }
+            vo[t] = v; bo[t] = (uint8_t)bi;
         }
-        if (FLAT) { out[c * npool + pp] = v; idx[c * npool + pp] = (uint8_t)bi; }
-        else { out[(ph * go.Wp + pw) * C + c] = v; idx[e] = (uint8_t)bi; }
+        if (FLAT) {
+            *reinterpret_cast<float4*>(out + c * npool + pp0) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+            *reinterpret_cast<uchar4*>(idx + c * npool + pp0) = make_uchar4(bo[0], bo[1], bo[2], bo[3]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                out[(ph * go.Wp + pw0 + t) * C + c] = vo[t];
+                idx[(pp0 + t) * C + c] = bo[t];
+            }
+        }
     }
 }
 
