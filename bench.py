@@ -40,7 +40,7 @@ WORKLOADS = {
 }
 # fwd + bwd algorithmic FLOPs per sample of the GEMM-shaped kernels (2 * MAC)
 GEMM_FLOPS = {
-    "simple_cnn": {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288,
+    "simple_cnn": {"conv2_fwd": 2 * 196 * 64 * 288, "conv2_dgrad": 2 * 196 * 32 * 576, "conv2_wgrad": 2 * 196 * 64 * 288, "conv2_wgrad_norm": 2 * 196 * 64 * 288,
                    "fc1_fwd": 2 * 3136 * 128, "fc1_dgrad": 2 * 3136 * 128, "fc1_wgrad": 2 * 3136 * 128},
     "cifar10_cnn": {f"conv{i}_{kind}": 2 * hw * ci * 9 * co for i, (hw, ci, co) in
                     enumerate([(1024, 3, 32), (1024, 32, 32), (256, 32, 64), (256, 64, 64), (64, 64, 128), (64, 128, 128)], start=1)

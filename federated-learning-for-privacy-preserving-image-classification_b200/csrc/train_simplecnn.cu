@@ -630,9 +630,12 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
             FLB_CUDA(cudaStreamWaitEvent(lane_ps->s, lane_ps->ev[0], 0));
         }
         conv1_bwd_kernel<true><<<per_sample, 256, 0, lane_ps ? lane_ps->s : st>>>(a, ws);
+        MARK("conv1_ps_grad");
         linear_ghost_norm_kernel<<<per_sample, 128, 0, st>>>(a, ws);
+        MARK("linear_ghost_norm");
         if (tcm & TC_CONV2_WGRAD) {          // per-sample conv2 gradient tiles live in TMEM only (tcgen05), squared on the way out
             if (int rc = tc::conv_wgrad_norm_32_64(a, kConv2, ws.a1p, ws.z2, ws.norm2, st)) return rc;
+            MARK("conv2_wgrad_norm");
             conv2_bias_grad_kernel<<<per_sample, 256, 0, st>>>(a, ws, 2);
         } else {
             ConvWgradNormProb p{}; p.a = a; p.g = kConv2; p.dz_all = ws.z2; p.xin_all = ws.a1p; p.norm2_all = ws.norm2;
@@ -644,7 +647,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
         }
         clip_coef_kernel<<<flb_cdiv(K * B, 256), 256, 0, st>>>(a, ws);
         coef = ws.coef;
-        MARK("per_sample_norms");
+        MARK("clip_coef");
     }
 
     // ---- weight gradients ----
