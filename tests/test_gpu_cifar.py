@@ -237,7 +237,7 @@ def test_tf32_tensor_core_path_matches_fp32_path(cuda_device):
     gradients in relative L2.  TF32 perturbs pre-activations by ~1e-3 relative, which flips the ReLU / max-pool
     decision of the ~0.1 % of units sitting that close to a tie; a fraction f of flipped units reroutes whole gradient
     elements and shows up as ~sqrt(f) relative L2 error (measured 3 % after fc2 growing to 7 % at conv1 through six
-    BatchNorm layers, scripts/dbg_cifar.py tf32) -- hence relative L2 with a 0.12 bound, not a max-norm bound."""
+    BatchNorm layers, tests/tools/dbg_cifar.py tf32) -- hence relative L2 with a 0.12 bound, not a max-norm bound."""
     sizes = [16, 9, 3]
     engs = {}
     for prec in ("fp32", "tf32"):
@@ -264,7 +264,7 @@ def test_tf32_tensor_core_path_matches_fp32_path(cuda_device):
 def test_tf32_training_epoch_tracks_fp32(cuda_device):
     """The TF32 trajectory starts ~6 % (relative L2 of the accumulated update) away from the fp32 one -- the one-step
     gradient error above -- and the two then drift apart like any two nearby trajectories of a ReLU/max-pool net
-    (measured, scripts/dbg_cifar_traj.py: 6 % after 1-3 steps, 15 % after 6, 29 % after 12 at batch 8)."""
+    (measured, tests/tools/dbg_cifar_traj.py: 6 % after 1-3 steps, 15 % after 6, 29 % after 12 at batch 8)."""
     sizes = (24, 16)
     outs = {}
     for prec in ("fp32", "tf32"):

@@ -1,6 +1,6 @@
 """debug aid: per-tensor gradient error of the CIFAR10CNN kernels vs the CPU oracle (fp64 oracle as the arbiter)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import flb200
 from flb200.training import BatchedClientTrainer

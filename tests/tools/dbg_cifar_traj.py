@@ -1,6 +1,6 @@
 """debug aid: divergence of the TF32 trajectory from the fp32 one, step by step (CIFAR10CNN, SGD)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import flb200
 from flb200.training import BatchedClientTrainer
