@@ -64,7 +64,7 @@ int flb_q8_dequantize(const uint8_t* q, long long ldq, const long long* seg_off,
 
 /* ---- one-pass update validation / convergence reductions --------------------------------------
  * src/shared/validation.py:72-91 (isnan / isinf / abs().max() per tensor: 3 passes + 3 syncs each upstream) and
- * src/aggregation/fedavg.py:144-190 (per-layer ||new - old||, ||new||).
+ * src/aggregation/fedavg.py:144-190, src/aggregation/convergence.py:189-217 (per-layer ||new - old||, ||new||).
  * ptrs[k*L + l] = device pointer of tensor l of client k (seg_off gives the element counts).
  * max_abs[k*L + l] = max |x| (NaN ignored), flags[k*L + l] = 1 if any NaN | 2 if any Inf. */
 int flb_update_stats(const float* const* ptrs, const long long* seg_off, float* max_abs, unsigned int* flags,
@@ -92,7 +92,8 @@ int flb_topk_scatter(const int* idx, const float* val, long long ldk, const long
                      const long long* out_off, float* dense, long long ld, int K, int L, long long P, void* stream);
 
 /* ---- batched local training: src/shared/training.py:60-212 (LocalTrainer._train_epoch), ------------------
- *      models src/shared/models_pytorch.py:59-97 (SimpleCNN), optimizers training.py:244-255 ----------------
+ *      models src/shared/models_pytorch.py:59-97 (SimpleCNN, model 0) and :100-165 (CIFAR10CNN, model 1),
+ *      optimizers training.py:244-255, evaluation training.py:214-242,307-360 (eval_mode) -----------------------
  * One call advances EVERY resident client by one minibatch step (zero_grad -> forward -> mean cross-entropy ->
  * backward -> optimizer step, training.py:189-197).  All pointers are device pointers; the struct itself is
  * host memory and is read at call time only. */
