@@ -353,8 +353,10 @@ def main():
             "roofline": roof, "clocks": sampler.summary()}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, sample = (cpu_baseline_run(CLIENTS_PER_GPU, threads, 4) if MODEL == "simple_cnn"
-                     else cpu_baseline_run(4, threads, 1, MODEL))
+        # a bounded sample of the same workload, ~10 s of CPU work: 24 rounds of the 10-client SimpleCNN job / 1 round of 8
+        # CIFAR10CNN clients
+        v, sample = (cpu_baseline_run(CLIENTS_PER_GPU, threads, 24) if MODEL == "simple_cnn"
+                     else cpu_baseline_run(8, threads, 1, MODEL))
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line), file=out, flush=True)
