@@ -51,6 +51,8 @@ def main():
                     v /= 1e6
                 elif metric.startswith("dram__bytes") and u == "Kbyte":
                     v /= 1e3
+                elif metric.startswith("dram__bytes") and u == "Gbyte":
+                    v *= 1e3
                 elif metric == "gpu__time_duration.sum" and u in ("ns", "nsecond"):
                     v /= 1e3
                 out.append(f"{v:.3f}".rstrip("0").rstrip("."))
