@@ -15,6 +15,12 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libflb.so")
 
 
+def fresh_seed() -> int:
+    """64 bits of OS entropy: the default Philox seed of every object that draws DP noise or dropout masks (the reference
+    draws from torch's nondeterministically seeded global RNG; a fixed default would make the noise reproducible by anyone)."""
+    return int.from_bytes(os.urandom(8), "little")
+
+
 class FlbError(RuntimeError):
     """A libflb.so call failed (or the library / device is unavailable)."""
 
@@ -46,6 +52,7 @@ SIGNATURES = {
     "flb_train_bn_floats": [_i],
     "flb_train_begin_epoch": [_vp, _vp],
     "flb_train_step": [_vp, _vp],
+    "flb_train_step_grads": [_vp, _vp, _ll, _vp],
     "flb_train_forward_backward": [_vp, _vp],
     "flb_train_forward": [_vp, _vp],
     "flb_train_advance": [_vp, _vp],
@@ -62,7 +69,7 @@ class TrainArgs(C.Structure):
         ("x", _vp), ("y", _vp), ("sample_off", _vp), ("nsamples", _vp), ("step_ctr", _vp),
         ("W", _vp), ("G", _vp), ("M", _vp), ("V", _vp), ("tcount", _vp), ("ws", _vp),
         ("loss_sum", _vp), ("correct", _vp), ("nbatch", _vp), ("nseen", _vp),
-        ("drop_keep", _vp), ("dp_z", _vp), ("bn_running", _vp),
+        ("drop_keep", _vp), ("dp_z", _vp), ("bn_running", _vp), ("epoch_nonce", _vp),
         ("ld", _ll), ("seed", _ull), ("client_base", _ull), ("client_stride", _ull),
         ("lr", _d), ("beta1", _d), ("beta2", _d), ("eps", _d), ("weight_decay", _d), ("momentum", _d),
         ("model", _i), ("K", _i), ("B", _i), ("precision", _i), ("opt", _i), ("dp_mode", _i), ("eval_mode", _i), ("tc_mask", _i),

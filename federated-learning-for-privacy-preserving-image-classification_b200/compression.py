@@ -25,6 +25,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .interfaces import CompressionInterface
 from .layout import ParamLayout
 from .models import ModelWeights
 
@@ -184,7 +185,7 @@ class TopKSparsificationCompressor(BaseCompressor):
         return f"topk_sparsification_{self.sparsity_ratio}"
 
 
-class ModelCompressionService:
+class ModelCompressionService(CompressionInterface):
     """src/shared/compression.py:371-470 (same methods and envelope)."""
 
     def __init__(self, algorithm: str = "quantization", **kwargs):

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
             }
             if (p0 < tab.g_zero_upto) reinterpret_cast<float4*>(G)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (DP && c.sigma > 0.f && !zrow) {
-                const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
+                const float4 zz = flb_normal4(flb_epoch_seed(a), a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + c4);
                 z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
             }
 #pragma unroll
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
                 if (DP) {
                     if (zrow) z = zrow[p];
                     else if (c.sigma > 0.f) {
-                        const float4 zz = flb_normal4(a.seed, a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + (p >> 2));
+                        const float4 zz = flb_normal4(flb_epoch_seed(a), a.client_base + a.client_stride * k, ((unsigned long long)t << 32) + (p >> 2));
                         const float za[4] = {zz.x, zz.y, zz.z, zz.w};
                         z = za[p & 3];
                     }
@@ -226,7 +226,10 @@ __global__ void advance_kernel(flb_train_args a) {
 __global__ void begin_epoch_kernel(flb_train_args a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < a.K) { a.loss_sum[k] = 0.f; a.correct[k] = 0; a.nbatch[k] = 0; a.nseen[k] = 0; }
-    if (k == 0) { a.step_ctr[0] = 0; a.step_ctr[1] = 0; }
+    if (k == 0) {
+        a.step_ctr[0] = 0; a.step_ctr[1] = 0;
+        if (a.epoch_nonce) *a.epoch_nonce += 1;
+    }
 }
 
 int check_args(const flb_train_args* a) {
@@ -319,6 +322,24 @@ extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     const int P = num_params(*a);
     launch_optimizer(*a, P, tab_of(*a), st);
     MARK("optimizer");
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+// flb_train_step that also hands out the minibatch gradient it applied (LocalTrainer.get_model_gradients,
+// training.py:362-371: param.grad after the last step): the rows are copied after the backward pass and before the
+// optimizer consumes (and re-zeroes) them; tensor-core conv layers are first brought back from the tap-major copy.
+extern "C" int flb_train_step_grads(const flb_train_args* a, float* grads_out, long long ld_out, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    const int P = num_params(*a);
+    FLB_CHECK_ARG(grads_out != nullptr && ld_out >= P, "flb_train_step_grads: need grads_out [K, ld_out >= %d]", P);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = fwd_bwd(*a, st, false)) return rc;
+    const TcConvTab t = tab_of(*a);
+    if (t.n) tc_repack_kernel<1><<<dim3(repack_blocks(*a, t), a->K), 256, 0, st>>>(*a, t);
+    FLB_CUDA(cudaMemcpy2DAsync(grads_out, (size_t)ld_out * sizeof(float), a->G, (size_t)a->ld * sizeof(float),
+                               (size_t)P * sizeof(float), (size_t)a->K, cudaMemcpyDeviceToDevice, st));
+    launch_optimizer(*a, P, t, st);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

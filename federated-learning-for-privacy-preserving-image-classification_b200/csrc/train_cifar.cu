@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(flb_train_args a, Co
 __device__ __forceinline__ bool drop_keep(const flb_train_args& a, int k, int b, int layer, int layer_off, int per_sample, int e_nchw) {
     if (a.drop_keep) return a.drop_keep[((long long)k * a.B + b) * DROP_PER_SAMPLE + layer_off + e_nchw] != 0;
     const unsigned long long e = (unsigned long long)b * per_sample + e_nchw;
-    const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
+    const flb_u4 r = flb_philox_block(flb_epoch_seed(a) ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
                                       ((unsigned long long)a.tcount[k] << 24) + ((unsigned long long)layer << 20) + (e >> 2));
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
     return flb_u01(rr[e & 3]) >= a.drop_p;
@@ -401,7 +401,7 @@ __device__ __forceinline__ void drop_keep4(const flb_train_args& a, int k, int b
         return;
     }
     const unsigned long long e = (unsigned long long)b * per_sample + e_nchw0;
-    const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
+    const flb_u4 r = flb_philox_block(flb_epoch_seed(a) ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
                                       ((unsigned long long)a.tcount[k] << 24) + ((unsigned long long)layer << 20) + (e >> 2));
     keep[0] = flb_u01(r.x) >= a.drop_p; keep[1] = flb_u01(r.y) >= a.drop_p;
     keep[2] = flb_u01(r.z) >= a.drop_p; keep[3] = flb_u01(r.w) >= a.drop_p;

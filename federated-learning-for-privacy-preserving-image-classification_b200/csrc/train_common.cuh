@@ -26,6 +26,12 @@ __device__ __forceinline__ int flb_bsz(const flb_train_args& a, int client) {
     return r < 0 ? 0 : (r > a.B ? a.B : r);
 }
 
+// Philox key of this epoch's dropout masks / per-sample-DP noise: the caller's seed advanced by the never-reset epoch
+// counter, so the optimizer step count t (reset by every train_local_model call) can stay the in-epoch counter part.
+__device__ __forceinline__ unsigned long long flb_epoch_seed(const flb_train_args& a) {
+    return a.seed + (a.epoch_nonce ? *a.epoch_nonce : 0ull) * 0x9E3779B97F4A7C15ull;
+}
+
 // SimpleCNN parameter offsets in a row (reference named_parameters order, models_pytorch.py:69-80)
 struct SimpleCnnOff {
     static constexpr int c1w = 0, c1b = 288, c2w = 320, c2b = 18752, f1w = 18816, f1b = 420224, f2w = 420352,

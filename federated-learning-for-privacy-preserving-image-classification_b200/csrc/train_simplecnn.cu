@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Sim
                 for (int i = 0; i < 4; ++i) keep[i] = a.drop_keep[kb * 128 + e + i] != 0;
             } else {
                 const int eg = b0 * 128 + e;                   // element index within the client's [B, 128] block
-                const flb_u4 r = flb_philox_block(a.seed ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
+                const flb_u4 r = flb_philox_block(flb_epoch_seed(a) ^ 0xD80F0A7ull, a.client_base + a.client_stride * k,
                                                   ((unsigned long long)a.tcount[k] << 12) + (eg >> 2));
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll

@@ -8,6 +8,9 @@ ToTensor + Normalize + host->device copy of its loaders (:298-306, :454-464, tra
     (``csrc/shards.cu``) writes the packed, device-resident sample store that ``FederatedRoundEngine.attach_device_shards``
     hands to the training kernels: no per-batch transform, no per-batch copy.
 
+  * ``DeviceShardLoader`` -- the reference's ``MNISTDataLoader`` / ``CIFAR10DataLoader`` contract (``DataLoaderInterface``:
+    load_training_data / load_validation_data / get_data_statistics, :267-420) over arrays the caller already holds.
+
 Dataset download (torchvision, network) and the CIFAR train-time RandomCrop / RandomHorizontalFlip augmentation are not
 part of this module."""
 from __future__ import annotations
@@ -21,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .interfaces import DataLoaderInterface
 
 logger = logging.getLogger(__name__)
 
@@ -212,3 +216,91 @@ class DeviceShardBuilder:
                    L.ptr(self.mean), L.ptr(self.std), L.ptr(x), st)
             L.call("flb_gather_labels", L.ptr(self.labels), L.ptr(idx_dev), L.ptr(y), M, st)
         return x, y, sizes
+
+
+class DeviceBatches:
+    """What ``DataLoader(dataset, batch_size, shuffle)`` yields (data_loader.py:356-362), over tensors that already sit
+    normalised on the device: every pass re-draws the permutation when ``shuffle`` is set; batches are slices, no copies
+    to the host and back.  ``LocalTrainer`` accepts it like any loader."""
+
+    def __init__(self, x: torch.Tensor, y: torch.Tensor, batch_size: int, shuffle: bool):
+        self.x, self.y, self.batch_size, self.shuffle = x, y, int(batch_size), shuffle
+        self.dataset = y                    # len(loader.dataset), as callers of a DataLoader use it
+
+    def __len__(self) -> int:
+        return (int(self.y.shape[0]) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = int(self.y.shape[0])
+        x, y = self.x, self.y
+        if self.shuffle and n:
+            perm = torch.randperm(n, device=x.device)
+            x, y = x[perm], y[perm]
+        for i in range(0, n, self.batch_size):
+            yield x[i:i + self.batch_size], y[i:i + self.batch_size]
+
+
+class DeviceShardLoader(DataLoaderInterface):
+    """``MNISTDataLoader`` / ``CIFAR10DataLoader`` (data_loader.py:267-420, :423-600) without the download: the caller
+    passes the raw uint8 training (and optionally test) arrays; partitioning follows ``DataPartitioner`` and the
+    per-client tensors are built by ONE gather + normalise launch each (``DeviceShardBuilder``) and cached on the device.
+    Client ids are parsed like upstream (:333): ``"client-3"`` or ``"3"``."""
+
+    def __init__(self, images, labels, mean: Sequence[float], std: Sequence[float], num_clients: int = 10,
+                 partition_strategy: str = "iid", batch_size: int = 32, validation_split: float = 0.1, device=None,
+                 test_images=None, test_labels=None, channels_last: bool = True):
+        self.num_clients, self.partition_strategy = num_clients, partition_strategy
+        self.batch_size, self.validation_split = batch_size, validation_split
+        self.builder = DeviceShardBuilder(images, labels, mean, std, device, channels_last)
+        self.test_builder = (DeviceShardBuilder(test_images, test_labels, mean, std, device, channels_last)
+                             if test_images is not None else None)
+        self.partitioner = DataPartitioner(None, num_clients, partition_strategy,
+                                           labels=[int(v) for v in np.asarray(labels).reshape(-1)])
+        self._splits: Dict[int, Tuple[List[int], List[int]]] = {}
+        self._shape = (self.builder.C, self.builder.H, self.builder.W)
+
+    @staticmethod
+    def _client_index(client_id) -> int:
+        cid = str(client_id)
+        return int(cid.split("-")[-1]) if "-" in cid else int(cid)
+
+    def _split(self, idx: int) -> Tuple[List[int], List[int]]:
+        """(train, validation) index lists of one client: ``int(n * split)`` held out (:344-352), drawn once per client
+        so that the two loaders never overlap (upstream re-draws ``random_split`` on every call)."""
+        if idx >= self.num_clients:
+            raise ValueError(f"Client ID {idx} exceeds number of clients {self.num_clients}")
+        if idx not in self._splits:
+            ind = list(self.partitioner.client_indices[idx])
+            n_val = int(len(ind) * self.validation_split) if self.validation_split > 0 else min(100, len(ind) // 10)
+            perm = torch.randperm(len(ind)).tolist() if self.validation_split > 0 else list(range(len(ind)))
+            val = [ind[i] for i in perm[:n_val]]
+            train = [ind[i] for i in perm[n_val:]] if self.validation_split > 0 else ind
+            self._splits[idx] = (train, val)
+        return self._splits[idx]
+
+    def _batches(self, builder: DeviceShardBuilder, indices: List[int], shuffle: bool) -> DeviceBatches:
+        x, y, sizes = builder.build({0: indices}, [0])
+        n = sizes[0]
+        return DeviceBatches(x[:n].view((n,) + self._shape), y[:n].to(torch.int64), self.batch_size, shuffle)
+
+    def load_training_data(self, client_id) -> DeviceBatches:
+        return self._batches(self.builder, self._split(self._client_index(client_id))[0], shuffle=True)
+
+    def load_validation_data(self, client_id=None) -> DeviceBatches:
+        if client_id:
+            return self._batches(self.builder, self._split(self._client_index(client_id))[1], shuffle=False)
+        if self.test_builder is None:
+            raise ValueError("no test set was given: pass test_images / test_labels for the global validation loader")
+        return self._batches(self.test_builder, list(range(self.test_builder.N)), shuffle=False)
+
+    def get_data_statistics(self, client_id) -> Dict[str, Any]:
+        try:
+            idx = self._client_index(client_id)
+            counts: Dict[int, int] = defaultdict(int)
+            for i in self.partitioner.client_indices[idx]:
+                counts[self.partitioner.labels[i]] += 1
+            return {"client_id": str(idx), "total_samples": len(self.partitioner.client_indices[idx]),
+                    "class_distribution": dict(counts), "num_classes": len(counts)}
+        except Exception as e:
+            logger.error(f"Failed to get data statistics for client {client_id}: {e}")
+            return {}

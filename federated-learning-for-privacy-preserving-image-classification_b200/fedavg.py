@@ -22,6 +22,7 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .interfaces import AggregationServiceInterface
 from .layout import ParamLayout
 from .models import GlobalModel, ModelUpdate, ModelWeights
 from .validation import ModelUpdateValidator, validate_model_compatibility
@@ -50,7 +51,7 @@ class _Staging:
         return self.host, self.dev
 
 
-class FedAvgAggregator:
+class FedAvgAggregator(AggregationServiceInterface):
     def __init__(self, min_clients: int = 2, max_clients: Optional[int] = None, validate_updates: bool = True,
                  device: Optional[torch.device] = None):
         self.min_clients = min_clients
@@ -204,6 +205,17 @@ class FedAvgAggregator:
             for name in u.model_weights:
                 if name not in layout.offsets:
                     logger.warning(f"Layer {name} not found in reference model")
+            # The kernels address every update with the FIRST update's layer sizes: a tensor of another shape (or a missing
+            # one) would be read out of bounds.  Upstream fails on the shape mismatch inside `+=` (fedavg.py:285); the
+            # compatibility filter can let such an update through (pop-while-enumerating, :237-243) and
+            # validate_updates=False skips it altogether, so the check lives here, before any pointer is taken.
+            for name in layout.names:
+                t = u.model_weights.get(name)
+                if t is None:
+                    raise FedAvgError(f"Update from {u.client_id} has no tensor for layer {name}")
+                if tuple(t.shape) != tuple(layout.shapes[name]):
+                    raise FedAvgError(f"Update from {u.client_id}: layer {name} has shape {tuple(t.shape)}, "
+                                      f"expected {tuple(layout.shapes[name])}")
         on_device = all(u.model_weights[n].device == device and u.model_weights[n].dtype == torch.float32
                         and u.model_weights[n].is_contiguous() for u in updates for n in layout.names)
         if on_device:

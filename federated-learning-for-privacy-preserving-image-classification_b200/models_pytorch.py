@@ -14,6 +14,7 @@ from typing import Any, Dict, List
 import torch
 import torch.nn as nn
 
+from .interfaces import ModelInterface
 from .models import ModelWeights
 
 logger = logging.getLogger(__name__)
@@ -22,7 +23,7 @@ MODEL_IDS = {"simple_cnn": 0, "cifar10_cnn": 1}
 INPUT_SHAPES = {"simple_cnn": (1, 28, 28), "cifar10_cnn": (3, 32, 32)}
 
 
-class FederatedCNNBase(nn.Module):
+class FederatedCNNBase(nn.Module, ModelInterface):
     def __init__(self):
         super().__init__()
         self.model_name = "base_cnn"

@@ -21,12 +21,11 @@ import torch
 
 from . import _lib as L
 from . import ops
+from .interfaces import PrivacyEngineInterface
 from .layout import ParamLayout
 from .models import ModelWeights, PrivacyConfig
 
 logger = logging.getLogger(__name__)
-
-DEFAULT_NOISE_SEED = 42
 
 
 class PrivacyError(Exception):
@@ -121,11 +120,13 @@ class GradientClipper:
 
 class GaussianNoiseGenerator:
     """sigma = S*sqrt(2 ln(1.25/delta))/eps (privacy.py:209); normals from Philox4x32-10 + Box-Muller in
-    registers instead of ``torch.normal`` (:212).  Every call advances ``self.stream`` so draws never repeat."""
+    registers instead of ``torch.normal`` (:212).  Every call advances ``self.stream`` so draws never repeat, and the
+    seed defaults to fresh OS entropy per generator (like torch's global RNG upstream): two engines, or two client
+    processes, never share a noise sequence.  ``seed=`` is for reproducible tests only."""
 
-    def __init__(self, device: Optional[torch.device] = None, seed: int = DEFAULT_NOISE_SEED):
+    def __init__(self, device: Optional[torch.device] = None, seed: Optional[int] = None):
         self.device = _default_device(device)
-        self.seed = seed
+        self.seed = L.fresh_seed() if seed is None else int(seed) & (2**64 - 1)
         self.stream = 0
 
     @staticmethod
@@ -156,16 +157,16 @@ class GaussianNoiseGenerator:
             raise PrivacyError(f"Adding noise to gradients failed: {str(e)}")
 
 
-class DifferentialPrivacyEngine:
+class DifferentialPrivacyEngine(PrivacyEngineInterface):
     """privacy.py:257-416.  ``device=None`` means the current CUDA device (the reference defaults to CPU;
     this package has no CPU path).  Inputs may live on the host: they are staged to the device and the
     result is returned on the input's device, as new tensors (inputs are never mutated)."""
 
-    def __init__(self, privacy_config: PrivacyConfig, device: Optional[torch.device] = None):
+    def __init__(self, privacy_config: PrivacyConfig, device: Optional[torch.device] = None, seed: Optional[int] = None):
         self.config = privacy_config
         self.device = _default_device(device)
         self.clipper = GradientClipper(privacy_config.max_grad_norm, self.device)
-        self.noise_generator = GaussianNoiseGenerator(self.device)
+        self.noise_generator = GaussianNoiseGenerator(self.device, seed)      # seed=None: fresh entropy
         self.budget_tracker = PrivacyBudgetTracker(privacy_config.epsilon, privacy_config.delta)
 
     # -- the hot call ----------------------------------------------------------------------------
@@ -302,9 +303,9 @@ class PrivacyAccountant:
 
 def create_privacy_engine(epsilon: float = 1.0, delta: float = 1e-5, max_grad_norm: float = 1.0,
                           noise_multiplier: float = 1.0,
-                          device: Optional[torch.device] = None) -> DifferentialPrivacyEngine:
+                          device: Optional[torch.device] = None, seed: Optional[int] = None) -> DifferentialPrivacyEngine:
     return DifferentialPrivacyEngine(PrivacyConfig(epsilon=epsilon, delta=delta, max_grad_norm=max_grad_norm,
-                                                   noise_multiplier=noise_multiplier), device)
+                                                   noise_multiplier=noise_multiplier), device, seed)
 
 
 def estimate_privacy_parameters(target_accuracy: float = 0.9, dataset_size: int = 10000,

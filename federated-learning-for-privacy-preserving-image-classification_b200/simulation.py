@@ -67,7 +67,7 @@ class FederatedRoundEngine:
                  process_group=None, batch_size: int = 32, local_epochs: int = 1, learning_rate: float = 0.001,
                  optimizer_type: str = "adam", dp_mode: str = "update", epsilon: float = 1.0, delta: float = 1e-5,
                  max_grad_norm: float = 1.0, dropout_rate: Optional[float] = None, precision: str = "fp32",
-                 compression: Optional[str] = None, seed: int = 42, use_graph: bool = True):
+                 compression: Optional[str] = None, seed: Optional[int] = None, use_graph: bool = True):
         if dp_mode not in ("none", "update", "per_sample"):
             raise ValueError("dp_mode must be 'none', 'update' (reference behaviour) or 'per_sample'")
         if compression not in (None, "q8"):
@@ -81,7 +81,10 @@ class FederatedRoundEngine:
         self.local_epochs, self.lr, self.optimizer_type = local_epochs, learning_rate, optimizer_type
         self.dp_mode, self.epsilon, self.delta, self.max_grad_norm = dp_mode, epsilon, delta, max_grad_norm
         self.compression = compression
-        self.seed = seed
+        # One Philox seed for the round's DP noise and the trainer's dropout masks.  None = fresh OS entropy (rank 0's
+        # draw is shared across ranks so that the streams, keyed by GLOBAL client index, do not depend on the GPU count).
+        self.seed = self._agree_on_seed(seed)
+        seed = self.seed
         self.trainer = BatchedClientTrainer(model_name, len(self.client_ids), device, batch_size, dropout_rate,
                                             precision, seed=seed, client_base=rank, client_stride=world_size, use_graph=use_graph)
         self.device = self.trainer.device
@@ -96,6 +99,17 @@ class FederatedRoundEngine:
         self.round_number = 0
         self.history: List[Dict[str, Any]] = []
         self.dp_z: Optional[torch.Tensor] = None             # injected standard normals [K_local, ld] (parity tests)
+
+    def _agree_on_seed(self, seed: Optional[int]) -> int:
+        if seed is not None:
+            return int(seed) & (2**64 - 1)
+        seed = L.fresh_seed()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            box = [seed]
+            dist.broadcast_object_list(box, src=0, group=self.pg)
+            seed = int(box[0])
+        return seed
 
     # ---- setup -------------------------------------------------------------------------------------------
     def set_global_weights(self, weights: Dict[str, torch.Tensor]) -> None:

@@ -58,7 +58,7 @@ class BatchedClientTrainer:
     """K simulated clients training side by side on one GPU (the "batched across clients" engine)."""
 
     def __init__(self, model_name: str, num_clients: int, device=None, batch_size: int = 32,
-                 dropout_rate: Optional[float] = None, precision: str = "fp32", seed: int = 42,
+                 dropout_rate: Optional[float] = None, precision: str = "fp32", seed: Optional[int] = None,
                  client_base: int = 0, client_stride: int = 1, use_graph: bool = True):
         if model_name not in MODEL_IDS:
             raise ValueError(f"Unknown model: {model_name}. Available: {list(MODEL_IDS)}")
@@ -73,7 +73,9 @@ class BatchedClientTrainer:
         self.device = _cuda_device(device)
         L.ensure_device(self.device)
         self.precision = precision
-        self.seed = seed
+        # Philox seed of dropout masks and per-sample-DP noise.  Default: fresh entropy per engine (torch's global RNG is
+        # nondeterministically seeded upstream too); pass ``seed=`` only for reproducible tests.
+        self.seed = L.fresh_seed() if seed is None else int(seed) & (2**64 - 1)
         self.client_base = client_base
         self.client_stride = client_stride
         self.use_graph = use_graph
@@ -88,6 +90,7 @@ class BatchedClientTrainer:
         self.V = lay.new_rows(K, dev)
         self.tcount = torch.zeros(K, dtype=torch.int32, device=dev)
         self.step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.epoch_nonce = torch.zeros(1, dtype=torch.int64, device=dev)   # +1 per epoch on the device, never reset (flb.h)
         # epoch accumulators in ONE buffer ([4, K] 32-bit words) so that they reach the host in one copy
         self._metrics = torch.zeros((4, K), dtype=torch.int32, device=dev)
         self.loss_sum = self._metrics[0].view(torch.float32)
@@ -111,6 +114,8 @@ class BatchedClientTrainer:
         self._staged = None                      # (x, y, event) uploaded ahead of time by prefetch_packed
         self._spare = None                       # the sample buffers not in use (double buffering)
         self._copy_stream = None
+        self.keep_last_grads = False              # LocalTrainer: the epoch's last step also stores its gradient rows
+        self.last_grads: Optional[torch.Tensor] = None
         self.args = L.TrainArgs()
 
     # ---- state ---------------------------------------------------------------------------------------
@@ -260,6 +265,7 @@ class BatchedClientTrainer:
         a.W, a.G, a.M, a.V, a.tcount, a.ws = p(self.W), p(self.G), p(self.M), p(self.V), p(self.tcount), p(self.ws)
         a.loss_sum, a.correct, a.nbatch, a.nseen = p(self.loss_sum), p(self.correct), p(self.nbatch), p(self.nseen)
         a.drop_keep, a.dp_z, a.bn_running = p(self.drop_keep), p(self.dp_z), p(self.bn_running)
+        a.epoch_nonce = p(self.epoch_nonce)
         a.eval_mode = 0 if train else 1
         a.ld, a.seed, a.client_base, a.client_stride = self.layout.ld, self.seed, self.client_base, self.client_stride
         a.lr, a.beta1, a.beta2, a.eps = float(lr), 0.9, 0.999, 1e-8            # torch.optim.Adam / AdamW defaults
@@ -278,14 +284,20 @@ class BatchedClientTrainer:
         st = L.stream_ptr(self.device)
         ap = C.byref(self.args)
         L.call("flb_train_begin_epoch", ap, st)
-        for _ in range(self.max_steps()):
-            L.call("flb_train_step", ap, st)
+        n = self.max_steps()
+        for s in range(n):
+            if self.keep_last_grads and s == n - 1:
+                L.call("flb_train_step_grads", ap, L.ptr(self.last_grads), self.layout.ld, st)
+            else:
+                L.call("flb_train_step", ap, st)
 
     def _run_epoch(self) -> None:
         """Eager the first time a configuration is seen, captured into one CUDA graph (begin_epoch + every step of the
         epoch) the second time, replayed afterwards.  All per-step variation is device-side, so the graph is static."""
         with torch.cuda.device(self.device):
-            key = (bytes(self.args), self.max_steps())
+            if self.keep_last_grads and self.last_grads is None:
+                self.last_grads = self.layout.new_rows(self.K, self.device)      # before any capture: no allocation inside
+            key = (bytes(self.args), self.max_steps(), self.keep_last_grads)
             if self.use_graph and key in self._graphs:
                 self._graphs[key].replay()
                 return
@@ -414,9 +426,11 @@ def _collect_loader(loader: Iterable, max_batch: int = MAX_BATCH) -> Tuple[torch
     return torch.cat(xs), torch.cat(ys), bs
 
 
-def _engine_for(model: FederatedCNNBase, device, batch_size: int, precision: str) -> BatchedClientTrainer:
+def _engine_for(model: FederatedCNNBase, device, batch_size: int, precision: str, role: str = "train") -> BatchedClientTrainer:
+    """K = 1 engine cached on the module.  ``role`` keeps evaluation apart from training: a validation pass between two
+    epochs must not touch the live optimizer state (step counts feed Adam's bias correction and the Philox counters)."""
     cache = model.__dict__.setdefault("_flb_engines", {})
-    key = (str(device), batch_size, precision)
+    key = (str(device), batch_size, precision, role)
     if key not in cache:
         cache[key] = BatchedClientTrainer(model.model_name, 1, device, batch_size, model.dropout_rate, precision)
     return cache[key]
@@ -427,7 +441,7 @@ def forward_logits(model: FederatedCNNBase, x: torch.Tensor, precision: str = "f
     p = next(model.parameters())
     if not p.is_cuda:
         raise L.FlbError("model.forward: parameters are on the CPU; move the model to a CUDA device (no CPU path)")
-    eng = _engine_for(model, p.device, MAX_BATCH, precision)
+    eng = _engine_for(model, p.device, MAX_BATCH, precision, "eval")
     _push_model(model, eng)
     eng.load_data([x.detach().to(torch.float32)], [torch.zeros(x.shape[0], dtype=torch.int64)])
     if model.training and model.dropout_rate > 0:
@@ -508,6 +522,7 @@ class LocalTrainer:
                 if eng is None:
                     eng = _engine_for(self.model, self.device, bs, self.precision)
                     eng.dropout_rate = float(self.model.dropout_rate)
+                    eng.keep_last_grads = True
                     self._push(eng)
                     eng.M.zero_(); eng.V.zero_(); eng.tcount.zero_()       # fresh optimizer (training.py:89)
                 elif eng.B != bs:
@@ -532,8 +547,8 @@ class LocalTrainer:
                         patience += 1
                         if patience >= early_stopping_patience:
                             break
-            if eng is not None:
-                self._last_grads = {n: v.clone() for n, v in eng.layout.views(eng.G[0]).items()}
+            if eng is not None and eng.last_grads is not None:
+                self._last_grads = {n: v.clone() for n, v in eng.layout.views(eng.last_grads[0]).items()}
             metrics = TrainingMetrics(loss=losses[-1] if losses else 0.0, accuracy=accs[-1] if accs else 0.0,
                                       epochs_completed=len(losses), training_time=time.time() - start,
                                       samples_processed=total_samples)
@@ -548,7 +563,7 @@ class LocalTrainer:
     def _validate_epoch(self, val_loader, criterion=None) -> Tuple[float, float]:
         self.model.eval()
         x, y, bs = _collect_loader(val_loader)
-        eng = _engine_for(self.model, self.device, bs, self.precision)
+        eng = _engine_for(self.model, self.device, bs, self.precision, "eval")
         self._push(eng)
         eng.load_data([x], [y])
         loss, acc, _, _ = eng.evaluate()
@@ -558,7 +573,7 @@ class LocalTrainer:
         try:
             self.model.eval()
             x, y, bs = _collect_loader(test_loader)
-            eng = _engine_for(self.model, self.device, bs, self.precision)
+            eng = _engine_for(self.model, self.device, bs, self.precision, "eval")
             self._push(eng)
             eng.load_data([x], [y])
             _, _, _, logits = eng.evaluate()
@@ -575,7 +590,9 @@ class LocalTrainer:
             raise TrainingError(f"Model evaluation failed: {str(e)}")
 
     def get_model_gradients(self) -> Dict[str, torch.Tensor]:
-        """Gradients of the last minibatch step (the kernels keep them in the flat G row, not in ``param.grad``)."""
+        """Gradients of the last minibatch step, as ``param.grad`` holds them upstream after ``train_local_model``
+        (training.py:362-371).  The kernels keep gradients in flat rows that the optimizer consumes; the epoch's last step
+        copies them out first (``flb_train_step_grads``)."""
         return {n: g.clone() for n, g in self._last_grads.items()}
 
     def set_model_gradients(self, gradients: Dict[str, torch.Tensor]):
@@ -637,7 +654,8 @@ class FederatedTrainingConfig:
 
 def create_adaptive_config(client_capabilities: Dict[str, Any]) -> FederatedTrainingConfig:
     """Per-client hyper-parameters from its declared capabilities (src/shared/training.py:455-501): host logic only.
-    Note the kernels take batches of at most 32 samples; a 'high' power client's batch of 64/128 must be split by the caller."""
+    The kernels take batches of at most ``MAX_BATCH`` = 32 samples (flb.h), so the upstream values 64 / 128 for 'high'
+    power or large clients are clamped to 32 here (logged): a config this function returns is always trainable."""
     power = client_capabilities.get("compute_power", "medium")
     bandwidth = client_capabilities.get("network_bandwidth", 10)
     samples = client_capabilities.get("available_samples", 1000)
@@ -648,6 +666,9 @@ def create_adaptive_config(client_capabilities: Dict[str, Any]) -> FederatedTrai
         batch = min(batch * 2, 128)
     if bandwidth < 5:                       # slow uplink: more local work per round
         epochs = max(epochs + 2, 7)
+    if batch > MAX_BATCH:
+        logger.info(f"create_adaptive_config: batch size {batch} clamped to {MAX_BATCH} (kernel limit)")
+        batch = MAX_BATCH
     return FederatedTrainingConfig(local_epochs=epochs, batch_size=batch, learning_rate=lr, optimizer_type="adam",
                                    early_stopping_patience=None, save_checkpoints=True, validation_split=0.1)
 

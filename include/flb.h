@@ -122,6 +122,9 @@ typedef struct flb_train_args {
     float* bn_running;            /* cifar10_cnn: client-local BatchNorm buffers [K, flb_train_bn_floats()] =
                                      running_mean of bn1..bn6 then running_var of bn1..bn6 (never federated,
                                      models_pytorch.py:25-27); NULL for simple_cnn                            */
+    unsigned long long* epoch_nonce; /* [1] device counter, +1 by every flb_train_begin_epoch and never reset: folded into
+                                     the Philox key of dropout masks and per-sample-DP noise so that no epoch / round /
+                                     train_local_model call ever re-draws an earlier one's randomness (NULL: 0)        */
     long long ld;
     unsigned long long seed;      /* Philox seed for dropout and per-sample-DP noise                 */
     unsigned long long client_base; /* global index of local client 0 (Philox stream = client_base + k*client_stride) */
@@ -129,7 +132,8 @@ typedef struct flb_train_args {
     double lr, beta1, beta2, eps, weight_decay, momentum;   /* torch.optim defaults are Python doubles */
     int model;                    /* 0 = simple_cnn, 1 = cifar10_cnn (models_pytorch.py:59-97, :100-165) */
     int K;                        /* resident clients                                                */
-    int B;                        /* batch size (<= 32)                                              */
+    int B;                        /* batch size, 1..32: the kernels map one batch to one 32-column MMA operand / one
+                                     warp of per-sample lanes; larger loader batches are rejected by the host layer  */
     int precision;                /* 0 = fp32 CUDA-core kernels, 1 = TF32 tcgen05 tensor-core kernels */
     int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
     int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise         */
@@ -150,6 +154,10 @@ long long flb_train_ws_offset(int model, int K, int B, const char* name);
 int flb_train_begin_epoch(const flb_train_args* a, void* stream);
 /* one minibatch step for all K clients; clients that have run out of samples are skipped */
 int flb_train_step(const flb_train_args* a, void* stream);
+/* same step, and grads_out[k*ld_out + p] (p < P) receives the minibatch gradient the optimizer applied (what
+ * LocalTrainer.get_model_gradients returns upstream, training.py:362-371: param.grad after the last step); in dp_mode 1
+ * it is the sum of the clipped per-sample gradients before noise and 1/B. */
+int flb_train_step_grads(const flb_train_args* a, float* grads_out, long long ld_out, void* stream);
 /* kernels launched by one flb_train_step with these args (for launch accounting under CUDA-graph replay) */
 int flb_train_step_launches(const flb_train_args* a);
 /* profiling aid: one step with a CUDA event after every kernel; synchronises.  names_out: newline-separated labels,

@@ -1,0 +1,309 @@
+"""GPU: round-2 behaviour fixes -- fresh randomness every epoch / round, validation that leaves the optimizer alone,
+last-minibatch gradients, FedAvg shape checks, the aggregator / privacy engine called from several host threads
+(upstream calls them from a daemon thread, grpc_server.py:214,468), the DataLoaderInterface loader, and the sharded
+round on two GPUs against the same round on one."""
+import os
+import socket
+import threading
+from datetime import datetime
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fedavg as OF
+from oracle import models as OM
+from oracle import round as OR
+from oracle import training as OT
+
+pytestmark = pytest.mark.gpu
+MODEL = "simple_cnn"
+
+
+def _data(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn((n, 1, 28, 28), generator=g), torch.randint(0, 10, (n,), generator=g)
+
+
+def test_epochs_never_reuse_dropout_masks_or_dp_noise(cuda_device):
+    """the Philox key of masks and per-sample noise advances with a never-reset epoch counter, so a
+    second train_local_model / round from the same state draws different randomness (and a fixed seed replays exactly)."""
+    from flb200.training import BatchedClientTrainer
+    x, y = _data(3, 32)
+    w = OM.init_weights(MODEL, 4)
+
+    def masks(eng):
+        eng.forward_backward()
+        return eng.ws_array("h", torch.float32, 128)[0].clone() != 0
+
+    eng = BatchedClientTrainer(MODEL, 1, cuda_device, 32, 0.25, "fp32", seed=11)
+    eng.set_client_weights(0, w)
+    eng.load_data([x], [y])
+    m1, m2 = masks(eng), masks(eng)
+    assert (m1 != m2).float().mean() > 0.05                      # fresh mask in the next epoch
+    eng_b = BatchedClientTrainer(MODEL, 1, cuda_device, 32, 0.25, "fp32", seed=11)
+    eng_b.set_client_weights(0, w)
+    eng_b.load_data([x], [y])
+    assert torch.equal(masks(eng_b), m1)                         # same seed, same epoch index: reproducible
+    eng_c = BatchedClientTrainer(MODEL, 1, cuda_device, 32, 0.25, "fp32")          # default seed: fresh entropy
+    eng_d = BatchedClientTrainer(MODEL, 1, cuda_device, 32, 0.25, "fp32")
+    assert eng_c.seed != eng_d.seed
+
+    # per-sample DP noise: two consecutive calls from identical weights (tcount is reset by both) must not repeat z
+    eng = BatchedClientTrainer(MODEL, 1, cuda_device, 32, 0.0, "fp32", seed=5)
+    eng.configure_dp("per_sample", 1e-12, 2.0)                   # gradients clipped to ~0: the step is lr * sigma * z / B
+    eng.load_data([x], [y])
+    zs = []
+    for _ in range(2):
+        eng.set_client_weights(0, w)
+        w0 = eng.W[0, :eng.layout.P].clone()
+        eng.train(1, 1.0, "sgd")
+        zs.append((w0 - eng.W[0, :eng.layout.P]) * 32 / 2.0)
+    assert abs(zs[0].std().item() - 1) < 1e-2 and abs(zs[1].std().item() - 1) < 1e-2
+    corr = float((zs[0] * zs[1]).mean())
+    assert abs(corr) < 1e-2, corr                                # independent draws (identical draws would give 1.0)
+
+
+def test_update_level_noise_differs_between_engines_and_rounds(cuda_device):
+    from flb200.privacy import create_privacy_engine
+    g = {"a": torch.zeros(4096, device=cuda_device), "b": torch.zeros(33, 7, device=cuda_device)}
+    g["a"][0] = 3.0                                              # norm 3 > C = 1: sensitivity = 1
+    e1, e2 = create_privacy_engine(epsilon=5.0), create_privacy_engine(epsilon=5.0)
+    n1, n2 = e1.add_noise(g, 1.0, 1e-5), e2.add_noise(g, 1.0, 1e-5)
+    assert not torch.equal(n1["a"], n2["a"])                     # two engines never share a stream
+    n1b = e1.add_noise(g, 1.0, 1e-5)
+    assert not torch.equal(n1["a"], n1b["a"])                    # nor do two calls of one engine
+    e3, e4 = create_privacy_engine(epsilon=5.0, seed=9), create_privacy_engine(epsilon=5.0, seed=9)
+    assert torch.equal(e3.add_noise(g, 1.0, 1e-5)["a"], e4.add_noise(g, 1.0, 1e-5)["a"])       # explicit seed: reproducible tests
+
+
+def test_validation_loader_leaves_optimizer_state_alone(cuda_device):
+    """_validate_epoch between two epochs must not advance Adam's step count (bias correction)."""
+    from flb200.models_pytorch import ModelFactory
+    from flb200.training import LocalTrainer
+    x, y = _data(22, 40)
+    xv, yv = _data(23, 24)
+    batches = OT.make_batches(x, y, 8)
+    val = OT.make_batches(xv, yv, 8)                            # same batch size as training, like the reference client
+    out = []
+    for vl in (None, val):
+        model = ModelFactory.create_model(MODEL, dropout_rate=0.0)
+        model.set_model_weights(OM.init_weights(MODEL, 12))
+        tr = LocalTrainer(model, cuda_device)
+        m = tr.train_local_model(batches, 3, learning_rate=1e-3, optimizer_type="adam", validation_loader=vl, save_checkpoints=False)
+        out.append(({k: v.cpu() for k, v in model.get_model_weights().items()}, m))
+    w = {a: b.clone() for a, b in OM.init_weights(MODEL, 12).items()}
+    OT.train_local_model(MODEL, w, batches, 3, 1e-3, "adam")
+    for name in w:
+        torch.testing.assert_close(out[1][0][name], out[0][0][name], rtol=0, atol=2e-5)       # with == without validation
+        assert float((out[1][0][name] - w[name]).abs().max()) <= 2e-3
+    assert abs(out[1][1].loss - out[0][1].loss) < 1e-5
+
+
+def test_get_model_gradients_is_the_last_minibatch_gradient(cuda_device):
+    """training.py:362-371: param.grad after the last optimizer step = gradient of the last batch at the weights BEFORE it."""
+    from flb200.models_pytorch import ModelFactory
+    from flb200.training import LocalTrainer
+    x, y = _data(31, 40)
+    batches = OT.make_batches(x, y, 8)
+    for precision, rtol in (("fp32", 2e-3), ("tf32", 5e-2)):
+        model = ModelFactory.create_model(MODEL, dropout_rate=0.0)
+        w0 = OM.init_weights(MODEL, 6)
+        model.set_model_weights(w0)
+        tr = LocalTrainer(model, cuda_device, precision=precision)
+        tr.train_local_model(batches, 1, learning_rate=1e-2, optimizer_type="sgd", save_checkpoints=False)
+        w = {a: b.clone() for a, b in w0.items()}
+        OT.train_local_model(MODEL, w, batches[:-1], 1, 1e-2, "sgd")
+        _, _, ref = OT.loss_and_grads(MODEL, w, batches[-1][0], batches[-1][1], train=True, dropout_rate=0.0)
+        got = tr.get_model_gradients()
+        assert set(got) == set(ref)
+        for name, g in ref.items():
+            err = float((got[name].cpu() - g).norm() / g.norm())
+            assert err < rtol, (precision, name, err)
+
+
+def _update(cid, w, n):
+    from flb200.models import ModelUpdate
+    return ModelUpdate(client_id=cid, round_number=1, model_weights=w, num_samples=n, training_loss=0.5,
+                       privacy_budget_used=0.1, compression_ratio=0.8, timestamp=datetime.now())
+
+
+def test_fedavg_rejects_mismatched_shapes_before_touching_memory(cuda_device):
+    """with validate_updates=False (or through the pop-while-enumerating filter quirk) a malformed
+    update must raise FedAvgError, not be read out of bounds by the pointer-table kernel."""
+    from flb200.fedavg import FedAvgAggregator, FedAvgError
+    good = {"w": torch.ones(64, 32, device=cuda_device), "b": torch.ones(64, device=cuda_device)}
+    bad = {"w": torch.ones(8, 32, device=cuda_device), "b": torch.ones(64, device=cuda_device)}
+    missing = {"w": torch.ones(64, 32, device=cuda_device)}
+    agg = FedAvgAggregator(min_clients=2, validate_updates=False)
+    with pytest.raises(FedAvgError, match="layer w has shape"):
+        agg.aggregate_updates([_update("a", good, 10), _update("b", bad, 10)])
+    with pytest.raises(FedAvgError, match="no tensor for layer b"):
+        agg.aggregate_updates([_update("a", good, 10), _update("b", missing, 10)])
+    out = agg.aggregate_updates([_update("a", good, 10), _update("b", {k: 3 * v for k, v in good.items()}, 30)])
+    assert torch.allclose(out.model_weights["w"], torch.full((64, 32), 2.5, device=cuda_device))
+    # host-resident updates take the staging path: same check
+    with pytest.raises(FedAvgError, match="layer w has shape"):
+        agg.aggregate_updates([_update("a", {k: v.cpu() for k, v in good.items()}, 10), _update("b", {k: v.cpu() for k, v in bad.items()}, 10)])
+
+
+def test_aggregator_and_privacy_engine_from_concurrent_host_threads(cuda_device):
+    """grpc_server.py:214,468 / round_manager.py:560,572 call the aggregator from a daemon thread: four threads aggregate
+    different update sets (and add DP noise) at once; every result must equal the oracle's for ITS inputs."""
+    from flb200.fedavg import FedAvgAggregator
+    from flb200.privacy import create_privacy_engine
+    spec = OM.model_spec(MODEL)
+    names = list(spec)
+    errs, results = [], {}
+
+    def work(t):
+        try:
+            torch.cuda.set_device(cuda_device)
+            g = torch.Generator().manual_seed(100 + t)
+            K = 3 + t
+            ws = [{k: torch.randn(spec[k], generator=g) * 0.05 for k in names} for _ in range(K)]
+            ns = [50 + 7 * i + t for i in range(K)]
+            agg = FedAvgAggregator(min_clients=2, validate_updates=(t % 2 == 0))
+            for rep in range(6):
+                ups = [_update(f"c{i}", {k: v.to(cuda_device) for k, v in w.items()} if (rep + t) % 2 else w, n)
+                       for i, (w, n) in enumerate(zip(ws, ns))]
+                gm = agg.aggregate_updates(ups)
+                flat = np.stack([OR.flatten(w, names) for w in ws])
+                ref, _, _, _ = OF.aggregate(flat, ns, [0.5] * K, min_clients=2)
+                got = np.concatenate([gm.model_weights[k].detach().cpu().reshape(-1).numpy() for k in names])
+                assert np.array_equal(got, ref), f"thread {t} rep {rep}"
+                eng = create_privacy_engine(epsilon=1.0, seed=t)
+                noisy = eng.add_noise({k: v.to(cuda_device) for k, v in ws[0].items()}, 1.0, 1e-5)
+                assert all(torch.isfinite(v).all() for v in noisy.values())
+            results[t] = True
+        except Exception as e:            # surfaced below: an assertion in a thread does not fail the test on its own
+            errs.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,), daemon=True) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errs, errs
+    assert sorted(results) == [0, 1, 2, 3]
+
+
+def test_batched_trainer_from_a_second_host_thread(cuda_device):
+    """The tensor-core launch path keeps thread-local state (side-lane streams, per-thread function attributes): a step
+    sequence issued from a worker thread must give the main thread's result."""
+    from flb200.training import BatchedClientTrainer
+    x, y = _data(41, 48)
+    w = OM.init_weights(MODEL, 9)
+
+    def run(out, key):
+        torch.cuda.set_device(cuda_device)
+        eng = BatchedClientTrainer(MODEL, 2, cuda_device, 16, 0.0, "tf32", seed=3)
+        for k in range(2):
+            eng.set_client_weights(k, w)
+        eng.load_data([x, x[:20]], [y, y[:20]])
+        eng.train(2, 1e-2, "sgd")
+        torch.cuda.synchronize(cuda_device)
+        out[key] = eng.W.clone()
+
+    out = {}
+    run(out, "main")
+    th = threading.Thread(target=run, args=(out, "worker"))
+    th.start()
+    th.join(timeout=300)
+    assert "worker" in out
+    # fp32 atomics reorder sums between runs: same tolerance as two runs on one thread
+    torch.testing.assert_close(out["worker"], out["main"], rtol=0, atol=5e-5)
+
+
+def test_device_shard_loader_contract(cuda_device):
+    """DataLoaderInterface (interfaces.py:123-139) over raw uint8 arrays: disjoint train / validation splits, normalised
+    batches identical to ToTensor + Normalize, and LocalTrainer consumes the loader as is."""
+    from flb200.data_loader import MNIST_MEAN_STD, DeviceShardLoader
+    from flb200.models_pytorch import ModelFactory
+    from flb200.training import LocalTrainer
+    rng = np.random.default_rng(0)
+    images = rng.integers(0, 256, (400, 28, 28), dtype=np.uint8)
+    labels = rng.integers(0, 10, 400)
+    ld = DeviceShardLoader(images, labels, *MNIST_MEAN_STD, num_clients=4, partition_strategy="iid", batch_size=16,
+                           validation_split=0.1, device=cuda_device, test_images=images[:50], test_labels=labels[:50])
+    train, val = ld.load_training_data("client-2"), ld.load_validation_data("client-2")
+    assert len(train.dataset) == 90 and len(val.dataset) == 10 and len(train) == 6
+    tr_idx, va_idx = ld._split(2)
+    assert not set(tr_idx) & set(va_idx) and sorted(tr_idx + va_idx) == sorted(ld.partitioner.client_indices[2])
+    xb, yb = next(iter(val))
+    ref = ((torch.from_numpy(images[va_idx]).float() / 255) - 0.1307) / 0.3081
+    torch.testing.assert_close(xb.cpu()[:, 0], ref, rtol=0, atol=0)
+    assert yb.cpu().tolist() == labels[va_idx].tolist()
+    stats = ld.get_data_statistics("2")
+    assert stats["total_samples"] == 100 and sum(stats["class_distribution"].values()) == 100
+    assert len(ld.load_validation_data().dataset) == 50
+    model = ModelFactory.create_model(MODEL)
+    m = LocalTrainer(model, cuda_device).train_local_model(train, 1, save_checkpoints=False, validation_loader=val)
+    assert m.samples_processed == 90 and np.isfinite(m.loss)
+
+
+# ---- two GPUs ----------------------------------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _round_on(device, rank, world, pg, K, sizes, precision, compression):
+    from flb200.simulation import FederatedRoundEngine
+    eng = FederatedRoundEngine(MODEL, K, device, rank=rank, world_size=world, process_group=pg, batch_size=16, learning_rate=1e-2,
+                               optimizer_type="sgd", dp_mode="update", epsilon=50.0, dropout_rate=0.25, precision=precision,
+                               compression=compression, seed=1234)
+    eng.set_global_weights(OM.init_weights(MODEL, 2))
+    data = [OR.synthetic_client_data(MODEL, c, n=sizes[c]) for c in eng.client_ids]
+    eng.load_data([d[0] for d in data], [d[1] for d in data], sizes)
+    outs = []
+    for _ in range(2):                      # two rounds: round-dependent Philox streams and the broadcast-by-all-reduce
+        eng.run_round()
+        outs.append(eng.global_row[:eng.layout.P].clone().cpu())
+    return outs
+
+
+def _two_gpu_worker(rank, world, port, K, sizes, precision, compression, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    outs = _round_on(dev, rank, world, dist.group.WORLD, K, sizes, precision, compression)
+    q.put((rank, [o.numpy() for o in outs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision,compression", [("fp32", None), ("tf32", "q8")])
+def test_two_gpu_round_equals_one_gpu_round(cuda_device, precision, compression):
+    """client i -> rank i mod G, Philox streams (dropout masks, DP noise) keyed by the GLOBAL client
+    index, partial sums with globally normalised weights + one all-reduce.  The aggregate after two rounds on 2 GPUs must
+    equal the 1-GPU aggregate up to fp32 re-association (Philox-generated noise and masks included, not injected)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    K, sizes = 5, [48, 33, 64, 40, 17]
+    one = _round_on(cuda_device, 0, 1, None, K, sizes, precision, compression)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, K, sizes, precision, compression, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(2):                      # every rank holds the same aggregate (the all-reduce is next round's broadcast)
+        for a, b in zip(res[0], res[r]):
+            assert np.array_equal(a, b)
+    w0 = OR.flatten(OM.init_weights(MODEL, 2), list(OM.model_spec(MODEL)))
+    for rnd in range(2):
+        upd1 = one[rnd].numpy() - w0
+        upd2 = res[0][rnd] - w0
+        rel = float(np.linalg.norm(upd2 - upd1) / np.linalg.norm(upd1))
+        # fp32: summation order of the aggregate only; tf32 + q8: plus near-tie flips of the uint8 rounding
+        assert rel < (1e-4 if precision == "fp32" else 2e-2), (rnd, rel)
