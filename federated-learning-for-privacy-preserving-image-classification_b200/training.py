@@ -422,7 +422,10 @@ def _collect_loader(loader: Iterable, max_batch: int = MAX_BATCH) -> Tuple[torch
     if any(s != bs for s in sizes[:-1]) or sizes[-1] > bs:
         raise ValueError(f"batches must share one size except a smaller last one, got sizes {sorted(set(sizes))}")
     if bs > max_batch:
-        raise ValueError(f"batch size {bs} > {max_batch} is not supported by the batched kernels")
+        # The kernels map one minibatch to one 32-column MMA operand.  A larger loader batch is trained as consecutive
+        # minibatches of 32 (same samples, same order, more optimizer steps) rather than refused.
+        logger.warning(f"loader batch size {bs} exceeds the kernel limit {max_batch}: training in minibatches of {max_batch}")
+        bs = max_batch
     return torch.cat(xs), torch.cat(ys), bs
 
 
@@ -654,8 +657,8 @@ class FederatedTrainingConfig:
 
 def create_adaptive_config(client_capabilities: Dict[str, Any]) -> FederatedTrainingConfig:
     """Per-client hyper-parameters from its declared capabilities (src/shared/training.py:455-501): host logic only.
-    The kernels take batches of at most ``MAX_BATCH`` = 32 samples (flb.h), so the upstream values 64 / 128 for 'high'
-    power or large clients are clamped to 32 here (logged): a config this function returns is always trainable."""
+    The table is upstream's, including the batch sizes 64 / 128 for 'high' power or large clients; ``LocalTrainer`` trains such a
+    loader in minibatches of ``MAX_BATCH`` = 32 (the kernel limit, flb.h) and logs that it does."""
     power = client_capabilities.get("compute_power", "medium")
     bandwidth = client_capabilities.get("network_bandwidth", 10)
     samples = client_capabilities.get("available_samples", 1000)
@@ -666,9 +669,6 @@ def create_adaptive_config(client_capabilities: Dict[str, Any]) -> FederatedTrai
         batch = min(batch * 2, 128)
     if bandwidth < 5:                       # slow uplink: more local work per round
         epochs = max(epochs + 2, 7)
-    if batch > MAX_BATCH:
-        logger.info(f"create_adaptive_config: batch size {batch} clamped to {MAX_BATCH} (kernel limit)")
-        batch = MAX_BATCH
     return FederatedTrainingConfig(local_epochs=epochs, batch_size=batch, learning_rate=lr, optimizer_type="adam",
                                    early_stopping_patience=None, save_checkpoints=True, validation_split=0.1)
 
