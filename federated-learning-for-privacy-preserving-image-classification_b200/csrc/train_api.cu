@@ -3,6 +3,7 @@
 // train_simplecnn.cu (model 0) and train_cifar.cu (model 1).
 #include "train_common.cuh"
 #include "philox.cuh"
+#include "opt_update.cuh"
 #include <string.h>
 
 StepProfile g_prof;
@@ -30,39 +31,6 @@ __global__ void __launch_bounds__(256) tc_repack_kernel(flb_train_args a, TcConv
     }
 }
 
-// Scalars of one optimizer step of one client: formed in double and rounded to fp32 once, like Python floats entering
-// fp32 tensor ops.
-struct OptScalars {
-    float step_size, inv_bc2_sqrt, lr, omb1, b2, omb2, eps, decay, mu, inv_b, sigma;
-    int t;
-};
-
-__device__ __forceinline__ float sqrt_fast(float x) {        // <= 1 ulp, exact 0 -> 0 (v can be exactly zero)
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// One element.  OPT: 0 Adam, 1 SGD(momentum), 2 AdamW.  DP: g is the sum of clipped per-sample gradients, z a standard normal.
-template <int OPT, bool DP>
-__device__ __forceinline__ void opt_update(const OptScalars& c, float g, float z, float& w, float& m, float& v) {
-    if (DP) g = (g + c.sigma * z) * c.inv_b;                // (sum clipped + N(0, sigma^2)) / B
-    if (OPT == 1) {                                         // SGD with momentum, dampening 0
-        const float buf = c.t == 1 ? g : fmaf(c.mu, m, g);
-        m = buf;
-        w = w - c.lr * buf;
-    } else {
-        if (OPT == 2) w = w * c.decay;                      // AdamW decoupled decay
-        m = m + (g - m) * c.omb1;                           // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * c.b2 + c.omb2 * g * g;                      // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
-        // denom = sqrt(v) / sqrt(1 - b2^t) + eps; param.addcdiv_(m, denom, -step_size).  Square root and division use
-        // the hardware approximations (<= 2 ulp): Adam trajectories are compared at +-lr granularity anyway
-        // (conftest.adam_trajectory_check) and the IEEE forms made this kernel instruction-bound (ncu).
-        const float denom = fmaf(sqrt_fast(v), c.inv_bc2_sqrt, c.eps);
-        w = w - c.step_size * __fdividef(m, denom);
-    }
-}
-
 // grid (blocks, K).  One specialisation per (optimizer, DP mode, tensor-core weight table) so that the loop body is
 // straight-line code; the quad of the NEXT iteration is loaded before the current one is processed (the kernel is a
 // single wave of ~7 iterations per thread: without the prefetch every iteration exposes a full DRAM round trip -- ncu
@@ -81,9 +49,13 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
         float* __restrict__ V = a.V + (long long)k * a.ld;
         const float* __restrict__ zrow = (DP && a.dp_z) ? a.dp_z + (long long)k * a.ld : nullptr;
         const int t = a.tcount[k] + 1;
+        // quads [skip_lo/4, skip_hi/4) were already updated by a weight-gradient GEMM epilogue (TcConvTab): the loop runs
+        // over the remaining nq_eff quads, e4 -> c4 maps around the hole
         const int nq = P >> 2, stride = gridDim.x * 256;
+        const int skip_q0 = tab.skip_lo >> 2, skip_n = (tab.skip_hi - tab.skip_lo) >> 2, nq_eff = nq - skip_n;
         const bool need_m = OPT != 1 || t > 1;
-        int c4 = blockIdx.x * 256 + tid;
+        int e4 = blockIdx.x * 256 + tid;
+        int c4 = e4 < skip_q0 ? e4 : e4 + skip_n;
         float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = g4, m4 = g4, v4 = g4, z4 = g4;
         auto load = [&](int c, float4& g, float4& w, float4& m, float4& v, float4& z) {
             g = reinterpret_cast<const float4*>(G)[c];
@@ -92,23 +64,10 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
             if (OPT != 1) v = reinterpret_cast<const float4*>(V)[c];
             if (DP && zrow) z = reinterpret_cast<const float4*>(zrow)[c];
         };
-        bool have = c4 < nq;
+        bool have = e4 < nq_eff;
         if (have) load(c4, g4, w4, m4, v4, z4);             // in flight while thread 0 forms the scalars (pow in double)
         if (tid == 0) {
-            OptScalars c;
-            // beta^t by binary exponentiation (<= 2 log2 t dependent double multiplies; libm pow() is hundreds of
-            // instructions on one thread while the CTA waits at the barrier below)
-            double p1 = 1.0, p2 = 1.0, q1 = a.beta1, q2 = a.beta2;
-            for (int e = t; e > 0; e >>= 1) {
-                if (e & 1) { p1 *= q1; p2 *= q2; }
-                q1 *= q1; q2 *= q2;
-            }
-            const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
-            c.step_size = (float)(a.lr / bc1);
-            c.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-            c.lr = (float)a.lr; c.omb1 = (float)(1.0 - a.beta1); c.b2 = (float)a.beta2; c.omb2 = (float)(1.0 - a.beta2);
-            c.eps = (float)a.eps; c.decay = (float)(1.0 - a.lr * a.weight_decay); c.mu = (float)a.momentum;
-            c.inv_b = 1.f / (float)bsz; c.sigma = a.dp_sigma; c.t = t;
+            const OptScalars c = opt_scalars(a, t, bsz);
             s_c = c;
         }
         __syncthreads();
@@ -122,8 +81,9 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
                 tab_hi = max(tab_hi, tab.woff[i] + tab.cout[i] * tab.cin[i] * 9);
             }
         while (have) {
-            const int nxt = c4 + stride;
-            const bool have_n = nxt < nq;
+            const int e_nxt = e4 + stride;
+            const int nxt = e_nxt < skip_q0 ? e_nxt : e_nxt + skip_n;
+            const bool have_n = e_nxt < nq_eff;
             float4 gn = make_float4(0.f, 0.f, 0.f, 0.f), wn = gn, mn = gn, vn = gn, zn = gn;
             if (have_n) load(nxt, gn, wn, mn, vn, zn);
             const int p0 = c4 * 4;
@@ -154,7 +114,7 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
                 for (int e = 0; e < 4; ++e)
                     if (q[e] >= 0) wt[q[e]] = w[e];
             }
-            c4 = nxt; have = have_n;
+            c4 = nxt; e4 = e_nxt; have = have_n;
             g4 = gn; w4 = wn; m4 = mn; v4 = vn; z4 = zn;
         }
         if (blockIdx.x == 0 && tid == 0) {                 // the P % 4 parameters after the last whole quad
@@ -201,7 +161,7 @@ __global__ void __launch_bounds__(256, 4) optimizer_kernel(flb_train_args a, int
 template <int OPT, bool DP, bool TAB>
 void launch_optimizer_k(const flb_train_args& a, int P, const TcConvTab& tab, cudaStream_t st) {
     static const int resident = flb_resident_ctas(optimizer_kernel<OPT, DP, TAB>, 256);
-    const int blocks = max(1, min(flb_cdiv(P / 4, 256), resident / a.K));
+    const int blocks = max(1, min(flb_cdiv((P - (tab.skip_hi - tab.skip_lo)) / 4, 256), resident / a.K));
     optimizer_kernel<OPT, DP, TAB><<<dim3(blocks, a.K), 256, 0, st>>>(a, P, tab);
 }
 template <int OPT, bool DP>
@@ -256,9 +216,9 @@ int check_args(const flb_train_args* a) {
 
 int num_params(const flb_train_args& a) { return a.model == 0 ? simplecnn::num_params() : cifar::num_params(); }
 
-TcConvTab tab_of(const flb_train_args& a) {
+TcConvTab tab_of(const flb_train_args& a, bool step = false) {
     TcConvTab t;
-    if (a.model == 0) simplecnn::tc_tab(a, &t); else cifar::tc_tab(a, &t);
+    if (a.model == 0) simplecnn::tc_tab(a, &t, step); else cifar::tc_tab(a, &t);
     return t;
 }
 int repack_blocks(const flb_train_args& a, const TcConvTab& t) {
@@ -302,8 +262,8 @@ extern "C" int flb_train_advance(const flb_train_args* a, void* stream) {
     return FLB_OK;
 }
 
-static int fwd_bwd(const flb_train_args& a, cudaStream_t st, bool zero_first) {
-    return a.model == 0 ? simplecnn::forward_backward(a, st, zero_first) : cifar::forward_backward(a, st);
+static int fwd_bwd(const flb_train_args& a, cudaStream_t st, bool zero_first, bool step = false) {
+    return a.model == 0 ? simplecnn::forward_backward(a, st, zero_first, step) : cifar::forward_backward(a, st);
 }
 
 extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {
@@ -318,9 +278,9 @@ extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream)
 extern "C" int flb_train_step(const flb_train_args* a, void* stream) {
     if (int rc = check_args(a)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = fwd_bwd(*a, st, false)) return rc;      // accumulators are zero: begin_epoch + the optimizer keep them so
+    if (int rc = fwd_bwd(*a, st, false, true)) return rc;      // accumulators are zero: begin_epoch + the optimizer keep them so
     const int P = num_params(*a);
-    launch_optimizer(*a, P, tab_of(*a), st);
+    launch_optimizer(*a, P, tab_of(*a, true), st);
     MARK("optimizer");
     FLB_LAUNCH_CHECK();
     return FLB_OK;

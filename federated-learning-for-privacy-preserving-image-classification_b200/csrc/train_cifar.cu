@@ -24,7 +24,7 @@ int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, floa
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
-int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st, bool adam = false);
 }  // namespace tc
 
 namespace {
@@ -901,6 +901,15 @@ __global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, Ci
 }
 
 // ---- orchestration ------------------------------------------------------------------------------------------------------
+// Which GEMM runs on the tensor cores (precision 1): args.tc_mask selects single kernels for the per-layer parity tests
+// (0 = all).  Bit 3*(layer-1) + kind for conv layers 1..5 (conv2..conv6; conv1 is a direct stencil on both paths),
+// bits 15..17 fc1, 18..20 fc2; kind 0 = forward, 1 = dgrad, 2 = wgrad.
+enum : int { TC_FWD = 0, TC_DGRAD = 1, TC_WGRAD = 2, TC_FC1_BIT = 15, TC_FC2_BIT = 18 };
+__host__ inline bool cifar_tc(const flb_train_args& a, int bit) {
+    if (a.precision != 1) return false;
+    return a.tc_mask == 0 || ((a.tc_mask >> bit) & 1);
+}
+__host__ inline bool cifar_tc_conv(const flb_train_args& a, int layer, int kind) { return layer > 0 && cifar_tc(a, 3 * (layer - 1) + kind); }
 template <int C>
 void bn_stats(const flb_train_args& a, const ConvGeom& g, const float* z, double* acc, int coff, cudaStream_t st) {
     static const int resident = flb_resident_ctas(bn_reduce_kernel<C, 0>, 256);
@@ -913,7 +922,7 @@ void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, float* d
     static const int resident_r = flb_resident_ctas(bn_reduce_kernel<C, 1>, 256), resident_a = flb_resident_ctas(bn_bwd_apply_kernel<C>, 256);
     const int chunks = max(1, min(64, resident_r / a.K)), chunks_a = max(1, min(64, resident_a / a.K));
     bn_reduce_kernel<C, 1><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
-    const int conv_boff = (a.precision == 1 && layer > 0) ? kNet.cb[layer] : -1;
+    const int conv_boff = cifar_tc_conv(a, layer, TC_WGRAD) ? kNet.cb[layer] : -1;      // else: an extra column of the fp32 wgrad GEMM
     bn_bwd_apply_kernel<C><<<dim3(chunks_a, a.K), 256, 0, st>>>(a, g, z, 1, dy, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
 // pooled layers (2, 4, 6): straight from the pooled-side gradient
@@ -923,7 +932,7 @@ void bn_pool_bwd(const flb_train_args& a, const ConvGeom& g, const ConvGeom& go,
     const dim3 per_sample(a.B, a.K);
     if constexpr (FLAT) bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
     else bn_pool_bwd_reduce_vec_kernel<C><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
-    const int conv_boff = a.precision == 1 ? kNet.cb[layer] : -1;
+    const int conv_boff = cifar_tc_conv(a, layer, TC_WGRAD) ? kNet.cb[layer] : -1;
     bn_pool_bwd_apply_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, dz, acc, kNet.coff[layer],
                                                                  kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
@@ -934,12 +943,12 @@ void bn_apply(const flb_train_args& a, const ConvGeom& g, const float* z, float*
     bn_relu_apply_kernel<C><<<dim3(chunks, a.K), 256, 0, st>>>(a, g, z, y, acc, kNet.coff[layer], kNet.bw[layer], kNet.bb[layer]);
 }
 
-struct Ctx { const flb_train_args& a; const CifarWs& ws; cudaStream_t st; int rc = FLB_OK; bool tc; bool tc_wgrad; };
+struct Ctx { const flb_train_args& a; const CifarWs& ws; cudaStream_t st; int rc = FLB_OK; };
 
 // returns true when the launch also accumulated the layer's BatchNorm statistics (sum z, sum z^2) into ws.acc
 bool conv_fwd(Ctx& c, const ConvGeom& g, const float* xin, float* z, int layer, bool want_stats) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) {
+    if (cifar_tc_conv(a, layer, TC_FWD)) {
         const bool fuse = want_stats && tc::conv_fwd_fuses_stats(g.Cin, g.Cout);
         if (int rc = tc::conv_fwd(a, g, xin, z, c.ws.wt + kNet.toff[layer], kNet.ldt, kNet.cb[layer], st,
                                   fuse ? c.ws.acc : nullptr, kNet.coff[layer], BN_CH)) c.rc = rc;
@@ -951,13 +960,13 @@ bool conv_fwd(Ctx& c, const ConvGeom& g, const float* xin, float* z, int layer, 
 }
 void conv_dgrad(Ctx& c, const ConvGeom& g, const float* dz, float* dx, int layer) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) { if (int rc = tc::conv_dgrad(a, g, dz, dx, c.ws.wt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
+    if (cifar_tc_conv(a, layer, TC_DGRAD)) { if (int rc = tc::conv_dgrad(a, g, dz, dx, c.ws.wt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
     ConvDgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.dx_all = dx; p.woff = kNet.cw[layer];
     simt::launch(p, a.B * g.PP(), g.Cin, 1, a.K, st);
 }
 void conv_wgrad(Ctx& c, const ConvGeom& g, const float* xin, const float* dz, int layer) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) { if (int rc = tc::conv_wgrad(a, g, xin, dz, c.ws.gt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
+    if (cifar_tc_conv(a, layer, TC_WGRAD)) { if (int rc = tc::conv_wgrad(a, g, xin, dz, c.ws.gt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
     ConvWgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.xin_all = xin; p.coef_all = nullptr;
     p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
     const int tiles = ((g.Cout + 63) / 64) * ((9 * g.Cin + 1 + 63) / 64);
@@ -966,19 +975,22 @@ void conv_wgrad(Ctx& c, const ConvGeom& g, const float* xin, const float* dz, in
 }
 void lin_fwd(Ctx& c, const float* act, float* out, int In, int Out, int woff, int splits) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) { if (int rc = tc::fc_fwd(a, act, out, In, Out, woff, splits, st)) c.rc = rc; return; }
+    if (cifar_tc(a, (In == 2048 ? TC_FC1_BIT : TC_FC2_BIT) + TC_FWD)) { if (int rc = tc::fc_fwd(a, act, out, In, Out, woff, splits, st)) c.rc = rc; return; }
     LinFwdProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.act_all = act; p.out_all = out;
     simt::launch(p, a.B, Out, splits, a.K, st);
 }
 void lin_dgrad(Ctx& c, const float* dout, float* dact, int In, int Out, int woff) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc) { if (int rc = tc::fc_dgrad(a, dout, dact, In, Out, woff, st)) c.rc = rc; return; }
+    if (cifar_tc(a, (In == 2048 ? TC_FC1_BIT : TC_FC2_BIT) + TC_DGRAD)) { if (int rc = tc::fc_dgrad(a, dout, dact, In, Out, woff, st)) c.rc = rc; return; }
     LinDgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.dout_all = dout; p.dact_all = dact;
     simt::launch(p, a.B, In, 1, a.K, st);
 }
 void lin_wgrad(Ctx& c, const float* dout, const float* act, int In, int Out, int woff) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
-    if (c.tc_wgrad) { if (int rc = tc::fc_wgrad(a, dout, act, In, Out, woff, st)) c.rc = rc; return; }
+    if (a.B % 8 == 0 && cifar_tc(a, (In == 2048 ? TC_FC1_BIT : TC_FC2_BIT) + TC_WGRAD)) {        // its K extent is the batch: whole 8-row MMA steps
+        if (int rc = tc::fc_wgrad(a, dout, act, In, Out, woff, st)) c.rc = rc;
+        return;
+    }
     LinWgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.boff = 0; p.dout_all = dout; p.act_all = act; p.coef_all = nullptr;
     simt::launch(p, Out, In, 1, a.K, st);
 }
@@ -995,7 +1007,7 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     FLB_CUDA(cudaMemsetAsync(ws.hpre2, 0, sizeof(float) * KB * 256, st));
     MARK("begin");
     const bool stats = !a.eval_mode;
-    Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
+    Ctx cx{a, ws, st, FLB_OK};
     static_assert(kNet.coff[0] == 0, "conv1_fwd_kernel adds its statistics at channel offset 0");
     conv1_fwd_kernel<<<per_sample, 256, 0, st>>>(a, ws.z1, stats ? ws.acc : nullptr);
     MARK("conv1_fwd");
@@ -1051,8 +1063,8 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     // gradients accumulated with atomics (conv weights / biases) start from zero; everything else is stored
     FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, kNet.f1w * sizeof(float), K, st));
     if (int rc = forward_impl(a, ws, st)) return rc;
-    Ctx cx{a, ws, st, FLB_OK, a.precision == 1, a.precision == 1 && a.B % 8 == 0};
-    if (cx.tc) FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kNet.ldt, st));
+    Ctx cx{a, ws, st, FLB_OK};
+    if (a.precision == 1) FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kNet.ldt, st));
 
     head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws);
     lin_wgrad(cx, ws.dh2, ws.h1, 512, 256, kNet.f2w);
@@ -1138,7 +1150,7 @@ void tc_tab(const flb_train_args& a, TcConvTab* t) {
     t->n = NCONV - 1;
     for (int i = 1; i < NCONV; ++i) {
         t->woff[i - 1] = kNet.cw[i]; t->cin[i - 1] = kNet.cin[i]; t->cout[i - 1] = kNet.cout[i];
-        t->toff[i - 1] = kNet.toff[i]; t->gt_live[i - 1] = 1;
+        t->toff[i - 1] = kNet.toff[i]; t->gt_live[i - 1] = cifar_tc_conv(a, i, TC_WGRAD) ? 1 : 0;
     }
     t->ldt = kNet.ldt; t->wt = ws.wt; t->gt = ws.gt;
 }

@@ -57,6 +57,7 @@ struct SimpleCnnWs {
     float* g1ps;     // [K][B][320]         per-sample conv1 weight+bias gradients (dp_mode 1)
     float* wt;       // [K][9][64][32]      conv2 weights, tap-major (tensor-core path)
     float* gt;       // [K][9][64][32]      conv2 weight gradients, tap-major
+    int* fc1_ctr;    // [K][2]              arrive / depart counters of the fused classifier kernel's client barrier (zero at rest)
 };
 
 // per-kernel CUDA-event timing of one step (flb_train_step_profiled); inactive otherwise
@@ -90,6 +91,9 @@ struct TcConvTab {
     // (Gt is cleared by a memset on the weight-gradient side lane: clearing it from the optimizer's scattered
     // tap-major accesses was measured 55 us slower.)  0 = the model's step zeroes its accumulators itself.
     int g_zero_upto = 0;
+    // Parameters [skip_lo, skip_hi) (multiples of 4) are NOT touched by the optimizer kernel in this step: the weight-gradient
+    // GEMM that produced their gradient applied the optimizer in its epilogue (SimpleCNN fc1.weight, 95 % of the model).
+    int skip_lo = 0, skip_hi = 0;
 };
 // reference-layout offset p -> tap-major offset (or -1 when p is not a tensor-core conv weight)
 __device__ __forceinline__ int tc_tab_map(const TcConvTab& t, int p, int& layer) {
@@ -110,10 +114,12 @@ int num_params();
 long long ws_bytes(int K, int B);
 long long ws_offset(int K, int B, const char* name);
 int forward(const flb_train_args& a, cudaStream_t st);
-int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first);
+// step: called from flb_train_step (an optimizer step follows): layers whose optimizer update is fused into their
+// weight-gradient epilogue are updated here and reported through TcConvTab::skip_* by tc_tab(a, t, true)
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, bool step);
 int begin_epoch_zero(const flb_train_args& a, cudaStream_t st);
 int step_launches(const flb_train_args& a);
-void tc_tab(const flb_train_args& a, TcConvTab* t);
+void tc_tab(const flb_train_args& a, TcConvTab* t, bool step = false);
 }
 namespace cifar {
 int num_params();
@@ -154,6 +160,7 @@ static inline size_t simplecnn_ws_carve(void* base, int K, int B, SimpleCnnWs* w
     CARVE(g1ps, float, KB * 320);
     CARVE(wt, float, (size_t)K * 18432);
     CARVE(gt, float, (size_t)K * 18432);
+    CARVE(fc1_ctr, int, (size_t)K * 2);
 #undef CARVE
     return off;
 }

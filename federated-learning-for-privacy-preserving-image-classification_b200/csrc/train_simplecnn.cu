@@ -31,7 +31,8 @@ int conv_fwd_pool_32_64(const flb_train_args& a, const ConvGeom& g, const float*
 int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
-int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st);
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st, bool adam = false);
+int fc1_fused(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st);
 }  // namespace tc
 
 namespace {
@@ -43,6 +44,21 @@ int tc_mask_of(const flb_train_args& a) {
     int m = a.precision == 1 ? (a.tc_mask ? a.tc_mask : 63) : 0;
     if (a.B % 8) m &= ~TC_FC1_WGRAD;        // its K extent is the batch: whole 8-row MMA steps only
     return m;
+}
+
+// fc1.weight's optimizer step applied in its weight-gradient GEMM epilogue (FcWgradT<.., ADAM>): only inside a real training
+// step (not the gradient-only entries), without per-sample clipping (which needs every layer's norm before any update)
+bool fuse_fc1_adam(const flb_train_args& a, bool step) {
+    static const bool off = getenv("FLB_NO_FUSED_ADAM") != nullptr;
+    return step && !off && a.dp_mode == 0 && (tc_mask_of(a) & TC_FC1_WGRAD);
+}
+
+// fc1 forward + classifier head + fc1 dgrad as ONE launch (fc1_fused.cu) whenever both GEMMs run on the tensor cores and a
+// backward pass follows (training step or gradient-only entry; evaluation keeps the separate forward kernels)
+bool fuse_fc1_block(const flb_train_args& a, bool backward) {
+    static const bool off = getenv("FLB_NO_FUSED_FC1") != nullptr;
+    const int m = tc_mask_of(a);
+    return backward && !off && (m & TC_FC1_FWD) && (m & TC_FC1_DGRAD);
 }
 
 using Off = SimpleCnnOff;
@@ -507,7 +523,7 @@ __global__ void clip_coef_kernel(flb_train_args a, SimpleCnnWs ws) {
 const ConvGeom kConv2{32, 64, 14, 14, 16, 16};
 constexpr int kLdt = 9 * 64 * 32;          // tap-major conv2 weights per client
 
-int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
+int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st, bool backward = false) {
     const int K = a.K, B = a.B;
     const dim3 per_sample(B, K);
     MARK("begin");          // hpre (split-K accumulator of fc1) is kept at zero by its consumer, head_fwd_bwd_kernel
@@ -523,6 +539,12 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
         MARK("conv2_fwd");
         pool2_kernel<<<dim3(7 * B, K), 112, 0, st>>>(a, ws);
         MARK("pool2");
+    }
+    if (fuse_fc1_block(a, backward)) {          // forward, head and the fc1 dgrad in one launch
+        if (int rc = tc::fc1_fused(a, ws, st)) return rc;
+        MARK("fc1_fused");
+        FLB_LAUNCH_CHECK();
+        return FLB_OK;
     }
     if (tcm & TC_FC1_FWD) {
         if (int rc = tc::fc_fwd(a, ws.a2, ws.hpre, 3136, 128, Off::f1w, 7, st)) return rc;
@@ -544,7 +566,7 @@ int zero_accumulators(const flb_train_args& a, const SimpleCnnWs&, cudaStream_t 
     return FLB_OK;
 }
 
-int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) {
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, bool step) {
     SimpleCnnWs ws;
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
     const int K = a.K, B = a.B;
@@ -552,20 +574,26 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     if (zero_first)
         if (int rc = zero_accumulators(a, ws, st)) return rc;
     if (a.dp_mode == 1) FLB_CUDA(cudaMemsetAsync(ws.norm2, 0, sizeof(float) * (size_t)K * B, st));
-    if (int rc = forward(a, ws, st)) return rc;
+    if (int rc = forward(a, ws, st, true)) return rc;
+    const bool fused_fc1 = fuse_fc1_block(a, true);
 
     // Weight gradients do not feed the activation-gradient chain: without per-sample clipping they run on a side
     // stream beside it (fork / join by events -- one graph with parallel branches when the epoch is captured).
     SideLane* lane = (a.dp_mode == 0 && !g_prof.on) ? flb_side_lane() : nullptr;
     const int tcm = tc_mask_of(a);
     const float* coef = nullptr;
+    const bool fused_adam = fuse_fc1_adam(a, step);
 
-    auto wgrads_head_fc1 = [&](cudaStream_t st) -> int {
+    auto wgrad_head = [&](cudaStream_t st) -> int {
         head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws, a.dp_mode == 1);
         MARK("head_wgrad");
+        return FLB_OK;
+    };
+    auto wgrad_fc1 = [&](cudaStream_t st) -> int {
         if (tcm & TC_FC1_WGRAD) {
             if (coef) scale_rows_kernel<<<per_sample, 256, 0, st>>>(a, ws.dh, coef, 128);
-            if (int rc = tc::fc_wgrad(a, ws.dh, ws.a2, 3136, 128, Off::f1w, st)) return rc;
+            if (int rc = tc::fc_wgrad(a, ws.dh, ws.a2, 3136, 128, Off::f1w, st, fused_adam)) return rc;
+            if (fused_adam) { MARK("fc1_wgrad_adam"); return FLB_OK; }
         } else {
             LinWgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.boff = Off::f1b;
             p.dout_all = ws.dh; p.act_all = ws.a2; p.coef_all = coef;
@@ -573,6 +601,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
         }
         MARK("fc1_wgrad");
         return FLB_OK;
+    };
+    auto wgrads_head_fc1 = [&](cudaStream_t st) -> int {
+        if (int rc = wgrad_head(st)) return rc;
+        return wgrad_fc1(st);
     };
     auto wgrads_conv2 = [&](cudaStream_t st) -> int {
         if (tcm & TC_CONV2_WGRAD) {
@@ -593,17 +625,27 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) 
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[0], st));
         FLB_CUDA(cudaStreamWaitEvent(lane->s, lane->ev[0], 0));
-        if (int rc = wgrads_head_fc1(lane->s)) return rc;
+        if (int rc = wgrad_head(lane->s)) return rc;
+        if (!fused_adam)
+            if (int rc = wgrad_fc1(lane->s)) return rc;
     }
 
     // ---- activation gradients ----
-    if (tcm & TC_FC1_DGRAD) {
+    if (fused_fc1) {
+        // da2 is already there
+    } else if (tcm & TC_FC1_DGRAD) {
         if (int rc = tc::fc_dgrad(a, ws.dh, ws.da2, 3136, 128, Off::f1w, st)) return rc;
+        MARK("fc1_dgrad");
     } else {
         LinDgradProb p{}; p.a = a; p.In = 3136; p.Out = 128; p.woff = Off::f1w; p.dout_all = ws.dh; p.dact_all = ws.da2;
         simt::launch(p, B, 3136, 1, K, st);
+        MARK("fc1_dgrad");
     }
-    MARK("fc1_dgrad");
+    if (lane && fused_adam) {                  // the fused epilogue overwrites fc1.weight: only after its last reader (the dgrad)
+        FLB_CUDA(cudaEventRecord(lane->ev[3], st));
+        FLB_CUDA(cudaStreamWaitEvent(lane->s, lane->ev[3], 0));
+        if (int rc = wgrad_fc1(lane->s)) return rc;
+    }
     const int fused_bias = ((tcm & TC_CONV2_WGRAD) && a.dp_mode == 0) ? 1 : 0;
     unpool2_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws, fused_bias);
     MARK("unpool2");
@@ -694,7 +736,7 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
     return ::forward(a, ws, st);
 }
-int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first) { return ::forward_backward(a, st, zero_first); }
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, bool step) { return ::forward_backward(a, st, zero_first, step); }
 int begin_epoch_zero(const flb_train_args& a, cudaStream_t st) {
     SimpleCnnWs ws;
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);
@@ -702,13 +744,14 @@ int begin_epoch_zero(const flb_train_args& a, cudaStream_t st) {
 }
 int step_launches(const flb_train_args& a) {
     const int m = tc_mask_of(a);
-    int n = 12 - ((m & TC_CONV2_FWD) ? 1 : 0);    // fused pool: one kernel less; conv2 bias gradient: fused into unpool2                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
+    int n = 12 - ((m & TC_CONV2_FWD) ? 1 : 0) - (fuse_fc1_block(a, true) ? 2 : 0);    // fused pool: one kernel less; conv2 bias gradient: fused into unpool2                 // + conv2_bias_grad (an extra GEMM column on the fp32 path)
     if (a.dp_mode == 1) n += 4 + ((m & TC_FC1_WGRAD) ? 1 : 0) + ((m & TC_CONV2_WGRAD) ? 3 : 0);
     return n;
 }
-void tc_tab(const flb_train_args& a, TcConvTab* t) {
+void tc_tab(const flb_train_args& a, TcConvTab* t, bool step) {
     const int m = tc_mask_of(a);
     t->g_zero_upto = Off::f1w;
+    if (fuse_fc1_adam(a, step)) { t->skip_lo = Off::f1w; t->skip_hi = Off::f1b; }
     if (!(m & (TC_CONV2_FWD | TC_CONV2_DGRAD | TC_CONV2_WGRAD))) return;
     SimpleCnnWs ws;
     simplecnn_ws_carve(a.ws, a.K, a.B, &ws);

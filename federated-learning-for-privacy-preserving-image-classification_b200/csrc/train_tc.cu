@@ -12,6 +12,7 @@
 // optimizer kernel keeps in sync with the reference-layout row, so BOTH operands of every GEMM are plain TMA boxes and
 // no CTA spends time permuting weights; conv weight gradients are accumulated in the same layout (Gt).
 #include "tc_gemm.cuh"
+#include "opt_update.cuh"
 #include <type_traits>
 #include <stdlib.h>
 
@@ -667,7 +668,12 @@ struct FcDgradT {
 };
 
 // ---- linear wgrad: D[128 out, 256 in] = sum_b dout[b, out] * act[b, in] ------------------------------------------------
-template <int IN, int OUT>
+// ADAM: the epilogue does not store the gradient tile -- it applies the optimizer step (opt_update.cuh: Adam / SGD-momentum /
+// AdamW, selected by args.opt) to W, M, V straight out of TMEM.  For SimpleCNN's fc1.weight (401 408 of the 421 642
+// parameters) this removes the gradient's HBM round trip (4 B written + 4 B read per parameter) and takes 95 % of the
+// optimizer's bytes off the step's critical path: the stand-alone optimizer kernel then skips this range (TcConvTab::skip_*).
+// The caller orders this kernel after the layer's dgrad (which still reads the old W).
+template <int IN, int OUT, bool ADAM = false>
 struct FcWgradT {
     struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
@@ -697,13 +703,56 @@ struct FcWgradT {
         for (int k = 0; k < ksteps; ++k)
             if (this->lead) mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
     }
+    template <int OPT>
+    static __device__ __forceinline__ void apply(const OptScalars& c, const float* g, float* __restrict__ W, float* __restrict__ M,
+                                                 float* __restrict__ V, bool need_m) {
+        // 16 parameters per pass: every load of the pass is in flight before the first update
+        float4 w4[4], m4[4], v4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            w4[q] = reinterpret_cast<const float4*>(W)[q];
+            m4[q] = need_m ? reinterpret_cast<const float4*>(M)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v4[q] = OPT != 1 ? reinterpret_cast<const float4*>(V)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            opt_update<OPT, false>(c, g[4 * q + 0], 0.f, w4[q].x, m4[q].x, v4[q].x);
+            opt_update<OPT, false>(c, g[4 * q + 1], 0.f, w4[q].y, m4[q].y, v4[q].y);
+            opt_update<OPT, false>(c, g[4 * q + 2], 0.f, w4[q].z, m4[q].z, v4[q].z);
+            opt_update<OPT, false>(c, g[4 * q + 3], 0.f, w4[q].w, m4[q].w, v4[q].w);
+            reinterpret_cast<float4*>(W)[q] = w4[q];
+            reinterpret_cast<float4*>(M)[q] = m4[q];
+            if (OPT != 1) reinterpret_cast<float4*>(V)[q] = v4[q];
+        }
+    }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int j = mt * 128 + quarter * 32 + lane;
-        float* g = p.a.G + (long long)client * p.a.ld + p.woff + (long long)j * IN;
+        const long long off = (long long)client * p.a.ld + p.woff + (long long)j * IN;
+        float* g = p.a.G + off;
+        OptScalars c;
+        bool need_m = true;
+        if (ADAM) {
+            const int t = p.a.tcount[client] + 1;             // the stand-alone optimizer kernel advances tcount later in the step
+            c = opt_scalars(p.a, t, flb_bsz(p.a, client));
+            need_m = p.a.opt != 1 || t > 1;
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+            if (ADAM) {
+#pragma unroll
+                for (int h = 0; h < 32; h += 16) {
+                    const int n = n0 + c0 + h;
+                    if (n < IN) {                               // IN % 16 == 0: whole 16-parameter passes
+                        float* W = p.a.W + off + n; float* M = p.a.M + off + n; float* V = p.a.V + off + n;
+                        if (p.a.opt == 0) apply<0>(c, v + h, W, M, V, need_m);
+                        else if (p.a.opt == 1) apply<1>(c, v + h, W, M, V, need_m);
+                        else apply<2>(c, v + h, W, M, V, need_m);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const int n = n0 + c0 + i;
@@ -914,14 +963,23 @@ static int fc_dgrad_t(const flb_train_args& a, const float* dout, float* dact, i
     p.a = a; p.dact_all = dact;
     return launch<T>(p, dim3((IN + 127) / 128, a.K), st);
 }
-template <int IN, int OUT>
+template <int IN, int OUT, bool ADAM>
 static int fc_wgrad_t(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
-    using T = FcWgradT<IN, OUT>;
+    static_assert(IN % 16 == 0, "the fused optimizer epilogue works in 16-parameter passes");
+    using T = FcWgradT<IN, OUT, ADAM>;
     typename T::Params p;
     if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, OUT, 32, true)) return rc;
     if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32, true)) return rc;
     p.a = a; p.woff = woff;
     return launch<T>(p, dim3((IN + 255) / 256, a.K, OUT / 128), st);
+}
+
+// tensor maps of SimpleCNN's fused classifier kernel (fc1_fused.cu): fc1.weight as K-major [128 x 32] boxes and as MN-major
+// [32 x 32] boxes, the activations a2 as [32 x 32] boxes
+int make_fc1_maps(const flb_train_args& a, const float* act, CUtensorMap* w, CUtensorMap* w_mn, CUtensorMap* m_act) {
+    if (int rc = make_w_map(w, a, SimpleCnnOff::f1w, 3136, 128, 128)) return rc;
+    if (int rc = make_w_map(w_mn, a, SimpleCnnOff::f1w, 3136, 128, 32, true)) return rc;
+    return make_map_2d(m_act, act, (uint64_t)a.K * a.B, 3136, 32);
 }
 
 #define FLB_FC_DISPATCH(FN, ...)                                                              \
@@ -937,8 +995,17 @@ int fc_fwd(const flb_train_args& a, const float* act, float* outp, int in, int o
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int out, int woff, cudaStream_t st) {
     FLB_FC_DISPATCH(fc_dgrad_t, a, dout, dact, woff, st)
 }
-int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int out, int woff, cudaStream_t st) {
-    FLB_FC_DISPATCH(fc_wgrad_t, a, dout, act, woff, st)
+int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int out, int woff, cudaStream_t st, bool adam) {
+    if (adam) {
+        if (in == 3136 && out == 128) return fc_wgrad_t<3136, 128, true>(a, dout, act, woff, st);
+        flb_set_error("tensor-core linear wgrad with the fused optimizer: unsupported shape %d -> %d", in, out);
+        return FLB_ERR_UNSUPPORTED;
+    }
+    if (in == 3136 && out == 128) return fc_wgrad_t<3136, 128, false>(a, dout, act, woff, st);
+    if (in == 2048 && out == 512) return fc_wgrad_t<2048, 512, false>(a, dout, act, woff, st);
+    if (in == 512 && out == 256) return fc_wgrad_t<512, 256, false>(a, dout, act, woff, st);
+    flb_set_error("tensor-core linear: unsupported shape %d -> %d", in, out);
+    return FLB_ERR_UNSUPPORTED;
 }
 
 }  // namespace tc

@@ -138,8 +138,9 @@ typedef struct flb_train_args {
     int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
     int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise         */
     int eval_mode;                /* 1: model.eval() semantics -- no dropout, BatchNorm uses the running statistics */
-    int tc_mask;                  /* precision 1 only: bit set = that GEMM on tensor cores (0 = all): 1 conv2 fwd,
-                                     2 fc1 fwd, 4 fc1 dgrad, 8 conv2 dgrad, 16 fc1 wgrad, 32 conv2 wgrad (test aid) */
+    int tc_mask;                  /* precision 1 only: bit set = that GEMM on tensor cores (0 = all).  simple_cnn: 1 conv2 fwd,
+                                     2 fc1 fwd, 4 fc1 dgrad, 8 conv2 dgrad, 16 fc1 wgrad, 32 conv2 wgrad.  cifar10_cnn: bit 3*(l-1)+kind for conv
+                                     layer l = 1..5 (conv2..conv6), bits 15..17 fc1, 18..20 fc2; kind 0 fwd, 1 dgrad, 2 wgrad (test aid) */
     float drop_p;                 /* dropout probability of SimpleCNN.dropout (0.25 upstream)        */
     float dp_clip;                /* per-sample max_grad_norm C                                      */
     float dp_sigma;               /* noise std of the summed clipped gradient (= C * sigma_unit)     */
