@@ -36,10 +36,12 @@ SIGNATURES = {
     "flb_fedavg_weighted_sum_q8": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_dp_sumsq": [_vp, _ll, _vp, _vp, _i, _ll, _vp],
     "flb_dp_clip_noise": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _ull, _i, _ll, _vp],
+    "flb_dp_clip_noise_absmax": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _ull, _vp, _i, _vp, _i, _ll, _vp],
     "flb_dp_add_noise": [_vp, _ll, _vp, _vp, _d, _ull, _ull, _i, _ll, _vp],
     "flb_philox_normal": [_vp, _ll, _ull, _ull, _vp],
     "flb_philox_raw": [_vp, _ll, _ull, _ull, _ull, _vp],
     "flb_q8_quantize": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _ll, _i, _i, _vp],
+    "flb_q8_quantize_absmax": [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _ll, _i, _vp],
     "flb_q8_dequantize": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _i, _ll, _vp],
     "flb_update_stats": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_delta_norms": [_vp, _vp, _vp, _vp, _i, _ll, _vp],

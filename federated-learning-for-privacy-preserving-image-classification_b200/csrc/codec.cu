@@ -83,6 +83,61 @@ q8_quantize_kernel(const float* __restrict__ x, long long ld, const long long* _
     }
 }
 
+// Same codes, 4 parameters per thread (16 B load, 4 B store) over the flat row; the layer of a quad comes from a binary
+// search in the (shared-memory) offset table, quads that straddle a layer boundary fall back to per-element lookups.
+// grid: (chunks, K)
+__global__ void __launch_bounds__(kThreads)
+q8_quantize_vec4_kernel(const float* __restrict__ x, long long ld, const long long* __restrict__ seg_off,
+                        const float* __restrict__ scale, const float* __restrict__ zp,
+                        uint8_t* __restrict__ q, long long ldq, int L, long long P, float qmax) {
+    extern __shared__ long long s_off[];
+    for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
+    __syncthreads();
+    const int k = blockIdx.y;
+    const float* __restrict__ row = x + (long long)k * ld;
+    uint8_t* __restrict__ qrow = q + (long long)k * ldq;
+    const float* __restrict__ sc = scale + (long long)k * L;
+    const float* __restrict__ zz = zp + (long long)k * L;
+    const long long P4 = (P + 3) >> 2;
+    for (long long c = (long long)blockIdx.x * kThreads + threadIdx.x; c < P4; c += (long long)gridDim.x * kThreads) {
+        const long long p = c << 2;
+        int lo = 0, hi = L;                       // largest l with s_off[l] <= p
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= p) lo = mid; else hi = mid; }
+        if (p + 3 < P && p + 3 < s_off[lo + 1]) {
+            const float s = sc[lo], z = zz[lo];
+            const float4 v4 = *reinterpret_cast<const float4*>(row + p);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            uint32_t word = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float t = __fadd_rn(__fdiv_rn(v[e], s), z);                   // compression.py:217
+                t = fminf(fmaxf(rintf(t), 0.f), qmax);                        // round-half-even, clamp (:218)
+                word |= (uint32_t)((s > 0.f) ? (uint8_t)t : (uint8_t)z) << (8 * e);
+            }
+            *reinterpret_cast<uint32_t*>(qrow + p) = word;
+        } else {
+            for (long long e = p; e < min(p + 4, P); ++e) {
+                int l = lo;
+                while (e >= s_off[l + 1]) ++l;
+                const float s = sc[l], z = zz[l];
+                float t = __fadd_rn(__fdiv_rn(row[e], s), z);
+                t = fminf(fmaxf(rintf(t), 0.f), qmax);
+                qrow[e] = (s > 0.f) ? (uint8_t)t : (uint8_t)z;
+            }
+        }
+    }
+}
+
+// symmetric scale / zero point from the bits of max|x| (flb_dp_clip_noise_absmax)
+__global__ void q8_params_absmax_kernel(const unsigned int* __restrict__ absmax_bits, float* __restrict__ scale,
+                                        float* __restrict__ zp, int n, int levels) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mx = (double)__uint_as_float(absmax_bits[i]);
+    scale[i] = (float)((2.0 * mx) / (double)(levels - 1));           // compression.py:207-210
+    zp[i] = (float)((levels - 1) / 2);
+}
+
 __global__ void __launch_bounds__(kThreads)
 q8_dequantize_kernel(const uint8_t* __restrict__ q, long long ldq, const long long* __restrict__ seg_off,
                      const float* __restrict__ scale, const float* __restrict__ zp,
@@ -105,6 +160,24 @@ int chunks_for(long long P, int L, int K) {
     return (int)(c > 1024 ? 1024 : c);
 }
 
+// the code pass: 4 parameters per thread when rows allow 16 B / 4 B accesses, else the per-layer scalar kernel
+int launch_quantize(const float* x, long long ld, const long long* seg_off, const float* scale, const float* zp, uint8_t* q,
+                    long long ldq, int K, int L, long long P, int levels, cudaStream_t st) {
+    const bool vec = (ld % 4 == 0) && (ldq % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)q % 4 == 0);
+    if (vec) {
+        static const int resident = flb_resident_ctas(q8_quantize_vec4_kernel, kThreads);
+        long long blocks = (P / 4 + kThreads - 1) / kThreads, cap = resident / K;
+        if (cap < 1) cap = 1;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        q8_quantize_vec4_kernel<<<dim3((unsigned)blocks, K), kThreads, (L + 1) * sizeof(long long), st>>>(x, ld, seg_off, scale, zp, q, ldq, L, P, (float)(levels - 1));
+    } else {
+        dim3 grid(chunks_for(P, L, K), L, K);
+        q8_quantize_kernel<<<grid, kThreads, 0, st>>>(x, ld, seg_off, scale, zp, q, ldq, L, (float)(levels - 1));
+    }
+    return FLB_OK;
+}
+
 }  // namespace
 
 extern "C" int flb_q8_quantize(const float* x, long long ld, const long long* seg_off, uint8_t* q, long long ldq,
@@ -122,7 +195,24 @@ extern "C" int flb_q8_quantize(const float* x, long long ld, const long long* se
     dim3 grid(chunks_for(P, L, K), L, K);
     q8_minmax_kernel<<<grid, kThreads, 0, st>>>(x, ld, seg_off, kmin, kmax, L, symmetric);
     q8_params_kernel<<<flb_cdiv(n, 256), 256, 0, st>>>(kmin, kmax, scale, zp, n, levels, symmetric);
-    q8_quantize_kernel<<<grid, kThreads, 0, st>>>(x, ld, seg_off, scale, zp, q, ldq, L, (float)(levels - 1));
+    if (int rc = launch_quantize(x, ld, seg_off, scale, zp, q, ldq, K, L, P, levels, st)) return rc;
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+// Symmetric quantisation whose per-(client, layer) max|x| is already known (absmax_bits from flb_dp_clip_noise_absmax):
+// one parameter kernel + the code pass -- the reduction pass over x is gone.
+extern "C" int flb_q8_quantize_absmax(const float* x, long long ld, const long long* seg_off, const unsigned int* absmax_bits,
+                                      uint8_t* q, long long ldq, float* scale, float* zp, int K, int L, long long P,
+                                      int bits, void* stream) {
+    FLB_CHECK_ARG(x && seg_off && absmax_bits && q && scale && zp, "flb_q8_quantize_absmax: null pointer");
+    FLB_CHECK_ARG(K >= 1 && K <= 65535 && L >= 1 && L <= 65535 && ld >= P && ldq >= P, "flb_q8_quantize_absmax: bad K/L/ld");
+    FLB_CHECK_ARG(bits >= 1 && bits <= 8, "flb_q8_quantize_absmax: bits must be in 1..8 (codes are stored in uint8)");
+    if (P == 0) return FLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = K * L, levels = 1 << bits;
+    q8_params_absmax_kernel<<<flb_cdiv(n, 256), 256, 0, st>>>(absmax_bits, scale, zp, n, levels);
+    if (int rc = launch_quantize(x, ld, seg_off, scale, zp, q, ldq, K, L, P, levels, st)) return rc;
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

@@ -20,6 +20,7 @@
 // resident.  Waits are bounded (trap instead of hanging the GPU).
 #include "tc_gemm.cuh"
 #include "philox.cuh"
+#include <stdlib.h>
 
 namespace tc {
 
@@ -98,6 +99,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) fc1_fused_kernel(const __grid_co
         float* hacc = p.ws.hpre + kb0 * F_OUT;       // [B, 128] accumulator, zero at rest
         int* ctr = p.ws.fc1_ctr + 2 * c;             // [0] arrivals, [1] departures, zero at rest
 
+        // Everything the head needs besides hpre is requested NOW by all threads (5 + 1 independent loads each) and parked in
+        // registers while the warps do their forward roles; it lands in shared memory just before the first barrier.
+        // (A first version let two idle warps copy fc2.weight in a loop of 20 dependent round trips: 10 us of the kernel.)
+        float w2r[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) w2r[i] = W[Off::f2w + tid + F_THREADS * i];
+        const float b2r = tid < 10 ? W[Off::f2b + tid] : 0.f;
+        const int labr = (tid < 32 && tid < bsz) ? a.y[a.sample_off[c] + (long long)(*a.step_ctr) * a.B + tid] : 0;
+
         // ---- 1. forward operands + MMAs ------------------------------------------------------------------------------
         if (warp == 0) {
             for (int i = 0; i < F_CH; ++i) {
@@ -138,14 +148,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) fc1_fused_kernel(const __grid_co
                 if (b < bsz) atomicAdd(hacc + b * F_OUT + j, v[b]);
             __threadfence();
         }
-        // independent of the barrier: everything the head needs besides hpre
-        if (warp == 2 || warp == 3) {
-            const int t2 = tid - 64;
-            for (int e = t2; e < 1280; e += 64) sw2[e >> 7][e & 127] = W[Off::f2w + e];
-            if (t2 < 10) sb2[t2] = W[Off::f2b + t2];
-            if (t2 < 32) slabel[t2] = t2 < bsz ? a.y[a.sample_off[c] + (long long)(*a.step_ctr) * a.B + t2] : 0;
-            if (t2 < 2) red[t2] = 0.f;
-        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { const int e = tid + F_THREADS * i; sw2[e >> 7][e & 127] = w2r[i]; }
+        if (tid < 10) sb2[tid] = b2r;
+        if (tid < 32) slabel[tid] = labr;
+        if (tid < 2) red[tid] = 0.f;
         tc_fence_before();
         __syncthreads();
 
@@ -198,16 +205,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) fc1_fused_kernel(const __grid_co
             __threadfence();
             s_last = atomicAdd(&ctr[1], 1) == F_S - 1;
         }
-        for (int e = warp; e < bsz * 10; e += F_THREADS / 32) {      // one warp per logit
-            const int b = e / 10, j = e % 10;
-            float acc = sh[b][lane] * sw2[j][lane];
-            acc = fmaf(sh[b][lane + 32], sw2[j][lane + 32], acc);
-            acc = fmaf(sh[b][lane + 64], sw2[j][lane + 64], acc);
-            acc = fmaf(sh[b][lane + 96], sw2[j][lane + 96], acc);
-            acc = flb_warp_sum(acc) + sb2[j];
-            if (lane == 0) {
-                slog[b][j] = acc;
-                if (pub) p.ws.logits[kb0 * 10 + e] = acc;
+        // logits: 4 lanes per dot product (32 elements each, interleaved so that the quad reads consecutive banks); every
+        // thread owns 5 (sample, class) pairs.  (One warp per logit was a chain of 40 x 5 dependent shuffles per warp.)
+        {
+            const int part = tid & 3;
+#pragma unroll 1
+            for (int r = 0; r < 5; ++r) {
+                const int eidx = (tid >> 2) + 64 * r;          // 320 pairs in all
+                const bool ok = eidx < bsz * 10;
+                const int e = ok ? eidx : 0, b = e / 10, j = e % 10;
+                float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                for (int u = 0; u < 32; u += 2) {
+                    t0 = fmaf(sh[b][4 * u + part], sw2[j][4 * u + part], t0);
+                    t1 = fmaf(sh[b][4 * u + 4 + part], sw2[j][4 * u + 4 + part], t1);
+                }
+                float t = t0 + t1;
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (part == 0 && ok) {
+                    t += sb2[j];
+                    slog[b][j] = t;
+                    if (pub) p.ws.logits[kb0 * 10 + eidx] = t;
+                }
             }
         }
         __syncthreads();
@@ -341,8 +361,9 @@ int fc1_fused(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st) {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;           // all CTAs co-resident or the launch fails: the client barrier spins
     at[0].val.cooperative = 1;
+    static const bool coop = getenv("FLB_FC1_NO_COOP") == nullptr;       // A/B switch (the grid never exceeds one CTA per SM either way)
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = coop ? 1 : 0;
     FLB_CUDA(cudaLaunchKernelEx(&cfg, fc1_fused_kernel, p));
     return FLB_OK;
 }

@@ -44,7 +44,7 @@ void flb_set_error(const char* fmt, ...);
         }                                                                          \
     } while (0)
 
-struct SideLane { bool ready = false; cudaStream_t s = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; };
+struct SideLane { bool ready = false; cudaStream_t s = nullptr, s2 = nullptr; cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };
 SideLane* flb_side_lane();   // per host thread and device; nullptr if it cannot be created
 
 int flb_num_sms();   // SM count of the current device (148 on B200), cached

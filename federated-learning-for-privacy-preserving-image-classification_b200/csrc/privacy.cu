@@ -53,13 +53,29 @@ dp_sumsq_kernel(const float* __restrict__ local, long long ld, const float* __re
     }
 }
 
-template <bool VEC>
+// ABSMAX (update codec, src/shared/compression.py:203-210): the quantiser's per-layer max|x| of the upload is a by-product
+// of this pass -- the bits of |x| are a monotone integer key for non-negative floats, reduced per thread while the layer
+// stays the same, then per CTA in shared memory, then with one atomicMax per (CTA, layer).  Saves the quantiser's own
+// reduction pass over the fp32 upload (4 B per parameter).
+constexpr int kMaxAbsLayers = 64;
+
+template <bool VEC, bool ABSMAX>
 __global__ void __launch_bounds__(kThreads)
 dp_clip_noise_kernel(const float* __restrict__ local, long long ld, const float* __restrict__ global_w,
                      const float* __restrict__ z_in, const double* __restrict__ norm2,
                      float* __restrict__ out, float* __restrict__ norms_out,
                      double max_norm, double sigma_unit, unsigned long long seed,
-                     unsigned long long stream_base, unsigned long long stream_stride, long long P) {
+                     unsigned long long stream_base, unsigned long long stream_stride, long long P,
+                     const long long* __restrict__ seg_off, int L, unsigned int* __restrict__ absmax_bits) {
+    __shared__ unsigned int s_max[ABSMAX ? kMaxAbsLayers : 1];
+    __shared__ long long s_off[ABSMAX ? kMaxAbsLayers + 1 : 1];
+    if (ABSMAX) {
+        for (int i = threadIdx.x; i <= L; i += kThreads) s_off[i] = seg_off[i];
+        for (int i = threadIdx.x; i < L; i += kThreads) s_max[i] = 0u;
+        __syncthreads();
+    }
+    int cur_l = 0;                       // layer of the running maximum
+    unsigned int cur_max = 0u;
     const int k = blockIdx.y;
     const double n = sqrt(norm2[k]);
     const float coef = n > max_norm ? (float)(max_norm / n) : 1.0f;        // privacy.py:127-131
@@ -104,6 +120,29 @@ dp_clip_noise_kernel(const float* __restrict__ local, long long ld, const float*
         } else {
             for (int e = 0; e < 4 && p + e < P; ++e) orow[p + e] = r[e];
         }
+        if (ABSMAX) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long pe = p + e;
+                if (pe >= P) break;
+                if (pe < s_off[cur_l] || pe >= s_off[cur_l + 1]) {           // another layer: flush, then find it
+                    if (cur_max) atomicMax(&s_max[cur_l], cur_max);
+                    cur_max = 0u;
+                    int lo = 0, hi = L;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= pe) lo = mid; else hi = mid; }
+                    cur_l = lo;
+                }
+                const unsigned int bits = __float_as_uint(fabsf(r[e]));
+                if (bits <= 0x7f800000u) cur_max = max(cur_max, bits);      // NaN is ignored, like torch.max of abs() would propagate
+                                                                            // it only into a scale that the validator rejects anyway
+            }
+        }
+    }
+    if (ABSMAX) {
+        if (cur_max) atomicMax(&s_max[cur_l], cur_max);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L; i += kThreads)
+            if (s_max[i]) atomicMax(&absmax_bits[(long long)k * L + i], s_max[i]);
     }
 }
 
@@ -181,10 +220,34 @@ extern "C" int flb_dp_clip_noise(const float* local, long long ld, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (ld % 4 == 0) && ((uintptr_t)local % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      (!global_w || (uintptr_t)global_w % 16 == 0) && (!z_in || (uintptr_t)z_in % 16 == 0);
-    static const int resident = flb_resident_ctas(dp_clip_noise_kernel<true>, kThreads);
+    static const int resident = flb_resident_ctas(dp_clip_noise_kernel<true, false>, kThreads);
     dim3 grid(blocks_per_client(P, K, resident), K);
-    if (vec) dp_clip_noise_kernel<true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
-    else dp_clip_noise_kernel<false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P);
+    if (vec) dp_clip_noise_kernel<true, false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P, nullptr, 0, nullptr);
+    else dp_clip_noise_kernel<false, false><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P, nullptr, 0, nullptr);
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+// Same pass, and absmax_bits[k * L + l] = bits of max |out[k, seg_off[l] .. seg_off[l+1])| (a monotone key for non-negative
+// floats; zeroed here): the input of flb_q8_quantize_absmax.
+extern "C" int flb_dp_clip_noise_absmax(const float* local, long long ld, const float* global_w, const float* z_in,
+                                        const double* norm2, float* out, float* norms_out, double max_norm,
+                                        double sigma_unit, unsigned long long seed, unsigned long long stream_base,
+                                        unsigned long long stream_stride, const long long* seg_off, int L,
+                                        unsigned int* absmax_bits, int K, long long P, void* stream) {
+    FLB_CHECK_ARG(local && norm2 && out && seg_off && absmax_bits, "flb_dp_clip_noise_absmax: null pointer");
+    FLB_CHECK_ARG(K >= 1 && K <= 65535 && P >= 0 && ld >= P, "flb_dp_clip_noise_absmax: need 1 <= K <= 65535, ld >= P");
+    FLB_CHECK_ARG(L >= 1 && L <= kMaxAbsLayers, "flb_dp_clip_noise_absmax: 1 <= L <= %d layers", kMaxAbsLayers);
+    FLB_CHECK_ARG(max_norm > 0.0 && sigma_unit >= 0.0, "flb_dp_clip_noise_absmax: need max_norm > 0 and sigma_unit >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    FLB_CUDA(cudaMemsetAsync(absmax_bits, 0, sizeof(unsigned int) * (size_t)K * L, st));
+    if (P == 0) return FLB_OK;
+    const bool vec = (ld % 4 == 0) && ((uintptr_t)local % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     (!global_w || (uintptr_t)global_w % 16 == 0) && (!z_in || (uintptr_t)z_in % 16 == 0);
+    static const int resident = flb_resident_ctas(dp_clip_noise_kernel<true, true>, kThreads);
+    dim3 grid(blocks_per_client(P, K, resident), K);
+    if (vec) dp_clip_noise_kernel<true, true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P, seg_off, L, absmax_bits);
+    else dp_clip_noise_kernel<false, true><<<grid, kThreads, 0, st>>>(local, ld, global_w, z_in, norm2, out, norms_out, max_norm, sigma_unit, seed, stream_base, stream_stride, P, seg_off, L, absmax_bits);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

@@ -33,7 +33,8 @@ SideLane* flb_side_lane() {
     SideLane& l = lanes[dev];
     if (!l.ready) {
         if (cudaStreamCreateWithFlags(&l.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 4; ++i)
+        if (cudaStreamCreateWithFlags(&l.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 6; ++i)
             if (cudaEventCreateWithFlags(&l.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         l.ready = true;
     }

@@ -649,10 +649,12 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, 
     const int fused_bias = ((tcm & TC_CONV2_WGRAD) && a.dp_mode == 0) ? 1 : 0;
     unpool2_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws, fused_bias);
     MARK("unpool2");
+    // with the optimizer fused into fc1's wgrad that kernel is a long memory stream: conv2's wgrad gets a lane of its own
+    cudaStream_t conv2_lane = lane ? (fused_adam ? lane->s2 : lane->s) : nullptr;
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[1], st));
-        FLB_CUDA(cudaStreamWaitEvent(lane->s, lane->ev[1], 0));
-        if (int rc = wgrads_conv2(lane->s)) return rc;
+        FLB_CUDA(cudaStreamWaitEvent(conv2_lane, lane->ev[1], 0));
+        if (int rc = wgrads_conv2(conv2_lane)) return rc;
     }
     if (tcm & TC_CONV2_DGRAD) {
         if (int rc = tc::conv_dgrad(a, kConv2, ws.z2, ws.da1p, ws.wt, kLdt, st)) return rc;
@@ -708,6 +710,10 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, 
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
         FLB_CUDA(cudaStreamWaitEvent(st, lane->ev[2], 0));
+        if (conv2_lane != lane->s) {
+            FLB_CUDA(cudaEventRecord(lane->ev[4], conv2_lane));
+            FLB_CUDA(cudaStreamWaitEvent(st, lane->ev[4], 0));
+        }
     }
     if (lane_ps) {
         FLB_CUDA(cudaEventRecord(lane_ps->ev[3], lane_ps->s));

@@ -668,16 +668,12 @@ struct FcDgradT {
 };
 
 // ---- linear wgrad: D[128 out, 256 in] = sum_b dout[b, out] * act[b, in] ------------------------------------------------
-// ADAM: the epilogue does not store the gradient tile -- it applies the optimizer step (opt_update.cuh: Adam / SGD-momentum /
-// AdamW, selected by args.opt) to W, M, V straight out of TMEM.  For SimpleCNN's fc1.weight (401 408 of the 421 642
-// parameters) this removes the gradient's HBM round trip (4 B written + 4 B read per parameter) and takes 95 % of the
-// optimizer's bytes off the step's critical path: the stand-alone optimizer kernel then skips this range (TcConvTab::skip_*).
-// The caller orders this kernel after the layer's dgrad (which still reads the old W).
-template <int IN, int OUT, bool ADAM = false>
+template <int IN, int OUT>
 struct FcWgradT {
     struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
     bool lead = false;               // this lane issues the TMA / MMA instructions (skeleton sets it; the rest of the warp runs along)
     static_assert(OUT % 128 == 0, "whole 128-row accumulator tiles");
+    static constexpr int NT = 256;
     static constexpr int STAGES = 1, STAGE_BYTES = 4 * 4096 + 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 256, MINB = 1;
     int client, n0, ksteps, mt;
     __device__ bool setup(const Params& p, int& num_kb) {
@@ -703,60 +699,111 @@ struct FcWgradT {
         for (int k = 0; k < ksteps; ++k)
             if (this->lead) mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
     }
-    template <int OPT>
-    static __device__ __forceinline__ void apply(const OptScalars& c, const float* g, float* __restrict__ W, float* __restrict__ M,
-                                                 float* __restrict__ V, bool need_m) {
-        // 16 parameters per pass: every load of the pass is in flight before the first update
-        float4 w4[4], m4[4], v4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            w4[q] = reinterpret_cast<const float4*>(W)[q];
-            m4[q] = need_m ? reinterpret_cast<const float4*>(M)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-            v4[q] = OPT != 1 ? reinterpret_cast<const float4*>(V)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            opt_update<OPT, false>(c, g[4 * q + 0], 0.f, w4[q].x, m4[q].x, v4[q].x);
-            opt_update<OPT, false>(c, g[4 * q + 1], 0.f, w4[q].y, m4[q].y, v4[q].y);
-            opt_update<OPT, false>(c, g[4 * q + 2], 0.f, w4[q].z, m4[q].z, v4[q].z);
-            opt_update<OPT, false>(c, g[4 * q + 3], 0.f, w4[q].w, m4[q].w, v4[q].w);
-            reinterpret_cast<float4*>(W)[q] = w4[q];
-            reinterpret_cast<float4*>(M)[q] = m4[q];
-            if (OPT != 1) reinterpret_cast<float4*>(V)[q] = v4[q];
-        }
-    }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int j = mt * 128 + quarter * 32 + lane;
-        const long long off = (long long)client * p.a.ld + p.woff + (long long)j * IN;
-        float* g = p.a.G + off;
-        OptScalars c;
-        bool need_m = true;
-        if (ADAM) {
-            const int t = p.a.tcount[client] + 1;             // the stand-alone optimizer kernel advances tcount later in the step
-            c = opt_scalars(p.a, t, flb_bsz(p.a, client));
-            need_m = p.a.opt != 1 || t > 1;
-        }
+        float* g = p.a.G + (long long)client * p.a.ld + p.woff + (long long)j * IN;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
-            if (ADAM) {
-#pragma unroll
-                for (int h = 0; h < 32; h += 16) {
-                    const int n = n0 + c0 + h;
-                    if (n < IN) {                               // IN % 16 == 0: whole 16-parameter passes
-                        float* W = p.a.W + off + n; float* M = p.a.M + off + n; float* V = p.a.V + off + n;
-                        if (p.a.opt == 0) apply<0>(c, v + h, W, M, V, need_m);
-                        else if (p.a.opt == 1) apply<1>(c, v + h, W, M, V, need_m);
-                        else apply<2>(c, v + h, W, M, V, need_m);
-                    }
-                }
-                continue;
-            }
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const int n = n0 + c0 + i;
                 if (n < IN) *reinterpret_cast<float4*>(g + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+};
+
+// ---- linear wgrad, transposed accumulator: D[128 in, 128 out] = sum_b act[b, in] * dout[b, out] ---------------------------
+// Same operands as above with the MMA roles swapped, so that a TMEM LANE is an input feature: for a fixed output feature j
+// the 32 lanes of a warp touch W[j][n .. n+32) -- one 128-byte line per warp instruction.  (With lanes = output features
+// every lane sits in a different 12.5 KB row: 32 LSU wavefronts per instruction; measured 49 us for the fused-optimizer
+// epilogue in that orientation, LSU-bound, regardless of how many loads were kept in flight.)
+// ADAM: the epilogue does not store the gradient -- it applies the optimizer step (opt_update.cuh: Adam / SGD-momentum /
+// AdamW by args.opt) to W, M, V straight out of TMEM.  For SimpleCNN's fc1.weight (401 408 of the 421 642 parameters) this
+// removes the gradient's memory round trip (4 B written + 4 B read per parameter) and takes 95 % of the optimizer's bytes
+// off the step's critical path: the stand-alone optimizer kernel skips the range (TcConvTab::skip_*).  The caller orders
+// this kernel after the layer's dgrad, which still reads the old W.
+template <int IN, bool ADAM>
+struct FcWgradSwapT {
+    struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
+    bool lead = false;
+    static constexpr int OUT = 128;
+    static constexpr int STAGES = 1, STAGE_BYTES = 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 128, MINB = 2;
+    int client, n0, ksteps;
+    __device__ bool setup(const Params& p, int& num_kb) {
+        client = blockIdx.y;
+        if (flb_bsz(p.a, client) == 0) return false;
+        n0 = blockIdx.x * 128;           // input-feature tile (the last one is partial: TMA zero-fills the columns past IN)
+        ksteps = p.a.B / 8;
+        num_kb = 1;
+        return true;
+    }
+    __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_dout); tma_prefetch_desc(&p.map_act); }
+    __device__ void stage_resident(const Params&, uint8_t*, int) {}
+    __device__ void load(const Params& p, int, uint8_t* stage, uint64_t* bar) {
+        if (this->lead) mbar_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_act, stage + c * 4096, bar, n0 + 32 * c, client * p.a.B);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_dout, stage + 4 * 4096 + c * 4096, bar, 32 * c, client * p.a.B);
+    }
+    __device__ void mma(int, uint32_t stage, uint32_t, uint32_t tmem) {
+        constexpr uint32_t id = idesc_tf32(128, 128, true, true);
+        for (int k = 0; k < ksteps; ++k)
+            if (this->lead) mma_tf32(tmem, smem_desc_mn(stage + k * 1024, 4096, 512), smem_desc_mn(stage + 4 * 4096 + k * 1024, 4096, 512), id, k > 0);
+    }
+    template <int OPT>
+    __device__ __forceinline__ void epilogue_opt(const Params& p, uint32_t taddr, long long off, bool live) {
+        const int t = p.a.tcount[client] + 1;                 // the stand-alone optimizer kernel advances tcount later in the step
+        const OptScalars c = opt_scalars(p.a, t, flb_bsz(p.a, client));
+        const bool need_m = OPT != 1 || t > 1;
+        float* __restrict__ W = p.a.W + off; float* __restrict__ M = p.a.M + off; float* __restrict__ V = p.a.V + off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < OUT; c0 += 32) {
+            float g[32], w[32], m[32], v[32];
+            if (live) {                                       // the chunk's 96 loads are in flight before the first update
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const long long e = (long long)(c0 + i) * IN;
+                    w[i] = W[e];
+                    m[i] = need_m ? M[e] : 0.f;
+                    v[i] = OPT != 1 ? V[e] : 0.f;
+                }
+            }
+            tmem_ld32(taddr + c0, g);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const long long e = (long long)(c0 + i) * IN;
+                    opt_update<OPT, false>(c, g[i], 0.f, w[i], m[i], v[i]);
+                    W[e] = w[i];
+                    M[e] = m[i];
+                    if (OPT != 1) V[e] = v[i];
+                }
+            }
+        }
+    }
+    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
+        const int n = n0 + quarter * 32 + lane;               // this thread's input feature
+        const bool live = n < IN;
+        const long long off = (long long)client * p.a.ld + p.woff + n;
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
+        if (ADAM) {
+            if (p.a.opt == 0) epilogue_opt<0>(p, taddr, off, live);
+            else if (p.a.opt == 1) epilogue_opt<1>(p, taddr, off, live);
+            else epilogue_opt<2>(p, taddr, off, live);
+            return;
+        }
+        float* __restrict__ g = p.a.G + off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < OUT; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) g[(long long)(c0 + i) * IN] = v[i];
             }
         }
     }
@@ -963,15 +1010,24 @@ static int fc_dgrad_t(const flb_train_args& a, const float* dout, float* dact, i
     p.a = a; p.dact_all = dact;
     return launch<T>(p, dim3((IN + 127) / 128, a.K), st);
 }
-template <int IN, int OUT, bool ADAM>
+template <int IN, int OUT>
 static int fc_wgrad_t(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
-    static_assert(IN % 16 == 0, "the fused optimizer epilogue works in 16-parameter passes");
-    using T = FcWgradT<IN, OUT, ADAM>;
+    using T = FcWgradT<IN, OUT>;
     typename T::Params p;
     if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, OUT, 32, true)) return rc;
     if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32, true)) return rc;
     p.a = a; p.woff = woff;
     return launch<T>(p, dim3((IN + 255) / 256, a.K, OUT / 128), st);
+}
+// out = 128 (SimpleCNN fc1): transposed accumulator, coalesced epilogue; ADAM applies the optimizer step instead of storing G
+template <int IN, bool ADAM>
+static int fc_wgrad_swap_t(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
+    using T = FcWgradSwapT<IN, ADAM>;
+    typename T::Params p;
+    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32, true)) return rc;
+    p.a = a; p.woff = woff;
+    return launch<T>(p, dim3((IN + 127) / 128, a.K, 1), st);
 }
 
 // tensor maps of SimpleCNN's fused classifier kernel (fc1_fused.cu): fc1.weight as K-major [128 x 32] boxes and as MN-major
@@ -996,14 +1052,17 @@ int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, in
     FLB_FC_DISPATCH(fc_dgrad_t, a, dout, dact, woff, st)
 }
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int out, int woff, cudaStream_t st, bool adam) {
+    static const bool no_swap = getenv("FLB_FC_WGRAD_NO_SWAP") != nullptr;       // A/B switch for the plain (gradient-storing) variant
+    if (in == 3136 && out == 128) {
+        if (adam) return fc_wgrad_swap_t<3136, true>(a, dout, act, woff, st);
+        return no_swap ? fc_wgrad_t<3136, 128>(a, dout, act, woff, st) : fc_wgrad_swap_t<3136, false>(a, dout, act, woff, st);
+    }
     if (adam) {
-        if (in == 3136 && out == 128) return fc_wgrad_t<3136, 128, true>(a, dout, act, woff, st);
         flb_set_error("tensor-core linear wgrad with the fused optimizer: unsupported shape %d -> %d", in, out);
         return FLB_ERR_UNSUPPORTED;
     }
-    if (in == 3136 && out == 128) return fc_wgrad_t<3136, 128, false>(a, dout, act, woff, st);
-    if (in == 2048 && out == 512) return fc_wgrad_t<2048, 512, false>(a, dout, act, woff, st);
-    if (in == 512 && out == 256) return fc_wgrad_t<512, 256, false>(a, dout, act, woff, st);
+    if (in == 2048 && out == 512) return fc_wgrad_t<2048, 512>(a, dout, act, woff, st);
+    if (in == 512 && out == 256) return fc_wgrad_t<512, 256>(a, dout, act, woff, st);
     flb_set_error("tensor-core linear: unsupported shape %d -> %d", in, out);
     return FLB_ERR_UNSUPPORTED;
 }

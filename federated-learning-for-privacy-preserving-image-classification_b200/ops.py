@@ -84,8 +84,9 @@ def gaussian_sigma_unit(epsilon: float, delta: float) -> float:
 
 def dp_clip_noise(local: torch.Tensor, global_w: Optional[torch.Tensor], max_norm: float, sigma_unit: float,
                   seed: int = 0, stream_base: int = 0, z: Optional[torch.Tensor] = None, P: Optional[int] = None,
-                  out: Optional[torch.Tensor] = None, stream_stride: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Batched update-level DP over K client rows.  Returns (upload rows [K, ld], ||delta_k|| [K])."""
+                  out: Optional[torch.Tensor] = None, stream_stride: int = 1, absmax_seg: Optional[torch.Tensor] = None):
+    """Batched update-level DP over K client rows.  Returns (upload rows [K, ld], ||delta_k|| [K]); with ``absmax_seg`` (the
+    layer offset table) also the per-(client, layer) max|upload| bit patterns [K, L] that ``q8_quantize(absmax=...)`` takes."""
     L.require_cuda_f32(local, "local")
     L.ensure_device(local.device)
     K, ld = local.shape[0], _row_stride(local)
@@ -104,6 +105,13 @@ def dp_clip_noise(local: torch.Tensor, global_w: Optional[torch.Tensor], max_nor
     with torch.cuda.device(dev):
         st = L.stream_ptr(dev)
         L.call("flb_dp_sumsq", L.ptr(local), ld, L.ptr(global_w), L.ptr(norm2), K, P, st)
+        if absmax_seg is not None:
+            Lyr = absmax_seg.numel() - 1
+            absmax = torch.empty((K, Lyr), dtype=torch.int32, device=dev)
+            L.call("flb_dp_clip_noise_absmax", L.ptr(local), ld, L.ptr(global_w), L.ptr(z), L.ptr(norm2), L.ptr(out),
+                   L.ptr(norms), float(max_norm), float(sigma_unit), int(seed) & (2**64 - 1),
+                   int(stream_base) & (2**64 - 1), int(stream_stride), L.ptr(absmax_seg), Lyr, L.ptr(absmax), K, P, st)
+            return out, norms, absmax
         L.call("flb_dp_clip_noise", L.ptr(local), ld, L.ptr(global_w), L.ptr(z), L.ptr(norm2), L.ptr(out),
                L.ptr(norms), float(max_norm), float(sigma_unit), int(seed) & (2**64 - 1),
                int(stream_base) & (2**64 - 1), int(stream_stride), K, P, st)
@@ -142,8 +150,9 @@ def philox_raw(nblocks: int, seed: int, stream: int, first_block: int, device) -
 
 
 def q8_quantize(x: torch.Tensor, seg_off: torch.Tensor, P: Optional[int] = None, bits: int = 8,
-                symmetric: bool = True):
-    """Per-(client, layer) affine quantisation of the K client rows.  Returns (q uint8 [K, ld], scale [K, L], zp [K, L])."""
+                symmetric: bool = True, absmax: Optional[torch.Tensor] = None):
+    """Per-(client, layer) affine quantisation of the K client rows.  Returns (q uint8 [K, ld], scale [K, L], zp [K, L]).
+    ``absmax`` (from ``dp_clip_noise(absmax_seg=...)``, symmetric mode only) skips the max|x| reduction pass."""
     L.require_cuda_f32(x, "x")
     L.ensure_device(x.device)
     K, ld = x.shape[0], _row_stride(x)
@@ -153,6 +162,13 @@ def q8_quantize(x: torch.Tensor, seg_off: torch.Tensor, P: Optional[int] = None,
     q = torch.empty((K, ld), dtype=torch.uint8, device=dev)
     scale = torch.empty((K, Lyr), dtype=torch.float32, device=dev)
     zp = torch.empty((K, Lyr), dtype=torch.float32, device=dev)
+    if absmax is not None:
+        if not symmetric:
+            raise L.FlbError("q8_quantize: a precomputed absmax only serves the symmetric mode")
+        with torch.cuda.device(dev):
+            L.call("flb_q8_quantize_absmax", L.ptr(x), ld, L.ptr(seg_off), L.ptr(absmax), L.ptr(q), ld, L.ptr(scale), L.ptr(zp),
+                   K, Lyr, P, bits, L.stream_ptr(dev))
+        return q, scale, zp
     scratch = torch.empty(2 * K * Lyr, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         L.call("flb_q8_quantize", L.ptr(x), ld, L.ptr(seg_off), L.ptr(q), ld, L.ptr(scale), L.ptr(zp), L.ptr(scratch),

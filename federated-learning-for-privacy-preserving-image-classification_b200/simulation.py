@@ -67,11 +67,16 @@ class FederatedRoundEngine:
                  process_group=None, batch_size: int = 32, local_epochs: int = 1, learning_rate: float = 0.001,
                  optimizer_type: str = "adam", dp_mode: str = "update", epsilon: float = 1.0, delta: float = 1e-5,
                  max_grad_norm: float = 1.0, dropout_rate: Optional[float] = None, precision: str = "fp32",
-                 compression: Optional[str] = None, seed: Optional[int] = None, use_graph: bool = True):
+                 compression: Optional[str] = None, seed: Optional[int] = None, use_graph: bool = True,
+                 topk_sparsity: float = 0.9):
         if dp_mode not in ("none", "update", "per_sample"):
             raise ValueError("dp_mode must be 'none', 'update' (reference behaviour) or 'per_sample'")
-        if compression not in (None, "q8"):
-            raise ValueError("compression must be None or 'q8'")
+        if compression not in (None, "q8", "topk"):
+            raise ValueError("compression must be None, 'q8' (QuantizationCompressor, 8 bit) or 'topk' (TopKSparsificationCompressor)")
+        if not (0.0 <= topk_sparsity <= 1.0):
+            raise ValueError("topk_sparsity must be in [0, 1]")
+        self.topk_sparsity = float(topk_sparsity)
+        self._topk_meta = None
         self.model_name = model_name
         self.num_clients = int(num_clients)
         self.rank, self.world_size, self.pg = rank, world_size, process_group
@@ -176,19 +181,35 @@ class FederatedRoundEngine:
         for _ in range(self.local_epochs):
             tr._run_epoch()
         rows = tr.W
+        absmax = None
         if self.dp_mode == "update":
             # fresh engine per client-round upstream (budget semantics); Philox stream = global
-            # client index + round * num_clients so results do not depend on how clients are spread over GPUs
+            # client index + round * num_clients so results do not depend on how clients are spread over GPUs.
+            # With the uint8 codec the clip + noise pass also reduces the quantiser's per-layer max|upload|.
             sigma_unit = ops.gaussian_sigma_unit(self.epsilon, self.delta)
-            rows, self.norms = ops.dp_clip_noise(tr.W, self.global_row, self.max_grad_norm, sigma_unit,
-                                                 seed=self.seed ^ 0x0DD5EED,
-                                                 stream_base=self.round_number * self.num_clients + self.rank,
-                                                 stream_stride=self.world_size, z=self.dp_z, P=lay.P, out=self.upload)
+            res = ops.dp_clip_noise(tr.W, self.global_row, self.max_grad_norm, sigma_unit,
+                                    seed=self.seed ^ 0x0DD5EED,
+                                    stream_base=self.round_number * self.num_clients + self.rank,
+                                    stream_stride=self.world_size, z=self.dp_z, P=lay.P, out=self.upload,
+                                    absmax_seg=lay.seg_off(self.device) if self.compression == "q8" and len(lay.names) <= 64 else None)
+            rows, self.norms = res[0], res[1]
+            absmax = res[2] if len(res) > 2 else None
         w = self.fedavg_weights()
         if self.compression == "q8":
             seg = lay.seg_off(self.device)
-            q, scale, zp = ops.q8_quantize(rows, seg, P=lay.P)
+            q, scale, zp = ops.q8_quantize(rows, seg, P=lay.P, absmax=absmax)
             partial = ops.fedavg_weighted_sum_q8(q, scale, zp, seg, w, lay.P)
+        elif self.compression == "topk":
+            # TopKSparsificationCompressor (compression.py:327-365) on every upload: keep the k = max(1, int(n * (1 - sparsity)))
+            # largest-magnitude entries of each layer, zeros elsewhere, then FedAvg over the reconstructed rows
+            seg = lay.seg_off(self.device)
+            if self._topk_meta is None:
+                import math
+                kk = [ops.topk_count(math.prod(lay.shapes[n]), self.topk_sparsity) for n in lay.names]
+                self._topk_meta = kk
+            idx, val, off_t, kk_t = ops.topk_select(rows, seg, self._topk_meta, P=lay.P)
+            dense = ops.topk_scatter(idx, val, seg, kk_t, off_t, lay.P, lay.ld)
+            partial = ops.fedavg_weighted_sum(dense, w, P=lay.P)
         else:
             partial = ops.fedavg_weighted_sum(rows, w, P=lay.P)
         if self.world_size > 1:

@@ -46,6 +46,14 @@ int flb_dp_clip_noise(const float* local, long long ld, const float* global_w, c
                       const double* norm2, float* out, float* norms_out, double max_norm,
                       double sigma_unit, unsigned long long seed, unsigned long long stream_base,
                       unsigned long long stream_stride, int K, long long P, void* stream);
+/* flb_dp_clip_noise that also delivers the update codec's per-(client, layer) max|out| (compression.py:207-210) as a
+ * by-product of the same pass: absmax_bits[k*L + l] = bit pattern of max |out[k, seg_off[l] .. seg_off[l+1])| (monotone for
+ * non-negative floats; zeroed by the call).  L <= 64.  Feeds flb_q8_quantize_absmax, which then skips its reduction pass. */
+int flb_dp_clip_noise_absmax(const float* local, long long ld, const float* global_w, const float* z_in,
+                             const double* norm2, float* out, float* norms_out, double max_norm,
+                             double sigma_unit, unsigned long long seed, unsigned long long stream_base,
+                             unsigned long long stream_stride, const long long* seg_off, int L,
+                             unsigned int* absmax_bits, int K, long long P, void* stream);
 /* out[k] = x[k] + sigma * z  (GaussianNoiseGenerator.add_noise_to_gradients alone, privacy.py:221-254) */
 int flb_dp_add_noise(const float* x, long long ld, const float* z_in, float* out, double sigma,
                      unsigned long long seed, unsigned long long stream_base, int K, long long P, void* stream);
@@ -59,6 +67,10 @@ int flb_philox_raw(uint32_t* out, long long nblocks, unsigned long long seed, un
 int flb_q8_quantize(const float* x, long long ld, const long long* seg_off, uint8_t* q, long long ldq,
                     float* scale, float* zp, uint32_t* scratch, int K, int L, long long P,
                     int bits, int symmetric, void* stream);
+/* symmetric quantisation from a known per-(client, layer) max|x| (absmax_bits as written by flb_dp_clip_noise_absmax) */
+int flb_q8_quantize_absmax(const float* x, long long ld, const long long* seg_off, const unsigned int* absmax_bits,
+                           uint8_t* q, long long ldq, float* scale, float* zp, int K, int L, long long P,
+                           int bits, void* stream);
 int flb_q8_dequantize(const uint8_t* q, long long ldq, const long long* seg_off, const float* scale,
                       const float* zp, float* out, long long ld, int K, int L, long long P, void* stream);
 

@@ -296,7 +296,14 @@ def test_tf32_training_epoch_tracks_fp32(cuda_device):
 #     carry only the TF32 rounding of that one kernel.
 # This is the evidence that the 0.12 end-to-end bound above is near-tie flips and not an indexing error in the halo /
 # streamed kernels: every kernel alone is within 2e-3 relative L2.
-_CONV_Z = {1: ("z2", 33 * 33 + 7, 32), 2: ("z3", None, 64), 3: ("z4", None, 64), 4: ("z5", None, 128), 5: ("z6", None, 128)}
+_CONV_Z = {1: ("z2", 32, 33, 32), 2: ("z3", 16, 17, 64), 3: ("z4", 16, 17, 64), 4: ("z5", 8, 9, 128), 5: ("z6", 8, 9, 128)}   # name, H = W, Wp, C
+
+
+def _real_pixels(rows, hw, wp, ch):
+    """[K, B, PP * C] NHWC rows on the padded grid -> [K, B, H, W, C] (pad positions hold don't-care values)."""
+    K, B, _ = rows.shape
+    grid = rows.view(K, B, -1, ch)[:, :, :hw * wp].reshape(K, B, hw, wp, ch)
+    return grid[:, :, :, :hw]
 
 
 def _run_masked(cuda_device, mask, sizes=(16, 9), B=16):
@@ -334,8 +341,11 @@ def test_each_tensor_core_forward_kernel_alone(cuda_device, fp32_reference_pass,
     bit = 3 * (layer - 1) if isinstance(layer, int) else (15 if layer == "fc1" else 18)
     got = _run_masked(cuda_device, 1 << bit)
     name = _CONV_Z[layer][0] if isinstance(layer, int) else ("hpre1" if layer == "fc1" else "hpre2")
+    ga, gb = _ws_rows(got, name), _ws_rows(ref, name)
+    if isinstance(layer, int):
+        ga, gb = _real_pixels(ga, *_CONV_Z[layer][1:]), _real_pixels(gb, *_CONV_Z[layer][1:])
     for k, n in enumerate((16, 9)):
-        a, b = _ws_rows(got, name)[k, :n], _ws_rows(ref, name)[k, :n]
+        a, b = ga[k, :n], gb[k, :n]
         assert float(b.abs().max()) > 0
         assert _rel(a, b) < 2e-3, (layer, k, _rel(a, b))
 
@@ -347,8 +357,8 @@ def test_each_tensor_core_backward_kernel_alone(cuda_device, fp32_reference_pass
     bit = (3 * (layer - 1) if isinstance(layer, int) else (15 if layer == "fc1" else 18)) + kind
     got = _run_masked(cuda_device, 1 << bit)
     lay = ref.layout
-    # the forward pass is untouched: identical decisions by construction
-    assert torch.equal(got.ws_array("logits", torch.float32, 10), ref.ws_array("logits", torch.float32, 10))
+    # the forward pass is untouched (the same fp32 kernels; their split-K atomics may reorder a sum by an ulp)
+    torch.testing.assert_close(got.ws_array("logits", torch.float32, 10)[0], ref.ws_array("logits", torch.float32, 10)[0], rtol=1e-5, atol=1e-6)
     worst = 0.0
     for k in range(2):
         for name in lay.names:
@@ -358,4 +368,17 @@ def test_each_tensor_core_backward_kernel_alone(cuda_device, fp32_reference_pass
             r = _rel(got.G[k, o:o + cnt], ref.G[k, o:o + cnt])
             worst = max(worst, r)
             assert r < 2e-3, (layer, kind, k, name, r)
-    assert worst > 0 or kind == 2                           # the tensor-core kernel really ran (dgrad perturbs upstream gradients)
+    assert worst > 1e-6                                     # the tensor-core kernel really ran (TF32 rounding is visible)
+
+
+def test_fp32_path_rerun_noise_floor(cuda_device, fp32_reference_pass):
+    """The yardstick for the per-kernel bounds above: two runs of the SAME fp32 path differ only by the order of their
+    atomic accumulations."""
+    ref, again = fp32_reference_pass, _run_masked(cuda_device, None)
+    lay = ref.layout
+    for k in range(2):
+        for name in lay.names:
+            if name.startswith("conv") and name.endswith(".bias"):
+                continue
+            o, cnt = lay.offsets[name], int(np.prod(lay.shapes[name]))
+            assert _rel(again.G[k, o:o + cnt], ref.G[k, o:o + cnt]) < 2e-4, (k, name)

@@ -92,3 +92,37 @@ def test_compression_service_round_trip(cuda_device, algo, kw):
         svc.compress_weights({k: v.cpu() for k, v in w.items()})          # no CPU fallback
     with pytest.raises(ValueError, match="Unknown compression algorithm"):
         ModelCompressionService("zstd")
+
+
+def test_q8_scale_from_the_dp_pass_is_bit_identical(cuda_device):
+    """f2: the clip + noise pass reduces the quantiser's per-(client, layer) max|upload| on the side
+    (flb_dp_clip_noise_absmax); quantising from it must give exactly the codes / scales of the stand-alone quantiser run on
+    the same upload rows -- including quads that straddle a layer boundary, an all-zero layer and NaN-free ragged tails."""
+    from flb200 import ops
+    g = torch.Generator().manual_seed(3)
+    offs = [0, 5, 5 + 288, 5 + 288 + 33, 5 + 288 + 33 + 1031, 5 + 288 + 33 + 1031 + 4096, 5 + 288 + 33 + 1031 + 4096 + 7]   # unaligned boundaries
+    P, K = offs[-1], 3
+    ld = (P + 31) // 32 * 32
+    local = torch.zeros((K, ld))
+    local[:, :P] = torch.randn((K, P), generator=g) * 0.05
+    glob = torch.zeros(ld)
+    glob[:P] = torch.randn(P, generator=g) * 0.05
+    local[:, offs[2]:offs[3]] = glob[offs[2]:offs[3]]              # layer 2: zero delta and zero global -> all-zero layer below
+    glob[offs[2]:offs[3]] = 0
+    local[:, offs[2]:offs[3]] = 0
+    local, glob = local.to(cuda_device), glob.to(cuda_device)
+    seg = torch.tensor(offs, dtype=torch.int64, device=cuda_device)
+    z = torch.zeros((K, ld), device=cuda_device)                     # sigma * 0: the upload is global + clipped delta
+    up_a, norms_a = ops.dp_clip_noise(local, glob, 0.5, 4.8448, seed=1, z=z, P=P)
+    up_b, norms_b, absmax = ops.dp_clip_noise(local, glob, 0.5, 4.8448, seed=1, z=z, P=P, absmax_seg=seg)
+    assert torch.equal(up_a, up_b) and torch.equal(norms_a, norms_b)
+    want = torch.stack([up_a[:, offs[i]:offs[i + 1]].abs().max(dim=1).values for i in range(len(offs) - 1)], dim=1)
+    assert torch.equal(absmax.view(torch.float32), want)
+    qa, sa, za = ops.q8_quantize(up_a, seg, P=P)
+    qb, sb, zb = ops.q8_quantize(up_b, seg, P=P, absmax=absmax)
+    assert torch.equal(sa, sb) and torch.equal(za, zb)
+    assert torch.equal(qa[:, :P], qb[:, :P])
+    # Philox noise path: same statement with generated noise (the absmax sees exactly the values that were written)
+    up_c, _, absmax_c = ops.dp_clip_noise(local, glob, 0.5, 4.8448, seed=9, stream_base=5, P=P, absmax_seg=seg)
+    want_c = torch.stack([up_c[:, offs[i]:offs[i + 1]].abs().max(dim=1).values for i in range(len(offs) - 1)], dim=1)
+    assert torch.equal(absmax_c.view(torch.float32), want_c)

@@ -56,7 +56,7 @@ def test_round_matches_reference_golden(cuda_device):
     assert (num / den) ** 0.5 < 2e-2
 
 
-@pytest.mark.parametrize("compression", [None, "q8"])
+@pytest.mark.parametrize("compression", [None, "q8", "topk"])
 def test_round_sgd_vs_oracle_tight(cuda_device, compression):
     """SGD(momentum) has no sign sensitivity: the whole round matches the oracle at fp32 tolerance
     (q8: after the oracle's quantise -> dequantise of each upload)."""
@@ -94,6 +94,26 @@ def test_round_sgd_vs_oracle_tight(cuda_device, compression):
             scale = 2 * float(np.abs(ref[name].numpy()).max()) / 255 + 1e-12
             assert np.abs(got[name].numpy() - ref[name].numpy()).max() <= 1.01 * scale, name
             assert np.mean(np.abs(got[name].numpy() - ref[name].numpy()) > 1e-6) < 0.02, name
+    elif compression == "topk":
+        # TopKSparsificationCompressor (sparsity 0.9) on every upload, then FedAvg of the reconstructed dense rows.  The kept
+        # SET is decided on each side's own uploads (fp32 reordering moves entries sitting exactly at the k-th magnitude), so
+        # the aggregate is compared entry by entry with a small budget for such boundary swaps.
+        names = list(spec)
+        dense = []
+        for theta in info["client_thetas"]:
+            parts, off = [], 0
+            for n in names:
+                k = int(np.prod(spec[n]))
+                v, i = OC.sparsify(theta[off:off + k], 0.9)
+                parts.append(OC.desparsify(v, i, (k,))); off += k
+            dense.append(np.concatenate(parts))
+        flat = OF.weighted_average_flat(np.stack(dense), info["weights"])
+        ref = OR.unflatten(flat, spec)
+        for name in ref:
+            g_, r_ = got[name].numpy().reshape(-1), ref[name].numpy().reshape(-1)
+            close = np.abs(g_ - r_) <= 2e-4 * np.abs(r_) + 2e-6
+            assert close.mean() > 0.995, (name, close.mean())
+            assert (g_ != 0).sum() <= int(r_.size * 0.1 * K) + K      # at most K clients x 10 % of the entries survive
     else:
         for name in ref:
             np.testing.assert_allclose(got[name].numpy(), ref[name].numpy(), rtol=2e-4, atol=2e-6, err_msg=name)
