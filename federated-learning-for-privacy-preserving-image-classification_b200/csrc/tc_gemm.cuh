@@ -101,6 +101,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 __device__ __forceinline__ uint64_t smem_desc_row(uint32_t addr) { return smem_desc_raw(addr, 16, 1024, 2); }
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) { return smem_desc_raw(addr, lbo, sbo, 1); }
 
+// A descriptor whose start address is `bytes` further on (bytes % 16 == 0).  The address field is the low 14 bits of
+// (addr >> 4) and shared-memory addresses stay below 256 KB, so the sum never carries into the neighbouring field: one
+// 32-bit add on the low word instead of rebuilding the descriptor (shift, mask, two ORs) for every MMA.  In the halo
+// convolutions that rebuild was ~12 uniform-datapath instructions per tcgen05.mma -- as long as the 40-cycle MMA itself
+// (N = 32; scripts/mma_microbench.py): the issuing warp, not the tensor core, set the pace.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) {
+    return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + (bytes >> 4));
+}
+
 // instruction descriptor: D = fp32, A = B = tf32, dense; a_mn / b_mn select MN-major operands
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -148,6 +157,15 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
         }
     }
     return v[0];
+}
+
+// Live batch size of every resident client, read ONCE per CTA into shared memory.  The persistent skeletons call
+// tile_setup() for every tile from every role; with flb_bsz() inside, that was two dependent global loads (~0.8 us) on the
+// critical path of each tile for the MMA warp, the producer and the epilogue warps (ncu source view, round 2).
+constexpr int BSZ_TAB = 1024;                        // flb_train_args.K <= 1024 (check_args)
+__device__ __forceinline__ void fill_bsz_table(const flb_train_args& a, int* tab) {
+    for (int c = threadIdx.x; c < a.K && c < BSZ_TAB; c += blockDim.x) tab[c] = flb_bsz(a, c);
+    // visible to all roles after the kernel's first __syncthreads()
 }
 
 // optional Traits::finish(p, lane): called once by every epilogue warp after its last tile (persistent skeletons)
@@ -245,6 +263,8 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
     uint8_t* stages = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base;
+    __shared__ int s_bsz[BSZ_TAB];
+    fill_bsz_table(p.a, s_bsz);
     constexpr int TCOLS = 2 * T::ACC_COLS <= 32 ? 32 : (2 * T::ACC_COLS <= 64 ? 64 : (2 * T::ACC_COLS <= 128 ? 128 : (2 * T::ACC_COLS <= 256 ? 256 : 512)));
     static_assert(2 * T::ACC_COLS <= 512, "double-buffered accumulator must fit TMEM");
 
@@ -265,6 +285,7 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
 
     if (warp == 0) {                                           // all lanes run the loop; one elected lane issues (see gemm_kernel)
         T t;
+        t.bsz_tab = s_bsz;
         t.lead = elect_one();
         uint32_t it = 0;                                       // k-blocks issued so far (all tiles)
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -279,6 +300,7 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
         }
     } else if (warp == 1) {
         T t;
+        t.bsz_tab = s_bsz;
         t.lead = elect_one();
         uint32_t it = 0, nt = 0;                               // k-blocks / tiles consumed so far
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -300,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
         }
     } else {
         T t;
+        t.bsz_tab = s_bsz;
         uint32_t nt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int num_kb = 0;
@@ -331,6 +354,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
     uint8_t* stages = wres + T::W_BYTES;
     __shared__ uint64_t full_bar[T::STAGES], empty_bar[T::STAGES], tfull_bar[2], tempty_bar[2], wfull_bar, wempty_bar;
     __shared__ uint32_t tmem_base;
+    __shared__ int s_bsz[BSZ_TAB];
+    fill_bsz_table(p.a, s_bsz);
     constexpr int TCOLS = 2 * T::ACC_COLS <= 32 ? 32 : (2 * T::ACC_COLS <= 64 ? 64 : (2 * T::ACC_COLS <= 128 ? 128 : (2 * T::ACC_COLS <= 256 ? 256 : 512)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,6 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
 
     if (warp == 0) {                                           // all lanes run the loop; one elected lane issues (see gemm_kernel)
         T t;
+        t.bsz_tab = s_bsz;
         t.lead = elect_one();
         uint32_t it = 0, wuse = 0;
         int cur = -1;
@@ -375,6 +401,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
         }
     } else if (warp == 1) {
         T t, tn;
+        t.bsz_tab = s_bsz;
+        tn.bsz_tab = s_bsz;
         t.lead = elect_one();
         uint32_t it = 0, nt = 0, wuse = 0;
         int cur = -1;
@@ -407,6 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
         }
     } else {
         T t;
+        t.bsz_tab = s_bsz;
         uint32_t nt = 0;
         for (int tile = t0; tile < t1; ++tile) {
             int num_kb = 0;

@@ -46,11 +46,15 @@ int tc_mask_of(const flb_train_args& a) {
     return m;
 }
 
-// fc1.weight's optimizer step applied in its weight-gradient GEMM epilogue (FcWgradT<.., ADAM>): only inside a real training
-// step (not the gradient-only entries), without per-sample clipping (which needs every layer's norm before any update)
+// fc1.weight's optimizer step applied in its weight-gradient GEMM epilogue (FcWgradSwapT<.., ADAM>): only inside a real
+// training step (not the gradient-only entries), without per-sample clipping (which needs every layer's norm before any update).
+// OPT-IN (FLB_FUSED_ADAM=1).  Measured at 10 clients per GPU (profiles/r02_fusion_ab.md): the epilogue streams W, M, V at
+// 3.6 TB/s (26.6 us) against 10.2 us for the plain weight-gradient GEMM plus 12.3 us saved in the stand-alone optimizer --
+// no less work, and the side lane it runs on cannot overlap the persistent conv2 dgrad (shared memory co-residency), so
+// the round is 2 % slower with it.
 bool fuse_fc1_adam(const flb_train_args& a, bool step) {
-    static const bool off = getenv("FLB_NO_FUSED_ADAM") != nullptr;
-    return step && !off && a.dp_mode == 0 && (tc_mask_of(a) & TC_FC1_WGRAD);
+    static const bool on = getenv("FLB_FUSED_ADAM") != nullptr;
+    return step && on && a.dp_mode == 0 && (tc_mask_of(a) & TC_FC1_WGRAD);
 }
 
 // fc1 forward + classifier head + fc1 dgrad as ONE launch (fc1_fused.cu) whenever both GEMMs run on the tensor cores and a

@@ -103,10 +103,11 @@ struct ConvFwdT {
         }
     }
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
+    const int* bsz_tab = nullptr;    // per-CTA shared-memory copy of the clients' live batch sizes (persistent skeletons)
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
         const int tpc = (p.a.B * p.g.PP() + 127) / 128;
         client = tile / tpc;
-        const int bsz = flb_bsz(p.a, client);
+        const int bsz = (bsz_tab && client < BSZ_TAB) ? bsz_tab[client] : flb_bsz(p.a, client);
         m0 = (tile - client * tpc) * 128;
         live_rows = bsz * p.g.PP();
         if (m0 >= live_rows) return false;
@@ -256,10 +257,11 @@ struct ConvDgradT {
         }
     }
     static __host__ __device__ int num_tiles(const Params& p) { return ((p.a.B * p.g.PP() + 127) / 128) * p.a.K; }
+    const int* bsz_tab = nullptr;    // per-CTA shared-memory copy of the clients' live batch sizes (persistent skeletons)
     __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
         const int tpc = (p.a.B * p.g.PP() + 127) / 128;
         client = tile / tpc;
-        const int bsz = flb_bsz(p.a, client);
+        const int bsz = (bsz_tab && client < BSZ_TAB) ? bsz_tab[client] : flb_bsz(p.a, client);
         m0 = (tile - client * tpc) * 128;
         if (m0 >= bsz * p.g.PP()) return false;
         row0 = client * p.a.B * p.g.PP();
@@ -346,13 +348,16 @@ struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL, 1> {         // one accumulator:
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t wres, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, false, false);
+        // base descriptors once per k-block; every MMA advances them by a (mostly compile-time) byte offset
+        const uint64_t a_base = smem_desc_row(stage), b_base = smem_desc(wres + (uint32_t)(kb * 9) * (COUT * 128), 16, 1024);
+        const uint32_t row_m = 128u, row_0 = (uint32_t)(wp + 1) * 128u, row_p = (uint32_t)(2 * wp + 1) * 128u;   // box row of tap (r, q = 1): r * wp + 1
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_addr = stage + (uint32_t)(wp + 1 + tap_shift(tap, wp)) * 128u;
-            const uint32_t b_addr = wres + (uint32_t)(kb * 9 + tap) * (COUT * 128);
+            const uint32_t a_off = (tap / 3 == 0 ? row_m : (tap / 3 == 1 ? row_0 : row_p)) + (uint32_t)(tap % 3 - 1) * 128u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (this->lead) mma_tf32(tmem, smem_desc_row(a_addr + k * 32), smem_desc(b_addr + k * 32, 16, 1024), id, kb > 0 || tap > 0 || k > 0);
+                if (this->lead) mma_tf32(tmem, desc_advance(a_base, a_off + k * 32), desc_advance(b_base, tap * (COUT * 128) + k * 32), id,
+                                         kb > 0 || tap > 0 || k > 0);
         }
     }
 };
@@ -386,13 +391,15 @@ struct ConvDgradHaloT : ConvDgradT<CIN, COUT, 3> {
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t wres, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, CIN, false, true);
+        const uint64_t a_base = smem_desc_row(stage), b_base = smem_desc_mn(wres + (uint32_t)(kb * 9 * NCH) * 4096u, 4096, 512);
+        // box row of tap (r, q): (wp + 1) - ((r - 1) * wp + (q - 1)) = (2 - r) * wp + 2 - q
+        const uint32_t row_r0 = (uint32_t)(2 * wp + 1) * 128u, row_r1 = (uint32_t)(wp + 1) * 128u, row_r2 = 128u;      // q = 1
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_addr = stage + (uint32_t)(wp + 1 - tap_shift(tap, wp)) * 128u;
-            const uint32_t b_addr = wres + (uint32_t)((kb * 9 + tap) * NCH) * 4096u;
+            const uint32_t a_off = (tap / 3 == 0 ? row_r0 : (tap / 3 == 1 ? row_r1 : row_r2)) - (uint32_t)(tap % 3 - 1) * 128u;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (this->lead) mma_tf32(tmem + (tap / 3) * CIN, smem_desc_row(a_addr + k * 32), smem_desc_mn(b_addr + k * 1024, 4096, 512), id,
+                if (this->lead) mma_tf32(tmem + (tap / 3) * CIN, desc_advance(a_base, a_off + k * 32), desc_advance(b_base, tap * NCH * 4096 + k * 1024), id,
                                          kb > 0 || (tap % 3) > 0 || k > 0);
         }
     }
@@ -535,15 +542,17 @@ struct ConvWgradHaloT {
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, true, true);
         const int ksteps = min(4, (total_rows - (kb0 + kb) * 32) >> 3);      // rows per image are a multiple of 8
+        // base descriptors once per k-block, advanced per MMA (tc_gemm.cuh desc_advance)
+        const uint64_t a_base = smem_desc_mn(stage + (uint32_t)(rbase * wp) * 128u, 128, 512), b_base = smem_desc_mn(stage + A_BYTES, 4096, 512);
+        const uint32_t row_step = (uint32_t)wp * 128u;
         for (int k = 0; k < ksteps; ++k)
 #pragma unroll
             for (int rl = 0; rl < RPC; ++rl)
 #pragma unroll
                 for (int c = 0; c < CCH; ++c) {
                     // box row of tap (r, j = 0) for pixel 0 of the k-block: halo + shift = (Wp + 1) + (r - 1) * Wp - 1 = r * Wp
-                    const uint32_t a_addr = stage + c * WG_BOX_BYTES + (uint32_t)((rbase + rl) * wp + 8 * k) * 128u;
-                    if (this->lead) mma_tf32(tmem + (rl * CCH + c) * COUT, smem_desc_mn(a_addr, 128, 512),
-                                             smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
+                    if (this->lead) mma_tf32(tmem + (rl * CCH + c) * COUT, desc_advance(a_base, c * WG_BOX_BYTES + rl * row_step + k * 1024),
+                                             desc_advance(b_base, k * 1024), id, kb > 0 || k > 0);
                 }
     }
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {

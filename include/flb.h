@@ -185,6 +185,12 @@ int flb_train_advance(const flb_train_args* a, void* stream);
 /* forward + loss/gradients only (no optimizer, no counter advance): fills G and the workspace, for parity tests */
 int flb_train_forward_backward(const flb_train_args* a, void* stream);
 
+/* ---- profiling aid: cycles of `reps` back-to-back tcgen05.mma kind::tf32 128 x n x 8 instructions issued from one CTA ----
+ * a_shift: the A operand starts that many 128-byte rows into its 1024-byte swizzle atom (the row-shifted tap windows of the
+ * halo convolutions); a_mn / b_mn: MN-major operands; rotate: distinct A windows cycled through.  cycles_out: one device
+ * int64 (SM clocks from the first issue to the completion of the final commit).  scripts/mma_microbench.py sweeps it. */
+int flb_mma_microbench(int n, int a_shift, int a_mn, int b_mn, int rotate, int reps, long long* cycles_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,7 +115,7 @@ def test_q8_scale_from_the_dp_pass_is_bit_identical(cuda_device):
     z = torch.zeros((K, ld), device=cuda_device)                     # sigma * 0: the upload is global + clipped delta
     up_a, norms_a = ops.dp_clip_noise(local, glob, 0.5, 4.8448, seed=1, z=z, P=P)
     up_b, norms_b, absmax = ops.dp_clip_noise(local, glob, 0.5, 4.8448, seed=1, z=z, P=P, absmax_seg=seg)
-    assert torch.equal(up_a, up_b) and torch.equal(norms_a, norms_b)
+    assert torch.equal(up_a[:, :P], up_b[:, :P]) and torch.equal(norms_a, norms_b)      # columns past P are never written
     want = torch.stack([up_a[:, offs[i]:offs[i + 1]].abs().max(dim=1).values for i in range(len(offs) - 1)], dim=1)
     assert torch.equal(absmax.view(torch.float32), want)
     qa, sa, za = ops.q8_quantize(up_a, seg, P=P)

@@ -95,8 +95,15 @@ def test_validation_loader_leaves_optimizer_state_alone(cuda_device):
         out.append(({k: v.cpu() for k, v in model.get_model_weights().items()}, m))
     w = {a: b.clone() for a, b in OM.init_weights(MODEL, 12).items()}
     OT.train_local_model(MODEL, w, batches, 3, 1e-3, "adam")
+    # with == without validation, up to the run-to-run noise of Adam (atomic accumulation order flips the sign of a +-lr step
+    # on near-zero gradients): compared on the scale of the accumulated update.  A validation pass that advanced the step
+    # count would change every bias correction (tens of per cent of the update).
+    w0 = OM.init_weights(MODEL, 12)
+    num = sum(float(((out[1][0][n] - out[0][0][n]).double() ** 2).sum()) for n in w)
+    den = sum(float(((out[0][0][n] - w0[n]).double() ** 2).sum()) for n in w)
+    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
     for name in w:
-        torch.testing.assert_close(out[1][0][name], out[0][0][name], rtol=0, atol=2e-5)       # with == without validation
+        assert float((out[1][0][name] - out[0][0][name]).abs().max()) <= 2e-3
         assert float((out[1][0][name] - w[name]).abs().max()) <= 5e-3       # Adam, 15 steps of +-lr: conftest.adam_trajectory_check scale
     assert abs(out[1][1].loss - out[0][1].loss) < 1e-5
 
