@@ -59,6 +59,7 @@ SIGNATURES = {
     "flb_train_forward": [_vp, _vp],
     "flb_train_advance": [_vp, _vp],
     "flb_train_step_launches": [_vp],
+    "flb_debug_trace_set": [_vp, _i],
     "flb_mma_microbench": [_i, _i, _i, _i, _i, _i, _vp, _vp],
     "flb_train_step_profiled": [_vp, _vp, C.c_char_p, _i, _vp, _i],
 }

@@ -21,6 +21,8 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("FLB_TRACE") == "1":          # per-role timeline of the resident conv kernels (scripts/conv_timeline.py)
+    NVCC_FLAGS.append("-DFLB_TRACE=1")
 
 
 def _nvcc() -> str:

@@ -88,7 +88,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {           // the a
 //       rows of 128 B (32 fp32 along M/N), consecutive K indices 128 B apart, 32-byte chunks XOR-ed with (row % 4);
 //       4-K groups `sbo` apart (512 when dense), 32-element M/N chunks `lbo` apart.
 //       Matches TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t smem_desc_raw(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout_type) {
+__host__ __device__ constexpr uint64_t smem_desc_raw(uint32_t addr, uint32_t lbo, uint32_t sbo, uint64_t layout_type) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout_type << 61);
 }
@@ -166,6 +166,28 @@ constexpr int BSZ_TAB = 1024;                        // flb_train_args.K <= 1024
 __device__ __forceinline__ void fill_bsz_table(const flb_train_args& a, int* tab) {
     for (int c = threadIdx.x; c < a.K && c < BSZ_TAB; c += blockDim.x) tab[c] = flb_bsz(a, c);
     // visible to all roles after the kernel's first __syncthreads()
+}
+
+// ---- per-role timeline of one CTA (profiling aid; flb_debug_trace_enable / _read in train_api.cu) -------------------------
+// When enabled, CTA 0 of the resident-weight convolution kernels appends (event id, tile, clock64) records: the only way to
+// see which of the three decoupled roles a tile is actually waiting for (ncu's warp-state samples cannot tell a producer
+// that waits for a free stage from one that waits for memory).
+struct TraceBuf { int n; int cap; long long rec[1]; };          // rec[3*i] = event, rec[3*i+1] = tile, rec[3*i+2] = clock
+static __device__ TraceBuf* g_trace = nullptr;      // per translation unit (no -rdc): set by flb_debug_trace_set in train_tc.cu
+// Every recording warp owns cap / 8 consecutive slots and counts them in a register (`slot`): three plain stores per event,
+// no atomic round trip in the timed code.  Unused slots stay zero (the buffer is cleared by the host).
+// Compiled in only with -DFLB_TRACE=1 (FLB_TRACE=1 python -m flb200.build --force): the product build carries no trace code.
+#ifndef FLB_TRACE
+#define FLB_TRACE 0
+#endif
+__device__ __forceinline__ void trace_event(TraceBuf* tb, int& slot, int ev, int tile) {
+#if FLB_TRACE
+    if (!tb) return;
+    // slot = (first record index of this warp's region) + count, kept in a register; the region's capacity is cap / 8 - 1
+    long long* r = tb->rec + 3 * (long long)slot;
+    r[0] = ev; r[1] = tile; r[2] = clock64();
+    ++slot;
+#endif
 }
 
 // optional Traits::finish(p, lane): called once by every epilogue warp after its last tile (persistent skeletons)
@@ -346,9 +368,40 @@ __global__ void __launch_bounds__(THREADS, T::MINB) gemm_persistent_kernel(const
 // Halo convolution with RESIDENT weights: like the persistent kernel, but each CTA owns a contiguous range of tiles
 // (consecutive tiles belong to the same client), keeps that client's whole tap-major weight tensor in shared memory and
 // streams only the activation boxes; the weights are re-loaded (w_full / w_empty handshake) when the client changes.
-// Extra Traits members: W_BYTES; load_w(p, wres, bar); load_a(p, kb, stage, bar); mma(kb, stage_addr, wres_addr, tmem).
+// Extra Traits members: W_BYTES; EPI_WARPS (4 or 8); tile_place(p, client, m0, live_rows) -> num_kb; load_w(p, wres, bar);
+// load_a(p, kb, stage, bar); mma(kb, stage_addr, wres_addr, tmem); epilogue(p, tmem, quarter, lane, part, nparts).
+//
+// Tile walk.  A CTA's tiles are consecutive, so (client, first row m0) advance incrementally -- no division, no global
+// load and no look-ahead call per tile.  (A per-role timeline of this kernel, scripts/conv_timeline.py, showed the MMA warp
+// spending ~1900 of its ~6600 cycles per tile of SimpleCNN's conv2 dgrad in tile_setup() -- an integer division by a
+// run-time tile count plus constant-bank reloads, twice per tile because the weight hand-back looked one tile ahead.)
+// Tiles at or past a client's live rows (ragged last batch, finished clients) are skipped by jumping to the next client.
+struct TileWalk {
+    int tile, t1, tpc, client, m0, rows_pc, pp;
+    const int* bsz;
+    __device__ __forceinline__ void init(int t0, int t1_, int rows_per_client, int rows_per_image, const int* bsz_tab) {
+        tile = t0; t1 = t1_; rows_pc = rows_per_client; pp = rows_per_image; bsz = bsz_tab;
+        tpc = (rows_pc + 127) >> 7;
+        client = t0 / tpc;                                     // the one division of the kernel
+        m0 = (t0 - client * tpc) << 7;
+    }
+    // positions on the next live tile; false when the range is exhausted.  live = live rows of `client`
+    __device__ __forceinline__ bool seek(int& live) {
+        while (tile < t1) {
+            live = bsz[client] * pp;
+            if (m0 < live) return true;
+            tile = (client + 1) * tpc; ++client; m0 = 0;        // nothing (more) to do for this client
+        }
+        return false;
+    }
+    __device__ __forceinline__ void advance() {
+        ++tile; m0 += 128;
+        if (m0 >= (tpc << 7)) { m0 = 0; ++client; }
+    }
+};
+
 template <class T>
-__global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_constant__ typename T::Params p) {
+__global__ void __launch_bounds__(64 + 32 * T::EPI_WARPS, 1) conv_resident_kernel(const __grid_constant__ typename T::Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* wres = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* stages = wres + T::W_BYTES;
@@ -357,13 +410,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
     __shared__ int s_bsz[BSZ_TAB];
     fill_bsz_table(p.a, s_bsz);
     constexpr int TCOLS = 2 * T::ACC_COLS <= 32 ? 32 : (2 * T::ACC_COLS <= 64 ? 64 : (2 * T::ACC_COLS <= 128 ? 128 : (2 * T::ACC_COLS <= 256 ? 256 : 512)));
+    static_assert(T::EPI_WARPS == 4 || T::EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quarter");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = T::num_tiles(p);
     const int t0 = (int)((long long)blockIdx.x * ntiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < T::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], T::EPI_WARPS); }
         mbar_init(&wfull_bar, 1);
         mbar_init(&wempty_bar, 1);
         fence_barrier_init();
@@ -375,82 +429,99 @@ __global__ void __launch_bounds__(THREADS, 1) conv_resident_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base;
+    TraceBuf* tb = (FLB_TRACE && blockIdx.x == 0 && lane == 0) ? g_trace : nullptr;      // one recorder lane per warp of CTA 0
+    int slot = 0, slot_base = 0;
+    if (tb) {                                                  // resume after the previous traced kernel (a region's last record holds its count)
+        slot_base = (threadIdx.x >> 5) * (tb->cap >> 3);
+        slot = slot_base + (int)tb->rec[3 * (slot_base + (tb->cap >> 3) - 1)];
+    }
+    trace_event(tb, slot, 1, warp);                            // 1: role loops start
 
+    TileWalk w;
+    w.init(t0, t1, p.a.B * p.g.PP(), p.g.PP(), s_bsz);
+    int live = 0;
     if (warp == 0) {                                           // all lanes run the loop; one elected lane issues (see gemm_kernel)
         T t;
-        t.bsz_tab = s_bsz;
         t.lead = elect_one();
         uint32_t it = 0, wuse = 0;
         int cur = -1;
-        for (int tile = t0; tile < t1; ++tile) {
-            int num_kb = 0;
-            if (!t.tile_setup(p, tile, num_kb)) continue;
-            if (t.client != cur) {
+        for (; w.seek(live); w.advance()) {
+            const int num_kb = t.tile_place(p, w.client, w.m0, live);
+            if (w.client != cur) {
                 mbar_wait(&wempty_bar, (wuse & 1) ^ 1);                // every MMA that read the old weights has completed
                 t.load_w(p, wres, &wfull_bar);
                 __syncwarp();
-                cur = t.client;
+                cur = w.client;
                 ++wuse;
+                trace_event(tb, slot, 10, w.tile);                   // 10: weight load issued
             }
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 t.load_a(p, kb, stages + (size_t)s * T::STAGE_BYTES, &full_bar[s]);
                 __syncwarp();
+                trace_event(tb, slot, 11, w.tile);                   // 11: activation box issued (after the stage was free)
             }
         }
     } else if (warp == 1) {
-        T t, tn;
-        t.bsz_tab = s_bsz;
-        tn.bsz_tab = s_bsz;
+        T t;
         t.lead = elect_one();
         uint32_t it = 0, nt = 0, wuse = 0;
         int cur = -1;
-        for (int tile = t0; tile < t1; ++tile) {
-            int num_kb = 0;
-            if (!t.tile_setup(p, tile, num_kb)) continue;
-            if (t.client != cur) {
+        for (; w.seek(live); w.advance()) {
+            trace_event(tb, slot, 27, w.tile);                       // 27: next tile found
+            const int num_kb = t.tile_place(p, w.client, w.m0, live);
+            if (w.client != cur) {
                 mbar_wait(&wfull_bar, wuse & 1);
-                cur = t.client;
+                cur = w.client;
                 ++wuse;
+                trace_event(tb, slot, 20, w.tile);                   // 20: weights landed
             }
             const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
+            trace_event(tb, slot, 28, w.tile * 2 + acc);             // 28: about to wait for the accumulator (tile * 2 + acc)
             mbar_wait(&tempty_bar[acc], aph ^ 1);
+            trace_event(tb, slot, 29, w.tile);                       // 29: accumulator wait over
             tc_fence_after();
+            trace_event(tb, slot, 21, w.tile);                       // 21: accumulator free
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const uint32_t s = it % T::STAGES, ph = (it / T::STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                trace_event(tb, slot, 22, w.tile);                   // 22: activation box landed
                 t.mma(kb, smem_u32(stages + (size_t)s * T::STAGE_BYTES), smem_u32(wres), tmem + acc * T::ACC_COLS);
                 if (t.lead) mma_commit(&empty_bar[s]);
                 __syncwarp();
+                trace_event(tb, slot, 23, w.tile);                   // 23: MMAs of the k-block issued
             }
             if (t.lead) mma_commit(&tfull_bar[acc]);
             ++nt;
-            // hand the weight buffer back when the next live tile belongs to another client
-            int nxt = tile + 1, nkb = 0;
-            while (nxt < t1 && !tn.tile_setup(p, nxt, nkb)) ++nxt;
-            if (nxt < t1 && tn.client != cur && t.lead) mma_commit(&wempty_bar);
+            // Hand the weight buffer back after the client's last live tile (the producer waits for this only if it has
+            // another client's weights to load; a hand-back nobody waits for is harmless).
+            if (w.m0 + 128 >= live && t.lead) mma_commit(&wempty_bar);
             __syncwarp();
+            trace_event(tb, slot, 24, w.tile);                       // 24: tile handed to the epilogue
         }
     } else {
         T t;
-        t.bsz_tab = s_bsz;
         uint32_t nt = 0;
-        for (int tile = t0; tile < t1; ++tile) {
-            int num_kb = 0;
-            if (!t.tile_setup(p, tile, num_kb)) continue;
+        const int part = (warp - 2) >> 2;
+        for (; w.seek(live); w.advance()) {
+            t.tile_place(p, w.client, w.m0, live);
             const uint32_t acc = nt & 1, aph = (nt >> 1) & 1;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
-            t.epilogue(p, tmem + acc * T::ACC_COLS, warp & 3, lane);
+            if (warp == 2) trace_event(tb, slot, 30, w.tile);        // 30: accumulator complete (MMAs done)
+            t.epilogue(p, tmem + acc * T::ACC_COLS, warp & 3, lane, part, T::EPI_WARPS / 4);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (warp == 2) trace_event(tb, slot, 31, w.tile);        // 31: epilogue of the tile done
             ++nt;
         }
         call_finish(t, p, lane, 0);
     }
+    trace_event(tb, slot, 2, warp);                            // 2: role done
+    if (tb) tb->rec[3 * (slot_base + (tb->cap >> 3) - 1)] = slot - slot_base;
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TCOLS>(tmem);

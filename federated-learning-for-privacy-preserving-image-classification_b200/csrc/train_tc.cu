@@ -115,10 +115,17 @@ struct ConvFwdT {
         num_kb = NKB;
         return true;
     }
+    // resident-weight skeleton: the tile walk (tc_gemm.cuh TileWalk) hands over the placement, nothing is recomputed
+    __device__ __forceinline__ int tile_place(const Params& p, int client_, int m0_, int live_rows_) {
+        client = client_; m0 = m0_; live_rows = live_rows_;
+        row0 = client * p.a.B * p.g.PP();
+        return NKB;
+    }
     static constexpr int CH = CIN / 32, NKB = 9 * CH, A_BYTES = 128 * 128, B_BYTES = COUT * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = COUT > 64 ? 3 : 4, RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<COUT>::value, MINB = 2;
     int client, m0, row0, live_rows = 0;
+    int epart = 0, enparts = 1;      // this epilogue warp handles the 32-column chunks c with c % enparts == epart
     // fused BatchNorm statistics: lane j of every epilogue warp carries the partial (sum, sum of squares) of column
     // 32 * chunk + j over the rows that warp has seen for client `bclient`
     // ROWACC (COUT = 32): the sums stay per ROW LANE (2 x 32 registers) across tiles and are transposed only when they are
@@ -138,6 +145,7 @@ struct ConvFwdT {
         double* A = p.bn_acc + (long long)bclient * 4 * p.bn_stride + p.bn_coff + lane;
 #pragma unroll
         for (int ch = 0; ch < COUT / 32; ++ch) {
+            if (ch % enparts != epart) continue;                // another epilogue warp of this lane quarter owns the chunk
             atomicAdd(A + ch * 32, (double)bs0[ch]);
             atomicAdd(A + p.bn_stride + ch * 32, (double)bs1[ch]);
             bs0[ch] = 0.f; bs1[ch] = 0.f;
@@ -170,7 +178,11 @@ struct ConvFwdT {
         for (int k = 0; k < 4; ++k)
             if (this->lead) mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc(stage + A_BYTES + k * 32, 16, 1024), id, kb > 0 || k > 0);
     }
-    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
+    // part / nparts: with two epilogue warps per TMEM lane quarter (conv_resident_kernel, EPI_WARPS = 8) each takes every
+    // second 32-column chunk -- the pooled epilogue is a chain of ~14 dependent instructions per channel and set the tile
+    // rate with four warps (3850 of 4400 cycles per tile, scripts/conv_timeline.py)
+    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane, int part = 0, int nparts = 1) {
+        epart = part; enparts = nparts;
         const int m = m0 + quarter * 32 + lane;
         const float* bias = p.a.W + (long long)client * p.a.ld + p.boff;
         if (POOL) {
@@ -182,7 +194,7 @@ struct ConvFwdT {
             float* o = p.pool_out + kb * (COUT * 49) + pp;
             uint8_t* oi = p.pool_idx + kb * (COUT * 49) + pp;
 #pragma unroll 1
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
+            for (int c0 = part * 32; c0 < COUT; c0 += 32 * nparts) {
                 float v[32];
                 ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
 #pragma unroll
@@ -216,6 +228,7 @@ struct ConvFwdT {
         }
 #pragma unroll
         for (int c0 = 0; c0 < COUT; c0 += 32) {
+            if ((c0 / 32) % nparts != part) continue;
             float v[32];
             ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
 #pragma unroll
@@ -268,6 +281,11 @@ struct ConvDgradT {
         num_kb = NKB;
         return true;
     }
+    __device__ __forceinline__ int tile_place(const Params& p, int client_, int m0_, int) {
+        client = client_; m0 = m0_;
+        row0 = client * p.a.B * p.g.PP();
+        return NKB;
+    }
     static constexpr int CH = COUT / 32, NKB = 9 * CH, NCH = CIN / 32, A_BYTES = 128 * 128, B_BYTES = NCH * 4096;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES, STAGES = CIN > 64 ? 3 : 4, RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<CIN>::value, MINB = 2;
@@ -297,12 +315,12 @@ struct ConvDgradT {
         for (int k = 0; k < 4; ++k)
             if (this->lead) mma_tf32(tmem, smem_desc(stage + k * 32, 16, 1024), smem_desc_mn(stage + A_BYTES + k * 1024, 4096, 512), id, kb > 0 || k > 0);
     }
-    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
+    __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane, int part = 0, int nparts = 1) {
         const int m = m0 + quarter * 32 + lane;
         float* dx = p.dx_all + ((long long)row0 + m) * CIN;
         const bool ok = m < p.a.B * p.g.PP();
 #pragma unroll 1
-        for (int c0 = 0; c0 < CIN; c0 += 32) {
+        for (int c0 = part * 32; c0 < CIN; c0 += 32 * nparts) {
             float v[32];
             ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
             if (ok) {
@@ -326,14 +344,14 @@ struct ConvFwdHaloT : ConvFwdT<CIN, COUT, POOL, 1> {         // one accumulator:
     using Base = ConvFwdT<CIN, COUT, POOL, 1>;
     using Params = typename Base::Params;
     static constexpr int CH = CIN / 32, W_BYTES = CH * 9 * COUT * 128, STAGE_BYTES = HALO_A_BYTES;
-    static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
+    static constexpr int FIT = (222 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
     static_assert(STAGES >= 2, "resident weights leave no room for the activation pipeline");
+    static constexpr int EPI_WARPS = COUT >= 64 ? 8 : 4;         // two epilogue warps per TMEM lane quarter once there are two column chunks
     int wp;
-    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
-        const bool ok = Base::tile_setup(p, tile, num_kb);
-        num_kb = CH;
+    __device__ __forceinline__ int tile_place(const Params& p, int client_, int m0_, int live_rows_) {
+        Base::tile_place(p, client_, m0_, live_rows_);
         wp = p.g.Wp;
-        return ok;
+        return CH;
     }
     __device__ void load_w(const Params& p, uint8_t* wres, uint64_t* bar) {
         if (this->lead) mbar_expect_tx(bar, W_BYTES);
@@ -367,14 +385,14 @@ struct ConvDgradHaloT : ConvDgradT<CIN, COUT, 3> {
     using Base = ConvDgradT<CIN, COUT, 3>;
     using Params = typename Base::Params;
     static constexpr int CH = COUT / 32, NCH = CIN / 32, W_BYTES = CH * 9 * NCH * 4096, STAGE_BYTES = HALO_A_BYTES;
-    static constexpr int FIT = (226 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
+    static constexpr int FIT = (222 * 1024 - W_BYTES) / STAGE_BYTES, STAGES = FIT > 4 ? 4 : FIT;
     static_assert(STAGES >= 2, "resident weights leave no room for the activation pipeline");
+    static constexpr int EPI_WARPS = CIN >= 64 ? 8 : 4;
     int wp;
-    __device__ bool tile_setup(const Params& p, int tile, int& num_kb) {
-        const bool ok = Base::tile_setup(p, tile, num_kb);
-        num_kb = CH;
+    __device__ __forceinline__ int tile_place(const Params& p, int client_, int m0_, int live_rows_) {
+        Base::tile_place(p, client_, m0_, live_rows_);
         wp = p.g.Wp;
-        return ok;
+        return CH;
     }
     __device__ void load_w(const Params& p, uint8_t* wres, uint64_t* bar) {
         if (this->lead) mbar_expect_tx(bar, W_BYTES);
@@ -845,7 +863,7 @@ static int launch_resident(const typename T::Params& p, cudaStream_t st) {
     if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(&conv_resident_kernel<T>), (int)smem)) return rc;
     const int tiles = T::num_tiles(p);
     const int grid = tiles < flb_num_sms() ? tiles : flb_num_sms();
-    conv_resident_kernel<T><<<grid, THREADS, smem, st>>>(p);
+    conv_resident_kernel<T><<<grid, 64 + 32 * T::EPI_WARPS, smem, st>>>(p);
     return FLB_OK;
 }
 
@@ -1077,3 +1095,15 @@ int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int i
 }
 
 }  // namespace tc
+
+// ---- per-role timeline of the resident-weight convolution kernels (tc_gemm.cuh TraceBuf; profiling aid) ----------------
+// buf: device memory of 8 + 24 * cap bytes ([int n][int cap][cap x (event, tile, clock) int64]), zeroed by the caller; NULL
+// disables.  Each of the CTA's warps records into its own eighth of the buffer; a region's last record holds its count.
+extern "C" int flb_debug_trace_set(void* buf, int cap) {
+    if (buf) {
+        const int hdr[2] = {0, cap};
+        FLB_CUDA(cudaMemcpy(buf, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    }
+    FLB_CUDA(cudaMemcpyToSymbol(tc::g_trace, &buf, sizeof(void*)));
+    return FLB_OK;
+}

@@ -185,6 +185,11 @@ int flb_train_advance(const flb_train_args* a, void* stream);
 /* forward + loss/gradients only (no optimizer, no counter advance): fills G and the workspace, for parity tests */
 int flb_train_forward_backward(const flb_train_args* a, void* stream);
 
+/* ---- profiling aid: per-role timeline of CTA 0 of the resident-weight convolution kernels (csrc/tc_gemm.cuh TraceBuf).
+ * buf: device memory, 8 + 24*cap bytes = [int n][int cap][cap x (event, tile, SM clock) int64]; NULL switches it off.
+ * Synchronous (cudaMemcpyToSymbol).  scripts/conv_timeline.py prints the trace of one conv2 forward / dgrad launch. */
+int flb_debug_trace_set(void* buf, int cap);
+
 /* ---- profiling aid: cycles of `reps` back-to-back tcgen05.mma kind::tf32 128 x n x 8 instructions issued from one CTA ----
  * a_shift: the A operand starts that many 128-byte rows into its 1024-byte swizzle atom (the row-shifted tap windows of the
  * halo convolutions); a_mn / b_mn: MN-major operands; rotate: distinct A windows cycled through.  cycles_out: one device
