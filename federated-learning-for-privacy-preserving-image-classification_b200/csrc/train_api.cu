@@ -218,7 +218,7 @@ int num_params(const flb_train_args& a) { return a.model == 0 ? simplecnn::num_p
 
 TcConvTab tab_of(const flb_train_args& a, bool step = false) {
     TcConvTab t;
-    if (a.model == 0) simplecnn::tc_tab(a, &t, step); else cifar::tc_tab(a, &t);
+    if (a.model == 0) simplecnn::tc_tab(a, &t, step); else cifar::tc_tab(a, &t, step);
     return t;
 }
 int repack_blocks(const flb_train_args& a, const TcConvTab& t) {
@@ -263,7 +263,7 @@ extern "C" int flb_train_advance(const flb_train_args* a, void* stream) {
 }
 
 static int fwd_bwd(const flb_train_args& a, cudaStream_t st, bool zero_first, bool step = false) {
-    return a.model == 0 ? simplecnn::forward_backward(a, st, zero_first, step) : cifar::forward_backward(a, st);
+    return a.model == 0 ? simplecnn::forward_backward(a, st, zero_first, step) : cifar::forward_backward(a, st, step);
 }
 
 extern "C" int flb_train_forward_backward(const flb_train_args* a, void* stream) {

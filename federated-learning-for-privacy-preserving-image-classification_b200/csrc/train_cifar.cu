@@ -25,6 +25,9 @@ int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, con
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st, bool adam = false);
+}
+#include <stdlib.h>
+namespace tc {
 }  // namespace tc
 
 namespace {
@@ -985,10 +988,16 @@ void lin_dgrad(Ctx& c, const float* dout, float* dact, int In, int Out, int woff
     LinDgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.dout_all = dout; p.dact_all = dact;
     simt::launch(p, a.B, In, 1, a.K, st);
 }
-void lin_wgrad(Ctx& c, const float* dout, const float* act, int In, int Out, int woff) {
+// fc1.weight (71 % of the model): optimizer step applied in the wgrad epilogue instead of a gradient round trip through
+// HBM -- opt-in (FLB_FUSED_ADAM=1), training step only, after the layer's dgrad has read the old weights
+bool fuse_fc1_adam(const flb_train_args& a, bool step) {
+    static const bool on = getenv("FLB_FUSED_ADAM") != nullptr;
+    return step && on && a.dp_mode == 0 && a.B % 8 == 0 && cifar_tc(a, TC_FC1_BIT + TC_WGRAD);
+}
+void lin_wgrad(Ctx& c, const float* dout, const float* act, int In, int Out, int woff, bool adam = false) {
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
     if (a.B % 8 == 0 && cifar_tc(a, (In == 2048 ? TC_FC1_BIT : TC_FC2_BIT) + TC_WGRAD)) {        // its K extent is the batch: whole 8-row MMA steps
-        if (int rc = tc::fc_wgrad(a, dout, act, In, Out, woff, st)) c.rc = rc;
+        if (int rc = tc::fc_wgrad(a, dout, act, In, Out, woff, st, adam)) c.rc = rc;
         return;
     }
     LinWgradProb p{}; p.a = a; p.In = In; p.Out = Out; p.woff = woff; p.boff = 0; p.dout_all = dout; p.act_all = act; p.coef_all = nullptr;
@@ -1055,7 +1064,7 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     return FLB_OK;
 }
 
-int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
+int forward_backward_impl(const flb_train_args& a, cudaStream_t st, bool step) {
     CifarWs ws;
     carve(a.ws, a.K, a.B, &ws);
     const int K = a.K, B = a.B;
@@ -1071,8 +1080,8 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st) {
     lin_dgrad(cx, ws.dh2, ws.dh1, 512, 256, kNet.f2w);
     fc1_mask_bias_kernel<<<K, 512, 0, st>>>(a, ws);
     MARK("fc23_bwd");
-    lin_wgrad(cx, ws.dh1, ws.a, 2048, 512, kNet.f1w);
-    lin_dgrad(cx, ws.dh1, ws.da, 2048, 512, kNet.f1w);
+    lin_dgrad(cx, ws.dh1, ws.da, 2048, 512, kNet.f1w);                 // before the wgrad: with the fused optimizer that one overwrites W
+    lin_wgrad(cx, ws.dh1, ws.a, 2048, 512, kNet.f1w, fuse_fc1_adam(a, step));
     MARK("fc1_bwd");
 
     // block 3 (8x8, 128 channels)
@@ -1139,11 +1148,12 @@ int forward(const flb_train_args& a, cudaStream_t st) {
     carve(a.ws, a.K, a.B, &ws);
     return forward_impl(a, ws, st);
 }
-int forward_backward(const flb_train_args& a, cudaStream_t st) { return forward_backward_impl(a, st); }
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool step) { return forward_backward_impl(a, st, step); }
 // forward 21 + backward 29 launches (conv1 carries its own BatchNorm statistics); on the tensor-core path three more
 // statistic passes ride in the conv epilogues
 int step_launches(const flb_train_args& a) { return 21 + 29 - (a.precision == 1 ? 3 : 0); }
-void tc_tab(const flb_train_args& a, TcConvTab* t) {
+void tc_tab(const flb_train_args& a, TcConvTab* t, bool step) {
+    if (fuse_fc1_adam(a, step)) { t->skip_lo = kNet.f1w; t->skip_hi = kNet.f1b; }
     if (a.precision != 1) return;
     CifarWs ws;
     carve(a.ws, a.K, a.B, &ws);

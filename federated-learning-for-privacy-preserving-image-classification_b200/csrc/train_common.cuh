@@ -127,9 +127,9 @@ long long bn_floats();
 long long ws_bytes(int K, int B);
 long long ws_offset(int K, int B, const char* name);
 int forward(const flb_train_args& a, cudaStream_t st);
-int forward_backward(const flb_train_args& a, cudaStream_t st);
+int forward_backward(const flb_train_args& a, cudaStream_t st, bool step = false);
 int step_launches(const flb_train_args& a);
-void tc_tab(const flb_train_args& a, TcConvTab* t);
+void tc_tab(const flb_train_args& a, TcConvTab* t, bool step = false);
 }
 
 static inline size_t flb_align256(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -756,11 +756,12 @@ template <int IN, bool ADAM>
 struct FcWgradSwapT {
     struct Params { CUtensorMap map_dout; CUtensorMap map_act; flb_train_args a; int woff; };
     bool lead = false;
-    static constexpr int OUT = 128;
+    static constexpr int OUT = 128;      // output features per CTA (blockIdx.z walks the layer's 128-feature groups)
     static constexpr int STAGES = 1, STAGE_BYTES = 8 * 4096, RESIDENT_BYTES = 0, TMEM_COLS = 128, MINB = 2;
-    int client, n0, ksteps;
+    int client, n0, ksteps, j0;
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
+        j0 = blockIdx.z * OUT;
         if (flb_bsz(p.a, client) == 0) return false;
         n0 = blockIdx.x * 128;           // input-feature tile (the last one is partial: TMA zero-fills the columns past IN)
         ksteps = p.a.B / 8;
@@ -774,7 +775,7 @@ struct FcWgradSwapT {
 #pragma unroll
         for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_act, stage + c * 4096, bar, n0 + 32 * c, client * p.a.B);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_dout, stage + 4 * 4096 + c * 4096, bar, 32 * c, client * p.a.B);
+        for (int c = 0; c < 4; ++c) if (this->lead) tma_load_2d(&p.map_dout, stage + 4 * 4096 + c * 4096, bar, j0 + 32 * c, client * p.a.B);
     }
     __device__ void mma(int, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, 128, true, true);
@@ -815,7 +816,7 @@ struct FcWgradSwapT {
     __device__ void epilogue(const Params& p, uint32_t tmem, int quarter, int lane) {
         const int n = n0 + quarter * 32 + lane;               // this thread's input feature
         const bool live = n < IN;
-        const long long off = (long long)client * p.a.ld + p.woff + n;
+        const long long off = (long long)client * p.a.ld + p.woff + (long long)j0 * IN + n;
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16);
         if (ADAM) {
             if (p.a.opt == 0) epilogue_opt<0>(p, taddr, off, live);
@@ -1046,15 +1047,15 @@ static int fc_wgrad_t(const flb_train_args& a, const float* dout, const float* a
     p.a = a; p.woff = woff;
     return launch<T>(p, dim3((IN + 255) / 256, a.K, OUT / 128), st);
 }
-// out = 128 (SimpleCNN fc1): transposed accumulator, coalesced epilogue; ADAM applies the optimizer step instead of storing G
+// transposed accumulator, coalesced epilogue (out a multiple of 128); ADAM applies the optimizer step instead of storing G
 template <int IN, bool ADAM>
-static int fc_wgrad_swap_t(const flb_train_args& a, const float* dout, const float* act, int woff, cudaStream_t st) {
+static int fc_wgrad_swap_t(const flb_train_args& a, const float* dout, const float* act, int woff, int out, cudaStream_t st) {
     using T = FcWgradSwapT<IN, ADAM>;
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, 128, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_dout, dout, (uint64_t)a.K * a.B, out, 32, true)) return rc;
     if (int rc = make_map_2d(&p.map_act, act, (uint64_t)a.K * a.B, IN, 32, true)) return rc;
     p.a = a; p.woff = woff;
-    return launch<T>(p, dim3((IN + 127) / 128, a.K, 1), st);
+    return launch<T>(p, dim3((IN + 127) / 128, a.K, out / 128), st);
 }
 
 // tensor maps of SimpleCNN's fused classifier kernel (fc1_fused.cu): fc1.weight as K-major [128 x 32] boxes and as MN-major
@@ -1081,15 +1082,18 @@ int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, in
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int out, int woff, cudaStream_t st, bool adam) {
     static const bool no_swap = getenv("FLB_FC_WGRAD_NO_SWAP") != nullptr;       // A/B switch for the plain (gradient-storing) variant
     if (in == 3136 && out == 128) {
-        if (adam) return fc_wgrad_swap_t<3136, true>(a, dout, act, woff, st);
-        return no_swap ? fc_wgrad_t<3136, 128>(a, dout, act, woff, st) : fc_wgrad_swap_t<3136, false>(a, dout, act, woff, st);
+        if (adam) return fc_wgrad_swap_t<3136, true>(a, dout, act, woff, out, st);
+        return no_swap ? fc_wgrad_t<3136, 128>(a, dout, act, woff, st) : fc_wgrad_swap_t<3136, false>(a, dout, act, woff, out, st);
+    }
+    if (in == 2048 && out == 512) {
+        if (adam) return fc_wgrad_swap_t<2048, true>(a, dout, act, woff, out, st);
+        return no_swap ? fc_wgrad_t<2048, 512>(a, dout, act, woff, st) : fc_wgrad_swap_t<2048, false>(a, dout, act, woff, out, st);
     }
     if (adam) {
         flb_set_error("tensor-core linear wgrad with the fused optimizer: unsupported shape %d -> %d", in, out);
         return FLB_ERR_UNSUPPORTED;
     }
-    if (in == 2048 && out == 512) return fc_wgrad_t<2048, 512>(a, dout, act, woff, st);
-    if (in == 512 && out == 256) return fc_wgrad_t<512, 256>(a, dout, act, woff, st);
+    if (in == 512 && out == 256) return no_swap ? fc_wgrad_t<512, 256>(a, dout, act, woff, st) : fc_wgrad_swap_t<512, false>(a, dout, act, woff, out, st);
     flb_set_error("tensor-core linear: unsupported shape %d -> %d", in, out);
     return FLB_ERR_UNSUPPORTED;
 }

@@ -60,13 +60,14 @@ def fedavg_weighted_sum_ptrs(ptr_table: torch.Tensor, seg_off: torch.Tensor, w, 
 
 
 def fedavg_weighted_sum_q8(q: torch.Tensor, scale: torch.Tensor, zp: torch.Tensor, seg_off: torch.Tensor, w,
-                           P: int) -> torch.Tensor:
+                           P: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if not (q.is_cuda and q.dtype == torch.uint8):
         raise L.FlbError("fedavg_weighted_sum_q8: q must be a CUDA uint8 tensor")
     L.ensure_device(q.device)
     K, Lyr = q.shape[0], seg_off.numel() - 1
     wt = as_weight_tensor(w, q.device)
-    out = torch.empty(P, dtype=torch.float32, device=q.device)
+    if out is None:
+        out = torch.empty(P, dtype=torch.float32, device=q.device)
     with torch.cuda.device(q.device):
         L.call("flb_fedavg_weighted_sum_q8", L.ptr(q), _row_stride(q), L.ptr(scale), L.ptr(zp), L.ptr(seg_off),
                L.ptr(wt), L.ptr(out), K, Lyr, P, L.stream_ptr(q.device))

@@ -195,10 +195,11 @@ class FederatedRoundEngine:
             rows, self.norms = res[0], res[1]
             absmax = res[2] if len(res) > 2 else None
         w = self.fedavg_weights()
-        if self.compression == "q8":
+        partial = self.global_row[:lay.P]                 # the aggregate is written straight into the global row (every client row was
+        if self.compression == "q8":                      # copied from it at the start of the round; nothing reads it until the next one)
             seg = lay.seg_off(self.device)
             q, scale, zp = ops.q8_quantize(rows, seg, P=lay.P, absmax=absmax)
-            partial = ops.fedavg_weighted_sum_q8(q, scale, zp, seg, w, lay.P)
+            partial = ops.fedavg_weighted_sum_q8(q, scale, zp, seg, w, lay.P, out=partial)
         elif self.compression == "topk":
             # TopKSparsificationCompressor (compression.py:327-365) on every upload: keep the k = max(1, int(n * (1 - sparsity)))
             # largest-magnitude entries of each layer, zeros elsewhere, then FedAvg over the reconstructed rows
@@ -209,13 +210,14 @@ class FederatedRoundEngine:
                 self._topk_meta = kk
             idx, val, off_t, kk_t = ops.topk_select(rows, seg, self._topk_meta, P=lay.P)
             dense = ops.topk_scatter(idx, val, seg, kk_t, off_t, lay.P, lay.ld)
-            partial = ops.fedavg_weighted_sum(dense, w, P=lay.P)
+            ops.fedavg_weighted_sum(dense, w, P=lay.P, out=partial)
         else:
-            partial = ops.fedavg_weighted_sum(rows, w, P=lay.P)
+            ops.fedavg_weighted_sum(rows, w, P=lay.P, out=partial)
         if self.world_size > 1:
+            # the rank's partial sum lands directly in the global row and is all-reduced in place: the collective is the
+            # client -> coordinator hop AND the next round's broadcast; no staging copy on either side of it
             import torch.distributed as dist
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.pg)
-        self.global_row[:lay.P].copy_(partial)
         self.round_number += 1
         self._round_w = w
 
