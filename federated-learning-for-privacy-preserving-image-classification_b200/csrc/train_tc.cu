@@ -126,6 +126,7 @@ struct ConvFwdT {
     static constexpr int TMEM_COLS = Pow2Cols<COUT>::value, MINB = 2;
     int client, m0, row0, live_rows = 0;
     int epart = 0, enparts = 1;      // this epilogue warp handles the 32-column chunks c with c % enparts == epart
+    int pool_tile = 0;               // tiles this epilogue warp has pooled (parity selects the staging buffer)
     // fused BatchNorm statistics: lane j of every epilogue warp carries the partial (sum, sum of squares) of column
     // 32 * chunk + j over the rows that warp has seen for client `bclient`
     // ROWACC (COUT = 32): the sums stay per ROW LANE (2 x 32 registers) across tiles and are transposed only when they are
@@ -186,13 +187,20 @@ struct ConvFwdT {
         const int m = m0 + quarter * 32 + lane;
         const float* bias = p.a.W + (long long)client * p.a.ld + p.boff;
         if (POOL) {
-            // lane = (grid row parity, grid column): window (ph, pw) = lanes {2pw, 2pw+1, 16+2pw, 17+2pw}
+            // lane = (grid row parity, grid column): window (ph, pw) = lanes {2pw, 2pw+1, 16+2pw, 17+2pw}.  A warp's 32
+            // accumulator rows are two grid rows = ONE pooled row of 7 windows; a 128-row tile is half an image.
+            // The pooled values are staged in shared memory ([channel][28 windows of the tile], double-buffered by tile parity)
+            // and written out by all epilogue threads together: for a fixed channel a tile's windows are one contiguous run of
+            // fc1's NCHW-flattened input.  (Storing straight from the owner lanes -- 7 lanes x 4 B per instruction, 512 such
+            // instructions per tile -- made this epilogue the kernel's pacing resource regardless of how many warps shared
+            // it: ~4000 cycles per tile against ~2200 for the tile's MMAs, scripts/conv_timeline.py.)
+            __shared__ float s_val[2][COUT * 28];
+            __shared__ uint8_t s_idx[2][COUT * 28];
             const int b = m >> 8, r = m & 255, h = r >> 4, w = r & 15;
             const bool owner = (lane < 16) && !(lane & 1) && w < 14 && h < 14;
-            const long long kb = (long long)client * p.a.B + b;
-            const int pp = (h >> 1) * 7 + (w >> 1);
-            float* o = p.pool_out + kb * (COUT * 49) + pp;
-            uint8_t* oi = p.pool_idx + kb * (COUT * 49) + pp;
+            const int half = (m0 >> 7) & 1, buf = pool_tile & 1;
+            ++pool_tile;
+            const int j = quarter * 7 + (w >> 1);               // window index within the tile
 #pragma unroll 1
             for (int c0 = part * 32; c0 < COUT; c0 += 32 * nparts) {
                 float v[32];
@@ -208,12 +216,26 @@ struct ConvFwdT {
                         if (x1 > best) { best = x1; bi = 1; }
                         if (x16 > best) { best = x16; bi = 2; }
                         if (x17 > best) { best = x17; bi = 3; }
-                        o[(c0 + i) * 49] = fmaxf(best, 0.f);
-                        oi[(c0 + i) * 49] = (uint8_t)bi;
+                        s_val[buf][(c0 + i) * 28 + j] = fmaxf(best, 0.f);
+                        s_idx[buf][(c0 + i) * 28 + j] = (uint8_t)bi;
                     }
                 }
             }
-            return;
+            // all epilogue warps of the CTA (named barrier 1; warps 0 / 1 are the producer and the MMA issuer)
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * 4 * nparts) : "memory");
+            const long long kb = (long long)client * p.a.B + b;
+            float* o = p.pool_out + kb * (COUT * 49) + half * 28;
+            uint8_t* oi = p.pool_idx + kb * (COUT * 49) + half * 28;
+            const int nvalid = half ? 21 : 28;                   // pooled rows 4..6 in the lower half (row 7 does not exist)
+            const int e0 = (part * 4 + quarter) * 32 + lane, nthr = 128 * nparts;
+            for (int e = e0; e < COUT * 28; e += nthr) {
+                const int c = e / 28, jj = e - c * 28;
+                if (jj < nvalid) {
+                    o[c * 49 + jj] = s_val[buf][e];
+                    oi[c * 49 + jj] = s_idx[buf][e];
+                }
+            }
+            return;                                              // the other buffer is used by the next tile: no second barrier
         }
         float* z = p.z_all + ((long long)row0 + m) * COUT;
         const bool ok = m < p.a.B * p.g.PP();
