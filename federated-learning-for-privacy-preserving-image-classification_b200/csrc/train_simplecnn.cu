@@ -72,10 +72,15 @@ constexpr int WP2 = 16;
 // ------------------------------------------------------------------------------------------------
 // conv1: direct stencil fused with bias + ReLU + 2x2 max-pool; two CTAs per (sample, client), one per half image
 // (pooled rows 0-6 / 7-13), so that 2 * B * K CTAs cover the GPU even at 10 clients.
-__global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, SimpleCnnWs ws) {
+// Lanes = the 32 output channels, warp g = pooled row g of the half: the 4 x 4 input window of a pooling position is the
+// same for all lanes (a shared-memory broadcast) and SLIDES along the row -- only its two new columns are loaded per
+// position, as four 8-byte loads.  (The first version gave each warp every 8th position and re-loaded all 16 window values
+// with 4-byte loads: 208 LDS per thread for 468 FMAs made the kernel MIO-bound, 11 us of SM time for ~3 us of math.)
+constexpr int C1_THREADS = 224;              // 7 warps = 7 pooled rows
+__global__ void __launch_bounds__(C1_THREADS) conv1_fwd_pool_kernel(flb_train_args a, SimpleCnnWs ws) {
     const int b = blockIdx.x >> 1, half = blockIdx.x & 1, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
-    __shared__ float img[16][31];            // input rows 14*half - 1 .. 14*half + 14 with a zero halo
+    __shared__ __align__(16) float img[16][32];   // input rows 14*half - 1 .. 14*half + 14 with a zero halo; col c holds x[.][c - 1]
     __shared__ float w[32][9];
     __shared__ float bias[32];
     const int tid = threadIdx.x;
@@ -83,28 +88,35 @@ __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, S
     const long long s = a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b;
     const float* x = a.x + s * 784;
     const int r0 = 14 * half - 1;
-    for (int i = tid; i < 16 * 30; i += 256) {
-        const int r = i / 30, c = i % 30, gr = r0 + r;
+    for (int i = tid; i < 16 * 32; i += C1_THREADS) {
+        const int r = i >> 5, c = i & 31, gr = r0 + r;
         img[r][c] = (gr >= 0 && gr < 28 && c >= 1 && c <= 28) ? x[gr * 28 + (c - 1)] : 0.f;
     }
-    for (int i = tid; i < 288; i += 256) w[i / 9][i % 9] = W[Off::c1w + i];
+    for (int i = tid; i < 288; i += C1_THREADS) w[i / 9][i % 9] = W[Off::c1w + i];
     if (tid < 32) bias[tid] = W[Off::c1b + tid];
     __syncthreads();
-    const int c = tid & 31, g = tid >> 5;
+    const int c = tid & 31, phl = tid >> 5, ph = half * 7 + phl;
     float wr[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) wr[i] = w[c][i];
     const float bc = bias[c];
     const long long kb = (long long)k * a.B + b;
-    float* outp = ws.a1p + kb * (PP2 * 32);
-    uint8_t* idx = ws.idx1 + kb * (196 * 32);
-    for (int pl = g; pl < 98; pl += 8) {
-        const int phl = pl / 14, pw = pl % 14, ph = half * 7 + phl;
-        float p[4][4];
+    float* outp = ws.a1p + kb * (PP2 * 32) + (ph * WP2) * 32 + c;
+    uint8_t* idx = ws.idx1 + kb * (196 * 32) + (ph * 14) * 32 + c;
+    float p[4][4];                                 // window rows 2*phl .. 2*phl + 3, columns 2*pw .. 2*pw + 3
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = *reinterpret_cast<const float2*>(&img[2 * phl + i][0]);
+        p[i][2] = v.x; p[i][3] = v.y;
+    }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[i][j] = img[2 * phl + i][2 * pw + j];
+    for (int pw = 0; pw < 14; ++pw) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 v = *reinterpret_cast<const float2*>(&img[2 * phl + i][2 * pw + 2]);
+            p[i][0] = p[i][2]; p[i][1] = p[i][3];
+            p[i][2] = v.x; p[i][3] = v.y;
+        }
         float best = -INFINITY;
         int bi = 0;
 #pragma unroll
@@ -118,8 +130,8 @@ __global__ void __launch_bounds__(256) conv1_fwd_pool_kernel(flb_train_args a, S
                     for (int q = 0; q < 3; ++q) v = fmaf(wr[r * 3 + q], p[i + r][j + q], v);
                 if (v > best) { best = v; bi = i * 2 + j; }
             }
-        outp[(ph * WP2 + pw) * 32 + c] = fmaxf(best, 0.f);
-        idx[(ph * 14 + pw) * 32 + c] = (uint8_t)bi;
+        outp[pw * 32] = fmaxf(best, 0.f);
+        idx[pw * 32] = (uint8_t)bi;
     }
 }
 
@@ -483,6 +495,81 @@ __global__ void __launch_bounds__(256, PS ? 2 : 5) conv1_bwd_kernel(flb_train_ar
     }
 }
 
+// conv1 weight + bias gradient without per-sample clipping, one CTA per half sample (pooled rows 0-6 / 7-13), warp g = pooled
+// row g, lanes = channels.  The 4 x 4 input window of a pooling position is loaded ONCE for the whole warp (broadcast 8-byte
+// loads, sliding along the row like conv1_fwd_pool_kernel) and the 3 x 3 patch under each lane's own argmax is picked out of
+// it with register selects.  (conv1_bwd_kernel<false> read the patch straight from shared memory at lane-dependent
+// addresses: 9 conflicting LDS per position -- MIO-bound; measured 15 us for ~2 us of math.)
+__global__ void __launch_bounds__(C1_THREADS, 5) conv1_bwd_rows_kernel(flb_train_args a, SimpleCnnWs ws) {
+    const int b = blockIdx.x >> 1, half = blockIdx.x & 1, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    __shared__ __align__(16) float img[16][32];   // input rows 14*half - 1 .. 14*half + 14 with a zero halo (col c = x column c - 1)
+    __shared__ float part[7][32][10];
+    const int tid = threadIdx.x;
+    const long long s = a.sample_off[k] + (long long)(*a.step_ctr) * a.B + b;
+    const float* x = a.x + s * 784;
+    const int r0 = 14 * half - 1;
+    for (int i = tid; i < 16 * 32; i += C1_THREADS) {
+        const int r = i >> 5, c = i & 31, gr = r0 + r;
+        img[r][c] = (gr >= 0 && gr < 28 && c >= 1 && c <= 28) ? x[gr * 28 + (c - 1)] : 0.f;
+    }
+    const int c = tid & 31, phl = tid >> 5, ph = half * 7 + phl;
+    const long long kb = (long long)k * a.B + b;
+    const float* da1 = ws.da1p + kb * (PP2 * 32) + (ph * WP2) * 32 + c;
+    const float* a1 = ws.a1p + kb * (PP2 * 32) + (ph * WP2) * 32 + c;
+    const uint8_t* idx = ws.idx1 + kb * (196 * 32) + (ph * 14) * 32 + c;
+    // the row's 14 gradient values and argmaxes first: 42 independent coalesced loads in flight
+    float gvv[14];
+    unsigned sel = 0;
+#pragma unroll
+    for (int pw = 0; pw < 14; ++pw) {
+        const float av = a1[pw * 32], dv = da1[pw * 32];
+        gvv[pw] = av > 0.f ? dv : 0.f;
+        sel |= (unsigned)(idx[pw * 32] & 3) << (2 * pw);
+    }
+    __syncthreads();
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+    float p[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = *reinterpret_cast<const float2*>(&img[2 * phl + i][0]);
+        p[i][2] = v.x; p[i][3] = v.y;
+    }
+#pragma unroll
+    for (int pw = 0; pw < 14; ++pw) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 v = *reinterpret_cast<const float2*>(&img[2 * phl + i][2 * pw + 2]);
+            p[i][0] = p[i][2]; p[i][1] = p[i][3];
+            p[i][2] = v.x; p[i][3] = v.y;
+        }
+        const float gv = gvv[pw];
+        const bool down = (sel >> (2 * pw + 1)) & 1, right = (sel >> (2 * pw)) & 1;     // argmax = 2 * (row in window) + (col in window)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float row[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) row[j] = down ? p[r + 1][j] : p[r][j];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[r * 3 + q] = fmaf(gv, right ? row[q + 1] : row[q], acc[r * 3 + q]);
+        }
+        acc[9] += gv;
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) part[phl][c][i] = acc[i];
+    __syncthreads();
+    float* G = a.G + (long long)k * a.ld;
+    for (int e = tid; e < 320; e += C1_THREADS) {
+        const int cc = e / 10, i = e % 10;
+        float v = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 7; ++gg) v += part[gg][cc][i];
+        atomicAdd(i == 9 ? &G[Off::c1b + cc] : &G[Off::c1w + cc * 9 + i], v);
+    }
+}
+
 // dp_mode 1: conv1 gradient = sum_b coef[b] * g1ps[b]
 __global__ void __launch_bounds__(320) conv1_ps_reduce_kernel(flb_train_args a, SimpleCnnWs ws) {
     const int k = blockIdx.x;
@@ -531,7 +618,7 @@ int forward(const flb_train_args& a, const SimpleCnnWs& ws, cudaStream_t st, boo
     const int K = a.K, B = a.B;
     const dim3 per_sample(B, K);
     MARK("begin");          // hpre (split-K accumulator of fc1) is kept at zero by its consumer, head_fwd_bwd_kernel
-    conv1_fwd_pool_kernel<<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
+    conv1_fwd_pool_kernel<<<dim3(2 * B, K), C1_THREADS, 0, st>>>(a, ws);
     MARK("conv1_fwd_pool");
     const int tcm = tc_mask_of(a);
     if (tcm & TC_CONV2_FWD) {          // bias + ReLU + max-pool fused into the GEMM epilogue: z2 is never written
@@ -709,7 +796,7 @@ int forward_backward(const flb_train_args& a, cudaStream_t st, bool zero_first, 
         if (int rc = wgrads_conv2(st)) return rc;
     }
     if (a.dp_mode == 1) conv1_ps_reduce_kernel<<<K, 320, 0, st>>>(a, ws);
-    else conv1_bwd_kernel<false><<<dim3(2 * B, K), 256, 0, st>>>(a, ws);
+    else conv1_bwd_rows_kernel<<<dim3(2 * B, K), C1_THREADS, 0, st>>>(a, ws);
     MARK("conv1_wgrad");
     if (lane) {
         FLB_CUDA(cudaEventRecord(lane->ev[2], lane->s));
