@@ -186,56 +186,68 @@ struct ConvFwdT {
         epart = part; enparts = nparts;
         const int m = m0 + quarter * 32 + lane;
         const float* bias = p.a.W + (long long)client * p.a.ld + p.boff;
-        if (POOL) {
-            // lane = (grid row parity, grid column): window (ph, pw) = lanes {2pw, 2pw+1, 16+2pw, 17+2pw}.  A warp's 32
-            // accumulator rows are two grid rows = ONE pooled row of 7 windows; a 128-row tile is half an image.
-            // The pooled values are staged in shared memory ([channel][28 windows of the tile], double-buffered by tile parity)
-            // and written out by all epilogue threads together: for a fixed channel a tile's windows are one contiguous run of
-            // fc1's NCHW-flattened input.  (Storing straight from the owner lanes -- 7 lanes x 4 B per instruction, 512 such
-            // instructions per tile -- made this epilogue the kernel's pacing resource regardless of how many warps shared
-            // it: ~4000 cycles per tile against ~2200 for the tile's MMAs, scripts/conv_timeline.py.)
-            __shared__ float s_val[2][COUT * 28];
-            __shared__ uint8_t s_idx[2][COUT * 28];
-            const int b = m >> 8, r = m & 255, h = r >> 4, w = r & 15;
-            const bool owner = (lane < 16) && !(lane & 1) && w < 14 && h < 14;
-            const int half = (m0 >> 7) & 1, buf = pool_tile & 1;
-            ++pool_tile;
-            const int j = quarter * 7 + (w >> 1);               // window index within the tile
+        if constexpr (POOL) {
+            // 16-wide grid, 256 rows per image: a 128-row tile is half an image = 8 grid rows = 4 pooled rows of 7 windows.
+            // The accumulator tile goes to shared memory as it is ([row][64 channels], 16-byte chunks XOR-swizzled with the
+            // row so that the 8 lanes of a store phase hit 8 different bank groups); then every epilogue thread pools
+            // (window, channel quad) tasks with four 16-byte loads, and the results are written out coalesced through a small
+            // staging array (for a fixed channel a tile's windows are one contiguous run of fc1's NCHW-flattened input).
+            // MIO instructions per thread and tile: ~60.  (The first version pooled with warp shuffles straight out of the
+            // TMEM registers: 96 SHFL + 32 LDG + 64 STS per thread and 32 channels -- MIO-bound at ~3800 cycles per tile
+            // against ~2200 for the tile's MMAs, unchanged by a second warp per lane quarter or by staging the stores;
+            // scripts/conv_timeline.py.)
+            static_assert(COUT == 64, "pooled epilogue: 64 output channels");
+            __shared__ __align__(16) float s_x[128 * COUT];
+            __shared__ float s_val[COUT * 28];
+            __shared__ uint8_t s_idx[COUT * 28];
+            const int nthr = 128 * nparts, e0 = (part * 4 + quarter) * 32 + lane;       // epilogue thread id
+            const int ml = quarter * 32 + lane;                                       // row within the tile
 #pragma unroll 1
             for (int c0 = part * 32; c0 < COUT; c0 += 32 * nparts) {
                 float v[32];
                 ld_acc(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = v[i] + __ldg(&bias[c0 + i]);
-                    const float x1 = __shfl_xor_sync(0xffffffffu, x, 1), x16 = __shfl_xor_sync(0xffffffffu, x, 16),
-                                x17 = __shfl_xor_sync(0xffffffffu, x, 17);
-                    if (owner) {
-                        float best = x;
-                        int bi = 0;
-                        if (x1 > best) { best = x1; bi = 1; }
-                        if (x16 > best) { best = x16; bi = 2; }
-                        if (x17 > best) { best = x17; bi = 3; }
-                        s_val[buf][(c0 + i) * 28 + j] = fmaxf(best, 0.f);
-                        s_idx[buf][(c0 + i) * 28 + j] = (uint8_t)bi;
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(&s_x[ml * COUT + (((c0 >> 2) + i) ^ (ml & 7)) * 4]) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");         // all epilogue warps (warps 0 / 1 are the producer and the MMA issuer)
+            const int b = m0 >> 8, half = (m0 >> 7) & 1;
+            {
+                const int cq = e0 & 15;                                    // channel quad of this thread's tasks
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 4 * cq));
+                for (int j = e0 >> 4; j < 28; j += nthr >> 4) {            // window j = pooled row (0..3) * 7 + pooled column
+                    const int pr = j / 7, pc = j - pr * 7;
+                    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {                          // (0,0), (0,1), (1,0), (1,1): first maximum wins, like the reference scan
+                        const int r = (2 * pr + (d >> 1)) * 16 + 2 * pc + (d & 1);
+                        const float4 x4 = *reinterpret_cast<const float4*>(&s_x[r * COUT + ((cq ^ (r & 7)) * 4)]);
+                        const float x[4] = {x4.x + bv.x, x4.y + bv.y, x4.z + bv.z, x4.w + bv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (x[e] > best[e]) { best[e] = x[e]; bi[e] = d; }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s_val[(4 * cq + e) * 28 + j] = fmaxf(best[e], 0.f);
+                        s_idx[(4 * cq + e) * 28 + j] = (uint8_t)bi[e];
                     }
                 }
             }
-            // all epilogue warps of the CTA (named barrier 1; warps 0 / 1 are the producer and the MMA issuer)
-            asm volatile("bar.sync 1, %0;" ::"r"(32 * 4 * nparts) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
             const long long kb = (long long)client * p.a.B + b;
             float* o = p.pool_out + kb * (COUT * 49) + half * 28;
             uint8_t* oi = p.pool_idx + kb * (COUT * 49) + half * 28;
             const int nvalid = half ? 21 : 28;                   // pooled rows 4..6 in the lower half (row 7 does not exist)
-            const int e0 = (part * 4 + quarter) * 32 + lane, nthr = 128 * nparts;
             for (int e = e0; e < COUT * 28; e += nthr) {
                 const int c = e / 28, jj = e - c * 28;
                 if (jj < nvalid) {
-                    o[c * 49 + jj] = s_val[buf][e];
-                    oi[c * 49 + jj] = s_idx[buf][e];
+                    o[c * 49 + jj] = s_val[e];
+                    oi[c * 49 + jj] = s_idx[e];
                 }
             }
-            return;                                              // the other buffer is used by the next tile: no second barrier
+            return;                    // the next tile's first barrier orders its writes to s_x / s_val behind this write-out
         }
         float* z = p.z_all + ((long long)row0 + m) * COUT;
         const bool ok = m < p.a.B * p.g.PP();
