@@ -537,9 +537,11 @@ def main():
     if not args.no_extra and args.workload == "mnist_dp" and args.dp_mode == "update":
         extra = {}
         sub_steps = max(3, min(args.steps, 6))
-        for key, name, mode in (("mnist50", "mnist_dp50", "update"), ("cifar100_q8", "cifar_dp_q8", "update"), ("per_sample", "mnist_dp", "per_sample")):
+        for key, name, mode in (("mnist50", "mnist_dp50", "update"), ("cifar100_q8", "cifar_dp_q8", "update"), ("per_sample", "mnist_dp", "per_sample"),
+                                ("cifar100_q8_per_sample", "cifar_dp_q8", "per_sample")):
             try:
-                r = measure_rounds(ctx, name, sub_steps, 3, args.precision, mode, e2e=(key != "cifar100_q8"), breakdown=False)
+                r = measure_rounds(ctx, name, sub_steps if mode == "update" or name == "mnist_dp" else 3, 3, args.precision, mode,
+                                   e2e=not key.startswith("cifar100_q8"), breakdown=False)
                 r.pop("_engine", None)
                 if mode == "per_sample":
                     r["oracle"] = "parity unpinned: no reference implementation of per-sample DP-SGD exists (oracle/dpsgd.py is a restatement)"

@@ -72,6 +72,7 @@ struct ConvWgradProb {
     static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
     flb_train_args a; ConvGeom g;
     const float* dz_all; const float* xin_all; const float* coef_all; int woff, boff;
+    int no_bias;                 // 1: the bias column is left out (CIFAR10CNN per-sample mode: the BatchNorm pass owns it)
     const float* dz; const float* xin; const float* coef; float* gw; float* gb; int Mtot;
     __device__ bool setup(int client, int& M, int& N, int& Kd) {
         const int bsz = flb_bsz(a, client);
@@ -83,7 +84,7 @@ struct ConvWgradProb {
         gw = a.G + (long long)client * a.ld + woff;
         gb = a.G + (long long)client * a.ld + boff;
         Mtot = a.B * g.PP();
-        M = g.Cout; N = 9 * g.Cin + 1; Kd = bsz * g.PP();
+        M = g.Cout; N = 9 * g.Cin + (no_bias ? 0 : 1); Kd = bsz * g.PP();
         return true;
     }
     __device__ float loadA(int m, int k) const {
@@ -110,6 +111,7 @@ struct ConvWgradNormProb {
     static constexpr bool A_MCONTIG = true, B_NCONTIG = true;
     flb_train_args a; ConvGeom g;
     const float* dz_all; const float* xin_all; float* norm2_all;
+    int no_bias;                 // 1: weight gradient only
     const float* dz; const float* xin; float* dst; float sq; int lo, hi;
     __device__ bool setup(int group, int& M, int& N, int& Kd) {
         const int client = group / a.B, b = group % a.B;
@@ -121,7 +123,7 @@ struct ConvWgradNormProb {
         lo = -b * g.PP(); hi = (a.B - b) * g.PP();       // row bounds relative to this sample's first pixel
         xin += (long long)b * g.PP() * g.Cin;
         dst = norm2_all + kb + b;
-        M = g.Cout; N = 9 * g.Cin + 1; Kd = g.PP();
+        M = g.Cout; N = 9 * g.Cin + (no_bias ? 0 : 1); Kd = g.PP();
         return true;
     }
     __device__ float loadA(int m, int k) const { return dz[(long long)k * g.Cout + m]; }

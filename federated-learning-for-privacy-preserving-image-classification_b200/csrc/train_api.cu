@@ -206,10 +206,6 @@ int check_args(const flb_train_args* a) {
     FLB_CHECK_ARG(a->dp_mode == 0 || a->dp_mode == 1, "flb_train: dp_mode must be 0 or 1");
     if (a->model == 1) {
         FLB_CHECK_ARG(a->bn_running != nullptr, "flb_train: cifar10_cnn needs the bn_running buffer");
-        if (a->dp_mode == 1) {
-            flb_set_error("flb_train: per-sample DP is undefined for cifar10_cnn (BatchNorm couples the samples of a batch)");
-            return FLB_ERR_UNSUPPORTED;
-        }
     }
     return FLB_OK;
 }

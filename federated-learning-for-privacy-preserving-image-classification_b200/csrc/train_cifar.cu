@@ -22,6 +22,7 @@ int conv_fwd(const flb_train_args& a, const ConvGeom& g, const float* xin, float
 bool conv_fwd_fuses_stats(int cin, int cout);
 int conv_dgrad(const flb_train_args& a, const ConvGeom& g, const float* dz, float* dx, const float* wt, long long ldt, cudaStream_t st);
 int conv_wgrad(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* gt, long long ldt, cudaStream_t st);
+int conv_wgrad_norm(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st);
 int fc_fwd(const flb_train_args& a, const float* act, float* out, int in, int outf, int woff, int splits, cudaStream_t st);
 int fc_dgrad(const flb_train_args& a, const float* dout, float* dact, int in, int outf, int woff, cudaStream_t st);
 int fc_wgrad(const flb_train_args& a, const float* dout, const float* act, int in, int outf, int woff, cudaStream_t st, bool adam = false);
@@ -88,6 +89,8 @@ struct CifarWs {
     float *d32a, *d32b, *d16p, *d16a, *d16b, *d8p, *d8a, *d8b;
     double* acc;                       // [K][4][448]
     float *wt, *gt;                    // [K][ldt] tap-major conv weights / weight gradients (tensor-core path)
+    float *norm2, *coef;               // [K][B] per-sample squared gradient norms / clip coefficients (dp_mode 1)
+    float* bnps;                       // [K][B][2][448] per-sample BatchNorm (dgamma | dbeta) (dp_mode 1)
 };
 
 size_t carve(void* base, int K, int B, CifarWs* ws) {
@@ -116,6 +119,9 @@ size_t carve(void* base, int K, int B, CifarWs* ws) {
     CARVE(acc, double, (size_t)K * 4 * BN_CH);
     CARVE(wt, float, (size_t)K * kNetLdt);
     CARVE(gt, float, (size_t)K * kNetLdt);
+    CARVE(norm2, float, KB);
+    CARVE(coef, float, KB);
+    CARVE(bnps, float, KB * 2 * BN_CH);
 #undef CARVE
     return off;
 }
@@ -188,7 +194,9 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(flb_train_args a, float*
 }
 
 // dW[c][ci][tap] += sum_px dz[px][c] * x[ci][px + shift(tap)], db[c] += sum_px dz[px][c]
-__global__ void __launch_bounds__(256) conv1_wgrad_kernel(flb_train_args a, const float* dz_all) {
+// NORM (dp_mode 1): the sample's [32][27 + 1] gradient is only squared into norm2[client, sample]
+template <bool NORM>
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(flb_train_args a, const float* dz_all, float* norm2) {
     const int b = blockIdx.x, k = blockIdx.y;
     if (b >= flb_bsz(a, k)) return;
     __shared__ __align__(16) float img[3][34][36];
@@ -224,12 +232,18 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(flb_train_args a, cons
     for (int i = 0; i < 28; ++i) part[g][c][i] = acc[i];
     __syncthreads();
     float* G = a.G + (long long)k * a.ld;
+    float sq = 0.f;
     for (int e = tid; e < 32 * 28; e += 256) {
         const int cc = e / 28, i = e % 28;
         float v = 0.f;
 #pragma unroll
         for (int gg = 0; gg < 8; ++gg) v += part[gg][cc][i];
-        atomicAdd(i == 27 ? &G[kC1B + cc] : &G[kC1W + cc * 27 + i], v);
+        if (NORM) sq = fmaf(v, v, sq);
+        else atomicAdd(i == 27 ? &G[kC1B + cc] : &G[kC1W + cc * 27 + i], v);
+    }
+    if (NORM) {
+        sq = flb_warp_sum(sq);
+        if ((tid & 31) == 0 && sq != 0.f) atomicAdd(&norm2[(long long)k * a.B + b], sq);
     }
 }
 
@@ -570,6 +584,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
     }
 }
 
+// dp_mode 1 (per-sample DP-SGD; the batch statistics are constants of the per-sample backward pass):
+// where a BatchNorm backward reduction runs one CTA per sample, its column sums ARE the sample's (dgamma, dbeta).  They
+// are stored in bnps[client, sample] and their squares -- plus the square of the sample's conv-bias gradient
+// gamma * invstd * dbeta when the layer's conv bias is not covered elsewhere -- join norm2[client, sample].
+struct PsOut { float* bnps; float* norm2; int gwoff; int conv_bias; };       // bnps == nullptr: batched mode (atomics into acc)
+__device__ __forceinline__ void ps_store(const flb_train_args& a, const PsOut& ps, long long kb, int k, int coff, int ch, float t0, float t1,
+                                         float invstd) {
+    float* row = ps.bnps + kb * 2 * BN_CH + coff + ch;
+    row[0] = t0;
+    row[BN_CH] = t1;
+    float sq = fmaf(t0, t0, t1 * t1);
+    if (ps.conv_bias) {
+        const float db = a.W[(long long)k * a.ld + ps.gwoff + ch] * invstd * t1;
+        sq = fmaf(db, db, sq);
+    }
+    sq = flb_warp_sum(sq);                                   // callers: whole warps (C is a multiple of 32)
+    if ((threadIdx.x & 31) == 0 && sq != 0.f) atomicAdd(&ps.norm2[kb], sq);
+}
+
 // ---- BatchNorm backward of the POOLED layers (2, 4, 6) straight from the pooled-side arrays -----------------------------
 // Upstream of a max-pool the gradient is one value per 2x2 window, so the dense dy tensor is never materialised: the
 // reduction reads dpool / pooled / argmax (a quarter of the grid) and gathers z at the argmax positions; the apply kernel
@@ -577,7 +610,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(flb_train_args a, Con
 template <int C, bool FLAT>
 __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
                                                                  const float* pooled_all, const uint8_t* idx_all,
-                                                                 const float* z_all, double* acc, int coff) {
+                                                                 const float* z_all, double* acc, int coff, PsOut ps) {
     const int b = blockIdx.x, k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (b >= bsz) return;
@@ -607,6 +640,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(flb_train_args 
     __syncthreads();
     if (tid < C) {
         for (int i = 1; i < 256 / C; ++i) { s0 += red[0][tid + i * C]; s1 += red[1][tid + i * C]; }
+        if (ps.bnps) { ps_store(a, ps, kb, k, coff, tid, s0, s1, invstd); return; }
         double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
         atomicAdd(A, (double)s0);
         atomicAdd(A + BN_CH, (double)s1);
@@ -620,7 +654,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_kernel(flb_train_args 
 template <int C>
 __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_vec_kernel(flb_train_args a, ConvGeom g, ConvGeom go, const float* dpool_all,
                                                                      const float* pooled_all, const uint8_t* idx_all,
-                                                                     const float* z_all, double* acc, int coff) {
+                                                                     const float* z_all, double* acc, int coff, PsOut ps) {
     const int b = blockIdx.x, k = blockIdx.y;
     const int bsz = flb_bsz(a, k);
     if (b >= bsz) return;
@@ -670,6 +704,7 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_reduce_vec_kernel(flb_train_a
         const int q = tid & 3, cq2 = tid >> 2;
         float t0 = 0.f, t1 = 0.f;
         for (int i = 0; i < PL; ++i) { t0 += red[q][i * C4 + cq2]; t1 += red[4 + q][i * C4 + cq2]; }
+        if (ps.bnps) { ps_store(a, ps, kb, k, coff, tid, t0, t1, s_invstd[tid]); return; }
         double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
         atomicAdd(A, (double)t0);
         atomicAdd(A + BN_CH, (double)t1);
@@ -691,12 +726,13 @@ __global__ void __launch_bounds__(256) bn_pool_bwd_apply_kernel(flb_train_args a
         float mean, invstd, vb;
         bn_moments(a, acc, k, coff + tid, n_real, mean, invstd, vb);
         const double* A = acc + (long long)k * 4 * BN_CH + 2 * BN_CH + coff + tid;
-        const float dgamma = (float)A[0], dbeta = (float)A[BN_CH];
+        const bool ps = a.dp_mode == 1;      // per-sample mode: statistics are constants, dz = gamma * invstd * g; G is written later
+        const float dgamma = ps ? 0.f : (float)A[0], dbeta = ps ? 0.f : (float)A[BN_CH];
         s_mean[tid] = mean; s_invstd[tid] = invstd;
         s_c0[tid] = a.W[(long long)k * a.ld + gwoff + tid] * invstd;
         s_c1[tid] = dbeta / (float)n_real;
         s_c2[tid] = dgamma / (float)n_real;
-        if (b == 0) {
+        if (b == 0 && !ps) {
             float* G = a.G + (long long)k * a.ld;
             G[gwoff + tid] = dgamma;
             G[gboff + tid] = dbeta;
@@ -828,7 +864,7 @@ __global__ void __launch_bounds__(256) head_fwd_bwd_kernel(flb_train_args a, Cif
         float se = 0.f;
         for (int j = 0; j < 10; ++j) se += expf(slog[tid][j] - mx);
         const float lse = logf(se) + mx;
-        const float gs = 1.f / (float)bsz;                                  // mean reduction (training.py:90)
+        const float gs = a.dp_mode == 1 ? 1.f : 1.f / (float)bsz;           // mean reduction (training.py:90); per-sample mode: 1/B in the optimizer
         for (int j = 0; j < 10; ++j) {
             const float p = expf(slog[tid][j] - lse);
             const float d = (p - (j == y ? 1.f : 0.f)) * gs;
@@ -903,6 +939,166 @@ __global__ void __launch_bounds__(512) fc1_mask_bias_kernel(flb_train_args a, Ci
     a.G[(long long)k * a.ld + kNet.f1b + j] = acc;
 }
 
+// ---- per-sample DP-SGD (dp_mode 1; north-star kernel 2 -- no reference code) -------------------------
+// Per-sample gradient g_i = d loss_i / d theta with every BatchNorm layer's batch statistics held constant (the forward pass
+// is the reference's, batch statistics included).  The backward chain is then independent per sample:
+// dz = gamma * invstd * relu'(.) * dy, dgamma_i = sum_px g * xhat, dbeta_i = sum_px g, conv-bias_i = gamma * invstd * dbeta_i.
+// Order of a step: activation gradients of all layers -> per-sample squared norms (ghost norms for the linears, per-sample
+// conv tiles squared on chip, BatchNorm / bias sums) -> clip coefficients (privacy.py:127-138) -> every layer's upstream
+// gradient rows scaled by their sample's coefficient in place -> the ordinary batched weight-gradient kernels.
+
+// BatchNorm + ReLU backward of the layers fed by a dgrad (1, 3, 5), one CTA per (sample, client): dz in place over dy (zeros
+// on the pads), the sample's (dgamma, dbeta) -> bnps, squares -> norm2.
+template <int C>
+__global__ void __launch_bounds__(256) bn_ps_bwd_kernel(flb_train_args a, ConvGeom g, const float* z_all, float* dy_all, const double* acc,
+                                                        int coff, int gwoff, int gboff, PsOut ps) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    const int bsz = flb_bsz(a, k);
+    if (b >= bsz) return;
+    __shared__ float s_mean[C], s_invstd[C], s_alpha[C], s_beta[C];
+    __shared__ float red[8][256];
+    const int tid = threadIdx.x;
+    if (tid < C) {
+        float mean, invstd, vb;
+        bn_moments(a, acc, k, coff + tid, bsz * g.H * g.W, mean, invstd, vb);
+        s_mean[tid] = mean; s_invstd[tid] = invstd;
+        s_alpha[tid] = invstd * a.W[(long long)k * a.ld + gwoff + tid];             // forward: y = relu(z * alpha + beta); c0 = alpha
+        s_beta[tid] = a.W[(long long)k * a.ld + gboff + tid] - mean * s_alpha[tid];
+    }
+    __syncthreads();
+    constexpr int C4 = C / 4, RL = 256 / C4;
+    const int cq = tid % C4, rl = tid / C4, c = cq * 4;
+    const long long kb = (long long)k * a.B + b;
+    float4* dy4 = reinterpret_cast<float4*>(dy_all + kb * g.PP() * C);
+    const float4* z4 = reinterpret_cast<const float4*>(z_all + kb * g.PP() * C);
+    const int w_shift = 31 - __clz(g.W);
+    float k_al[4], k_be[4], k_mi[4], k_is[4], s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { k_al[q] = s_alpha[c + q]; k_be[q] = s_beta[c + q]; k_mi[q] = s_mean[c + q]; k_is[q] = s_invstd[c + q]; }
+    for (int p = rl; p < g.H * g.W; p += RL) {
+        const int e = ((p >> w_shift) * g.Wp + (p & (g.W - 1))) * C4 + cq;
+        const float4 gv4 = dy4[e], zv = z4[e];
+        float gv[4] = {gv4.x, gv4.y, gv4.z, gv4.w}, o[4];
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!(__fadd_rn(__fmul_rn(zz[q], k_al[q]), k_be[q]) > 0.f)) gv[q] = 0.f;
+            s0[q] = fmaf(gv[q], (zz[q] - k_mi[q]) * k_is[q], s0[q]);
+            s1[q] += gv[q];
+            o[q] = k_al[q] * gv[q];
+        }
+        dy4[e] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    const int n_pad = g.PP() - g.H * g.W;          // the dgrad GEMM left values on the pads
+    for (int j = rl; j < n_pad; j += RL) dy4[(long long)pad_row(g, j) * C4 + cq] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { red[q][tid] = s0[q]; red[4 + q][tid] = s1[q]; }
+    __syncthreads();
+    if (tid < C) {
+        const int q = tid & 3, cq2 = tid >> 2;
+        float t0 = 0.f, t1 = 0.f;
+        for (int i = 0; i < RL; ++i) { t0 += red[q][i * C4 + cq2]; t1 += red[4 + q][i * C4 + cq2]; }
+        ps_store(a, ps, kb, k, coff, tid, t0, t1, s_invstd[tid]);
+    }
+}
+
+// ghost norms of the three linear layers: ||dW_i||^2 = ||dout_i||^2 * ||act_i||^2, ||db_i||^2 = ||dout_i||^2
+__global__ void __launch_bounds__(256) linear_ghost_norm_kernel(flb_train_args a, CifarWs ws) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const int tid = threadIdx.x;
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // |a|^2, |dh1|^2, |h1|^2, |dh2|^2, |h|^2, |dlog|^2
+    for (int e = tid; e < 2048; e += 256) { const float v = ws.a[kb * 2048 + e]; s[0] = fmaf(v, v, s[0]); }
+    for (int e = tid; e < 512; e += 256) {
+        const float v = ws.dh1[kb * 512 + e], u = ws.h1[kb * 512 + e];
+        s[1] = fmaf(v, v, s[1]); s[2] = fmaf(u, u, s[2]);
+    }
+    { const float v = ws.dh2[kb * 256 + tid], u = ws.h[kb * 256 + tid]; s[3] = v * v; s[4] = u * u; }
+    if (tid < 10) { const float v = ws.dlog[kb * 10 + tid]; s[5] = v * v; }
+    __shared__ float red[6][8];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float t = flb_warp_sum(s[i]);
+        if ((tid & 31) == 0) red[i][tid >> 5] = t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float t[6];
+        for (int i = 0; i < 6; ++i) { t[i] = 0.f; for (int w = 0; w < 8; ++w) t[i] += red[i][w]; }
+        atomicAdd(&ws.norm2[kb], t[1] * (t[0] + 1.f) + t[3] * (t[2] + 1.f) + t[5] * (t[4] + 1.f));
+    }
+}
+
+__global__ void clip_coef_kernel(flb_train_args a, CifarWs ws) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.K * a.B) return;
+    const float n = sqrtf(ws.norm2[i]);
+    ws.coef[i] = n > a.dp_clip ? a.dp_clip / n : 1.f;         // clip rule of privacy.py:127-138, per sample
+}
+
+// every layer's upstream-gradient rows times their sample's clip coefficient, in place (TMA cannot scale an operand in
+// flight); grid (sample, client, buffer)
+struct ScaleTab { float* p[9]; int n[9]; };
+__global__ void __launch_bounds__(256) scale_rows_kernel(flb_train_args a, ScaleTab t, const float* coef) {
+    const int b = blockIdx.x, k = blockIdx.y;
+    if (b >= flb_bsz(a, k)) return;
+    const long long kb = (long long)k * a.B + b;
+    const float c = coef[kb];
+    if (c == 1.f) return;
+    const int n = t.n[blockIdx.z];
+    float* buf = t.p[blockIdx.z] + kb * n;
+    if (n & 3) {
+        for (int e = threadIdx.x; e < n; e += 256) buf[e] *= c;
+        return;
+    }
+    float4* p = reinterpret_cast<float4*>(buf);
+    for (int e = threadIdx.x; e < n / 4; e += 256) {
+        float4 v = p[e];
+        v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+        p[e] = v;
+    }
+}
+
+// fc1 bias gradient from the scaled rows (fc1_mask_bias_kernel formed it before the coefficients existed)
+__global__ void __launch_bounds__(512) fc1_bias_ps_kernel(flb_train_args a, CifarWs ws) {
+    const int k = blockIdx.x;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    const int j = threadIdx.x;
+    float acc = 0.f;
+    for (int b = 0; b < bsz; ++b) acc += ws.dh1[((long long)k * a.B + b) * 512 + j];
+    a.G[(long long)k * a.ld + kNet.f1b + j] = acc;
+}
+
+// clipped sums of the per-sample BatchNorm gradients, and the conv biases of layers 2..6: gamma * invstd * sum_b coef_b dbeta_b
+struct PsTab { int coff[NCONV], bw[NCONV], bb[NCONV], cb[NCONV]; };        // kNet's per-layer offsets as a kernel argument
+__global__ void __launch_bounds__(BN_CH) bn_ps_reduce_kernel(flb_train_args a, CifarWs ws, PsTab t) {
+    const int k = blockIdx.x;
+    const int bsz = flb_bsz(a, k);
+    if (bsz == 0) return;
+    const int ch = threadIdx.x;
+    int layer = 0;
+    while (layer + 1 < NCONV && ch >= t.coff[layer + 1]) ++layer;
+    const int cl = ch - t.coff[layer], hw = layer < 2 ? 1024 : (layer < 4 ? 256 : 64);
+    const long long kb = (long long)k * a.B;
+    float t0 = 0.f, t1 = 0.f;
+    for (int b = 0; b < bsz; ++b) {
+        const float c = ws.coef[kb + b];
+        const float* row = ws.bnps + (kb + b) * 2 * BN_CH + ch;
+        t0 = fmaf(c, row[0], t0);
+        t1 = fmaf(c, row[BN_CH], t1);
+    }
+    float* G = a.G + (long long)k * a.ld;
+    G[t.bw[layer] + cl] = t0;
+    G[t.bb[layer] + cl] = t1;
+    if (layer > 0) {                                   // conv1's bias comes out of its own weight-gradient kernel
+        float mean, invstd, vb;
+        bn_moments(a, ws.acc, k, ch, bsz * hw, mean, invstd, vb);
+        G[t.cb[layer] + cl] = a.W[(long long)k * a.ld + t.bw[layer] + cl] * invstd * t1;
+    }
+}
+
 // ---- orchestration ------------------------------------------------------------------------------------------------------
 // Which GEMM runs on the tensor cores (precision 1): args.tc_mask selects single kernels for the per-layer parity tests
 // (0 = all).  Bit 3*(layer-1) + kind for conv layers 1..5 (conv2..conv6; conv1 is a direct stencil on both paths),
@@ -931,11 +1127,11 @@ void bn_bwd(const flb_train_args& a, const ConvGeom& g, const float* z, float* d
 // pooled layers (2, 4, 6): straight from the pooled-side gradient
 template <int C, bool FLAT>
 void bn_pool_bwd(const flb_train_args& a, const ConvGeom& g, const ConvGeom& go, const float* dpool, const float* pooled,
-                 const uint8_t* idx, const float* z, float* dz, double* acc, int layer, cudaStream_t st) {
+                 const uint8_t* idx, const float* z, float* dz, double* acc, int layer, cudaStream_t st, PsOut ps = PsOut{nullptr, nullptr, 0, 0}) {
     const dim3 per_sample(a.B, a.K);
-    if constexpr (FLAT) bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
-    else bn_pool_bwd_reduce_vec_kernel<C><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer]);
-    const int conv_boff = cifar_tc_conv(a, layer, TC_WGRAD) ? kNet.cb[layer] : -1;
+    if constexpr (FLAT) bn_pool_bwd_reduce_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer], ps);
+    else bn_pool_bwd_reduce_vec_kernel<C><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, acc, kNet.coff[layer], ps);
+    const int conv_boff = (!ps.bnps && cifar_tc_conv(a, layer, TC_WGRAD)) ? kNet.cb[layer] : -1;
     bn_pool_bwd_apply_kernel<C, FLAT><<<per_sample, 256, 0, st>>>(a, g, go, dpool, pooled, idx, z, dz, acc, kNet.coff[layer],
                                                                  kNet.bw[layer], kNet.bb[layer], conv_boff);
 }
@@ -971,7 +1167,7 @@ void conv_wgrad(Ctx& c, const ConvGeom& g, const float* xin, const float* dz, in
     const flb_train_args& a = c.a; cudaStream_t st = c.st;
     if (cifar_tc_conv(a, layer, TC_WGRAD)) { if (int rc = tc::conv_wgrad(a, g, xin, dz, c.ws.gt + kNet.toff[layer], kNet.ldt, st)) c.rc = rc; return; }
     ConvWgradProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.xin_all = xin; p.coef_all = nullptr;
-    p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer];
+    p.woff = kNet.cw[layer]; p.boff = kNet.cb[layer]; p.no_bias = a.dp_mode == 1;      // per-sample mode: bn_ps_reduce_kernel owns the conv biases
     const int tiles = ((g.Cout + 63) / 64) * ((9 * g.Cin + 1 + 63) / 64);
     const int splits = max(1, min(64, flb_num_sms() * 2 / (tiles * a.K)));
     simt::launch(p, g.Cout, 9 * g.Cin + 1, splits, a.K, st);
@@ -1064,6 +1260,77 @@ int forward_impl(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
     return FLB_OK;
 }
 
+// per-sample squared norm of a conv layer's weight gradient (bias excluded) -> norm2
+void conv_wgrad_norm(Ctx& c, const ConvGeom& g, const float* xin, const float* dz, int layer) {
+    const flb_train_args& a = c.a; cudaStream_t st = c.st;
+    if (cifar_tc_conv(a, layer, TC_WGRAD)) { if (int rc = tc::conv_wgrad_norm(a, g, xin, dz, c.ws.norm2, st)) c.rc = rc; return; }
+    ConvWgradNormProb p{}; p.a = a; p.g = g; p.dz_all = dz; p.xin_all = xin; p.norm2_all = c.ws.norm2; p.no_bias = 1;
+    simt::launch(p, g.Cout, 9 * g.Cin, 1, a.K * a.B, st);
+}
+
+// dp_mode 1: backward pass of the per-sample DP-SGD step (see the kernel section above); G ends up holding
+// sum_i clip(g_i), the optimizer kernel adds sigma * z and divides by the batch size
+int backward_per_sample(const flb_train_args& a, const CifarWs& ws, cudaStream_t st) {
+    const int K = a.K, B = a.B;
+    const dim3 per_sample(B, K);
+    Ctx cx{a, ws, st, FLB_OK};
+    auto ps = [&](int layer, bool conv_bias) { return PsOut{ws.bnps, ws.norm2, kNet.bw[layer], conv_bias ? 1 : 0}; };
+    // ---- activation gradients of every layer (each keeps its own buffer until the weight gradients are formed) ----
+    lin_dgrad(cx, ws.dh2, ws.dh1, 512, 256, kNet.f2w);
+    fc1_mask_bias_kernel<<<K, 512, 0, st>>>(a, ws);
+    lin_dgrad(cx, ws.dh1, ws.da, 2048, 512, kNet.f1w);
+    MARK("fc_dgrads");
+    bn_pool_bwd<128, true>(a, G6, G6, ws.da, ws.a, ws.i3, ws.z6, ws.d8a, ws.acc, 5, st, ps(5, true));
+    conv_dgrad(cx, G6, ws.d8a, ws.d8b, 5);
+    bn_ps_bwd_kernel<128><<<per_sample, 256, 0, st>>>(a, G5, ws.z5, ws.d8b, ws.acc, kNet.coff[4], kNet.bw[4], kNet.bb[4], ps(4, true));
+    conv_dgrad(cx, G5, ws.d8b, ws.d8p, 4);
+    MARK("block3_dgrads");
+    bn_pool_bwd<64, false>(a, G4, G5, ws.d8p, ws.p2, ws.i2, ws.z4, ws.d16a, ws.acc, 3, st, ps(3, true));
+    conv_dgrad(cx, G4, ws.d16a, ws.d16b, 3);
+    bn_ps_bwd_kernel<64><<<per_sample, 256, 0, st>>>(a, G3, ws.z3, ws.d16b, ws.acc, kNet.coff[2], kNet.bw[2], kNet.bb[2], ps(2, true));
+    conv_dgrad(cx, G3, ws.d16b, ws.d16p, 2);
+    MARK("block2_dgrads");
+    bn_pool_bwd<32, false>(a, G2, G3, ws.d16p, ws.p1, ws.i1, ws.z2, ws.d32a, ws.acc, 1, st, ps(1, true));
+    conv_dgrad(cx, G2, ws.d32a, ws.d32b, 1);
+    bn_ps_bwd_kernel<32><<<per_sample, 256, 0, st>>>(a, G1, ws.z1, ws.d32b, ws.acc, kNet.coff[0], kNet.bw[0], kNet.bb[0], ps(0, false));
+    MARK("block1_dgrads");
+    // ---- per-sample norms -> clip coefficients ----
+    linear_ghost_norm_kernel<<<per_sample, 256, 0, st>>>(a, ws);
+    conv1_wgrad_kernel<true><<<per_sample, 256, 0, st>>>(a, ws.d32b, ws.norm2);
+    MARK("ghost_conv1_norms");
+    conv_wgrad_norm(cx, G6, ws.y5, ws.d8a, 5);
+    conv_wgrad_norm(cx, G5, ws.p2, ws.d8b, 4);
+    conv_wgrad_norm(cx, G4, ws.y3, ws.d16a, 3);
+    conv_wgrad_norm(cx, G3, ws.p1, ws.d16b, 2);
+    conv_wgrad_norm(cx, G2, ws.y1, ws.d32a, 1);
+    MARK("conv_wgrad_norms");
+    clip_coef_kernel<<<flb_cdiv(K * B, 256), 256, 0, st>>>(a, ws);
+    ScaleTab tab{{ws.dlog, ws.dh2, ws.dh1, ws.d8a, ws.d8b, ws.d16a, ws.d16b, ws.d32a, ws.d32b},
+                 {10, 256, 512, PP8 * 128, PP8 * 128, PP16 * 64, PP16 * 64, PP32 * 32, PP32 * 32}};
+    scale_rows_kernel<<<dim3(B, K, 9), 256, 0, st>>>(a, tab, ws.coef);
+    MARK("clip_scale");
+    // ---- the ordinary batched weight-gradient kernels on the scaled rows ----
+    head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws);
+    lin_wgrad(cx, ws.dh2, ws.h1, 512, 256, kNet.f2w);
+    lin_wgrad(cx, ws.dh1, ws.a, 2048, 512, kNet.f1w);
+    fc1_bias_ps_kernel<<<K, 512, 0, st>>>(a, ws);
+    MARK("fc_wgrads");
+    conv_wgrad(cx, G6, ws.y5, ws.d8a, 5);
+    conv_wgrad(cx, G5, ws.p2, ws.d8b, 4);
+    conv_wgrad(cx, G4, ws.y3, ws.d16a, 3);
+    conv_wgrad(cx, G3, ws.p1, ws.d16b, 2);
+    conv_wgrad(cx, G2, ws.y1, ws.d32a, 1);
+    conv1_wgrad_kernel<false><<<per_sample, 256, 0, st>>>(a, ws.d32b, nullptr);
+    MARK("conv_wgrads");
+    PsTab pt;
+    for (int i = 0; i < NCONV; ++i) { pt.coff[i] = kNet.coff[i]; pt.bw[i] = kNet.bw[i]; pt.bb[i] = kNet.bb[i]; pt.cb[i] = kNet.cb[i]; }
+    bn_ps_reduce_kernel<<<K, BN_CH, 0, st>>>(a, ws, pt);
+    MARK("bn_ps_reduce");
+    if (cx.rc) return cx.rc;
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
 int forward_backward_impl(const flb_train_args& a, cudaStream_t st, bool step) {
     CifarWs ws;
     carve(a.ws, a.K, a.B, &ws);
@@ -1071,9 +1338,11 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st, bool step) {
     const dim3 per_sample(B, K);
     // gradients accumulated with atomics (conv weights / biases) start from zero; everything else is stored
     FLB_CUDA(cudaMemset2DAsync(a.G, a.ld * sizeof(float), 0, kNet.f1w * sizeof(float), K, st));
+    if (a.dp_mode == 1) FLB_CUDA(cudaMemsetAsync(ws.norm2, 0, sizeof(float) * (size_t)K * B, st));
     if (int rc = forward_impl(a, ws, st)) return rc;
     Ctx cx{a, ws, st, FLB_OK};
     if (a.precision == 1) FLB_CUDA(cudaMemsetAsync(ws.gt, 0, sizeof(float) * (size_t)K * kNet.ldt, st));
+    if (a.dp_mode == 1) return backward_per_sample(a, ws, st);
 
     head_wgrad_kernel<<<K, 256, 0, st>>>(a, ws);
     lin_wgrad(cx, ws.dh2, ws.h1, 512, 256, kNet.f2w);
@@ -1121,7 +1390,7 @@ int forward_backward_impl(const flb_train_args& a, cudaStream_t st, bool step) {
     MARK("conv2_dgrad");
     bn_bwd<32>(a, G1, ws.z1, ws.d32b, ws.acc, 0, st);
     MARK("bn1_bwd");
-    conv1_wgrad_kernel<<<per_sample, 256, 0, st>>>(a, ws.d32b);
+    conv1_wgrad_kernel<false><<<per_sample, 256, 0, st>>>(a, ws.d32b, nullptr);
     MARK("conv1_wgrad");
     if (cx.rc) return cx.rc;
     FLB_LAUNCH_CHECK();
@@ -1140,6 +1409,7 @@ long long ws_offset(int K, int B, const char* name) {
 #define FIELD(f) if (!strcmp(name, #f)) return (long long)(uintptr_t)ws.f;
     FIELD(z1) FIELD(y1) FIELD(z2) FIELD(p1) FIELD(z3) FIELD(y3) FIELD(z4) FIELD(p2) FIELD(z5) FIELD(y5) FIELD(z6) FIELD(a)
     FIELD(hpre1) FIELD(h1) FIELD(hpre2) FIELD(h) FIELD(logits) FIELD(dlog) FIELD(dh2) FIELD(dh1) FIELD(da) FIELD(acc) FIELD(d32a) FIELD(d32b) FIELD(d16p) FIELD(d16a) FIELD(d16b) FIELD(d8p) FIELD(d8a) FIELD(d8b)
+    FIELD(norm2) FIELD(coef) FIELD(bnps)
 #undef FIELD
     return -1;
 }
@@ -1151,7 +1421,7 @@ int forward(const flb_train_args& a, cudaStream_t st) {
 int forward_backward(const flb_train_args& a, cudaStream_t st, bool step) { return forward_backward_impl(a, st, step); }
 // forward 21 + backward 29 launches (conv1 carries its own BatchNorm statistics); on the tensor-core path three more
 // statistic passes ride in the conv epilogues
-int step_launches(const flb_train_args& a) { return 21 + 29 - (a.precision == 1 ? 3 : 0); }
+int step_launches(const flb_train_args& a) { return 21 + (a.dp_mode == 1 ? 37 : 29) - (a.precision == 1 ? 3 : 0); }
 void tc_tab(const flb_train_args& a, TcConvTab* t, bool step) {
     if (fuse_fc1_adam(a, step)) { t->skip_lo = kNet.f1w; t->skip_hi = kNet.f1b; }
     if (a.precision != 1) return;

@@ -567,15 +567,23 @@ struct ConvWgradHaloT {
     static constexpr int STAGES = STAGE_BYTES * 4 <= 200 * 1024 ? 4 : (STAGE_BYTES * 3 <= 200 * 1024 ? 3 : 2), RESIDENT_BYTES = 0;
     static constexpr int TMEM_COLS = Pow2Cols<TILES * COUT>::value, MINB = 1;
     static_assert(TILES * COUT <= 512, "accumulators must fit TMEM");
-    int client, row0, kb0, rbase, total_rows, wp;
+    int client, row0, row_off, rows_end, rbase, wp;      // this CTA reduces over rows [row_off, rows_end) of its client
     __device__ bool setup(const Params& p, int& num_kb) {
         client = blockIdx.y;
         const int bsz = flb_bsz(p.a, client);
-        total_rows = bsz * p.g.PP();
-        const int total = (total_rows + 31) / 32;
-        kb0 = blockIdx.x * p.kb_per_split;
-        if (kb0 >= total) return false;
-        num_kb = min(p.kb_per_split, total - kb0);
+        if (NORM) {                              // one split per SAMPLE: rows per image are a multiple of 8, not of 32
+            if ((int)blockIdx.x >= bsz) return false;
+            row_off = blockIdx.x * p.g.PP();
+            rows_end = row_off + p.g.PP();
+            num_kb = (p.g.PP() + 31) / 32;
+        } else {
+            rows_end = bsz * p.g.PP();
+            const int total = (rows_end + 31) / 32;
+            const int kb0 = blockIdx.x * p.kb_per_split;
+            if (kb0 >= total) return false;
+            num_kb = min(p.kb_per_split, total - kb0);
+            row_off = kb0 * 32;
+        }
         row0 = client * p.a.B * p.g.PP();
         rbase = blockIdx.z * RPC;
         wp = p.g.Wp;
@@ -584,7 +592,7 @@ struct ConvWgradHaloT {
     __device__ void prefetch(const Params& p) { tma_prefetch_desc(&p.map_x); tma_prefetch_desc(&p.map_dz); }
     __device__ void stage_resident(const Params&, uint8_t*, int) {}
     __device__ void load(const Params& p, int kb, uint8_t* stage, uint64_t* bar) {
-        const int px = row0 + (kb0 + kb) * 32, halo = p.g.Wp + 1;
+        const int px = row0 + row_off + kb * 32, halo = p.g.Wp + 1;
         if (this->lead) mbar_expect_tx(bar, CCH * (32 + 2 * halo) * 128 + BCH * 4096);
 #pragma unroll
         for (int c = 0; c < CCH; ++c) if (this->lead) tma_load_2d(&p.map_x, stage + c * WG_BOX_BYTES, bar, c * 32, px - halo);
@@ -593,7 +601,7 @@ struct ConvWgradHaloT {
     }
     __device__ void mma(int kb, uint32_t stage, uint32_t, uint32_t tmem) {
         constexpr uint32_t id = idesc_tf32(128, COUT, true, true);
-        const int ksteps = min(4, (total_rows - (kb0 + kb) * 32) >> 3);      // rows per image are a multiple of 8
+        const int ksteps = min(4, (rows_end - (row_off + kb * 32)) >> 3);    // rows per image are a multiple of 8
         // base descriptors once per k-block, advanced per MMA (tc_gemm.cuh desc_advance)
         const uint64_t a_base = smem_desc_mn(stage + (uint32_t)(rbase * wp) * 128u, 128, 512), b_base = smem_desc_mn(stage + A_BYTES, 4096, 512);
         const uint32_t row_step = (uint32_t)wp * 128u;
@@ -962,16 +970,30 @@ static int conv_wgrad_t(const flb_train_args& a, const ConvGeom& g, const float*
     return launch<T>(p, dim3(splits, a.K, groups), st);
 }
 
-// per-sample squared norms of the conv weight gradient (bias excluded): norm2[client, b] += || dW_b ||^2
-int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
-    using T = ConvWgradHaloT<32, 64, 3, true>;
-    if (g.PP() % 32) { flb_set_error("conv_wgrad_norm_32_64: rows per image must be a multiple of 32"); return FLB_ERR_ARG; }
+// per-sample squared norms of the conv weight gradient (bias excluded): norm2[client, b] += || dW_b ||^2.
+// grid (sample, client, kernel-row group): finished samples drop out in setup(); the groups of a sample meet in norm2.
+template <int CIN, int COUT, int RPC>
+static int conv_wgrad_norm_t(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
+    using T = ConvWgradHaloT<CIN, COUT, RPC, true>;
+    if (g.PP() % 8 || g.Wp + 1 > 35) { flb_set_error("conv_wgrad_norm: rows per image must be a multiple of 8, grid width <= 34"); return FLB_ERR_ARG; }
     typename T::Params p;
-    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), 32, 32 + 2 * (g.Wp + 1), true)) return rc;
-    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), 64, 32, true)) return rc;
+    if (int rc = make_map_2d(&p.map_x, xin, (uint64_t)a.K * a.B * g.PP(), CIN, 32 + 2 * (g.Wp + 1), true)) return rc;
+    if (int rc = make_map_2d(&p.map_dz, dz, (uint64_t)a.K * a.B * g.PP(), COUT, 32, true)) return rc;
     p.a = a; p.g = g; p.gt_all = nullptr; p.ldt = 0; p.norm2_all = norm2;
-    p.kb_per_split = g.PP() / 32;                           // split index = sample index; finished samples drop out in setup()
-    return launch<T>(p, dim3(a.B, a.K, 1), st);
+    p.kb_per_split = (g.PP() + 31) / 32;
+    return launch<T>(p, dim3(a.B, a.K, 3 / RPC), st);
+}
+int conv_wgrad_norm(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
+    if (g.Cin == 32 && g.Cout == 32) return conv_wgrad_norm_t<32, 32, 3>(a, g, xin, dz, norm2, st);
+    if (g.Cin == 32 && g.Cout == 64) return conv_wgrad_norm_t<32, 64, 3>(a, g, xin, dz, norm2, st);
+    if (g.Cin == 64 && g.Cout == 64) return conv_wgrad_norm_t<64, 64, 3>(a, g, xin, dz, norm2, st);
+    if (g.Cin == 64 && g.Cout == 128) return conv_wgrad_norm_t<64, 128, 1>(a, g, xin, dz, norm2, st);
+    if (g.Cin == 128 && g.Cout == 128) return conv_wgrad_norm_t<128, 128, 1>(a, g, xin, dz, norm2, st);
+    flb_set_error("tensor-core conv wgrad norm: unsupported channels %d -> %d", g.Cin, g.Cout);
+    return FLB_ERR_UNSUPPORTED;
+}
+int conv_wgrad_norm_32_64(const flb_train_args& a, const ConvGeom& g, const float* xin, const float* dz, float* norm2, cudaStream_t st) {
+    return conv_wgrad_norm(a, g, xin, dz, norm2, st);
 }
 
 // ---- host entry points used by the step orchestrators ---------------------------------------------------------------------

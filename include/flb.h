@@ -148,7 +148,8 @@ typedef struct flb_train_args {
                                      warp of per-sample lanes; larger loader batches are rejected by the host layer  */
     int precision;                /* 0 = fp32 CUDA-core kernels, 1 = TF32 tcgen05 tensor-core kernels */
     int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
-    int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise         */
+    int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise (cifar10_cnn: the BatchNorm
+                                     batch statistics are constants of the per-sample backward pass) */
     int eval_mode;                /* 1: model.eval() semantics -- no dropout, BatchNorm uses the running statistics */
     int tc_mask;                  /* precision 1 only: bit set = that GEMM on tensor cores (0 = all).  simple_cnn: 1 conv2 fwd,
                                      2 fc1 fwd, 4 fc1 dgrad, 8 conv2 dgrad, 16 fc1 wgrad, 32 conv2 wgrad.  cifar10_cnn: bit 3*(l-1)+kind for conv

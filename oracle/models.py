@@ -115,10 +115,17 @@ def simple_cnn_forward(w: Dict[str, torch.Tensor], x: torch.Tensor, train: bool 
 def cifar10_cnn_forward(w: Dict[str, torch.Tensor], x: torch.Tensor, train: bool = True,
                         dropout_rate: float = 0.0, masks: Optional[List[torch.Tensor]] = None,
                         bn_state: Optional[Dict[str, torch.Tensor]] = None, eps: float = 1e-5,
-                        momentum: float = 0.1):
-    # models_pytorch.py:136-165; BatchNorm2d defaults eps=1e-5, momentum=0.1, batch stats in train mode
+                        momentum: float = 0.1, bn_record: Optional[dict] = None, bn_fixed: Optional[dict] = None):
+    # models_pytorch.py:136-165; BatchNorm2d defaults eps=1e-5, momentum=0.1, batch stats in train mode.
+    # bn_record / bn_fixed (per-sample DP-SGD restatement, oracle/dpsgd.py -- no upstream counterpart): record every
+    # layer's batch (mean, biased variance) / normalise with the given constants instead of the batch's own statistics.
     def block(x, i):
         x = F.conv2d(x, w[f"conv{i}.weight"], w[f"conv{i}.bias"], padding=1)
+        if bn_fixed is not None:
+            m, v = bn_fixed[i]
+            return F.relu(F.batch_norm(x, m, v, w[f"bn{i}.weight"], w[f"bn{i}.bias"], False, 0.0, eps))
+        if bn_record is not None:
+            bn_record[i] = (x.mean((0, 2, 3)).detach(), x.var((0, 2, 3), unbiased=False).detach())
         rm = bn_state[f"bn{i}.running_mean"] if bn_state is not None else None
         rv = bn_state[f"bn{i}.running_var"] if bn_state is not None else None
         use_batch = train or rm is None
