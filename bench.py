@@ -407,6 +407,10 @@ def fedavg_sweep(ctx: Ctx, reps: int = 5, max_gb: float = 60.0):
     peak = ctx.pk["hbm_gbs"]
     rows = []
     for P in (1_000_000, 10_000_000, 100_000_000):
+        red = None
+        if ctx.world > 1 and not os.environ.get("FLB_NO_P2P"):      # FedAvg fused with the NVLink reduction (csrc/p2p_reduce.cu)
+            from flb200.p2p import PeerFedAvg
+            red = PeerFedAvg((P + 31) // 32 * 32, ctx.dev, ctx.rank, ctx.world, None)
         for K in (10, 100, 1000):
             Kl = len(range(ctx.rank, K, ctx.world))
             gb = Kl * P * 4 / 1e9
@@ -421,6 +425,9 @@ def fedavg_sweep(ctx: Ctx, reps: int = 5, max_gb: float = 60.0):
             out = torch.empty(P, dtype=torch.float32, device=ctx.dev)
 
             def run():
+                if red is not None:
+                    red.reduce(theta, wt, P)
+                    return
                 ops.fedavg_weighted_sum(theta, wt, P=P, out=out)
                 if ctx.world > 1:
                     torch.distributed.all_reduce(out)
@@ -449,7 +456,9 @@ def fedavg_sweep(ctx: Ctx, reps: int = 5, max_gb: float = 60.0):
             rows.append(row)
             del theta, out
             torch.cuda.empty_cache()
-    return {"peak_GBs": peak, "n_gpus": ctx.world, "l2": "flushed before every launch in cells under 512 MB", "rows": rows}
+        if red is not None:
+            red.close()
+    return {"peak_GBs": peak, "n_gpus": ctx.world, "collective": "none" if ctx.world == 1 else ("fused peer-memory kernel" if red is not None else "nccl all_reduce"), "l2": "flushed before every launch in cells under 512 MB", "rows": rows}
 
 
 def parity_gate(ctx: Ctx):

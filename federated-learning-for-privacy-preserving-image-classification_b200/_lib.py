@@ -34,6 +34,13 @@ SIGNATURES = {
     "flb_fedavg_weighted_sum": [_vp, _ll, _vp, _vp, _i, _ll, _i, _vp],
     "flb_fedavg_weighted_sum_ptrs": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_fedavg_weighted_sum_q8": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
+    "flb_p2p_region_layout": [_ll, _i, _i, _vp],
+    "flb_p2p_alloc": [_vp, _ll],
+    "flb_p2p_free": [_vp],
+    "flb_p2p_export": [_vp, _vp],
+    "flb_p2p_open": [_vp, _vp],
+    "flb_p2p_close": [_vp],
+    "flb_fedavg_allreduce_p2p": [_vp, _ll, _vp, _i, _ll, _vp, _vp, _i, C.c_uint, _vp],
     "flb_dp_sumsq": [_vp, _ll, _vp, _vp, _i, _ll, _vp],
     "flb_dp_clip_noise": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _ull, _i, _ll, _vp],
     "flb_dp_clip_noise_absmax": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _d, _d, _ull, _ull, _ull, _vp, _i, _vp, _i, _ll, _vp],
@@ -63,7 +70,13 @@ SIGNATURES = {
     "flb_mma_microbench": [_i, _i, _i, _i, _i, _i, _vp, _vp],
     "flb_train_step_profiled": [_vp, _vp, C.c_char_p, _i, _vp, _i],
 }
-_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset", "flb_train_bn_floats"}
+_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset", "flb_train_bn_floats", "flb_p2p_region_layout"}
+
+
+class P2pLayout(C.Structure):
+    """``flb_p2p_layout`` of include/flb.h, field for field."""
+    _fields_ = [("bytes", _ll), ("off_flags_a", _ll), ("off_flags_b", _ll), ("off_inbox", _ll), ("off_global", _ll), ("ld", _ll),
+                ("world", _i), ("chunk", _i)]
 
 
 

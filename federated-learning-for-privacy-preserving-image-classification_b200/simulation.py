@@ -13,6 +13,7 @@ with globally normalised weights n_k / sum(n) and the client -> coordinator hop 
 from __future__ import annotations
 
 import logging
+import os
 import time
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -97,7 +98,19 @@ class FederatedRoundEngine:
         if dp_mode == "per_sample":
             self.trainer.configure_dp("per_sample", max_grad_norm,
                                       max_grad_norm * ops.gaussian_sigma_unit(epsilon, delta))
-        self.global_row = torch.zeros(self.layout.ld, dtype=torch.float32, device=self.device)
+        # Several ranks: the aggregate is formed by ONE kernel per rank over NVLink peer memory (p2p.PeerFedAvg: FedAvg partial
+        # sum fused with the cross-GPU reduction), and the global row lives in the peer-mapped region.  FLB_NO_P2P=1, or peer
+        # memory being unavailable (all ranks agree on that inside the constructor), selects FedAvg kernel + NCCL all_reduce.
+        self.p2p = None
+        if world_size > 1 and not os.environ.get("FLB_NO_P2P"):
+            from .p2p import PeerFedAvg
+            try:
+                self.p2p = PeerFedAvg(self.layout.ld, self.device, rank, world_size, process_group)
+            except L.FlbError:
+                self.p2p = None
+        self.global_row = (self.p2p.global_row if self.p2p is not None
+                           else torch.zeros(self.layout.ld, dtype=torch.float32, device=self.device))
+        self._stage_row = torch.zeros(self.layout.ld, dtype=torch.float32, device=self.device) if self.p2p is not None else None
         self.upload = self.layout.new_rows(len(self.client_ids), self.device)
         self.norms: Optional[torch.Tensor] = None
         self.num_samples_all: List[int] = []
@@ -195,8 +208,15 @@ class FederatedRoundEngine:
             rows, self.norms = res[0], res[1]
             absmax = res[2] if len(res) > 2 else None
         w = self.fedavg_weights()
-        partial = self.global_row[:lay.P]                 # the aggregate is written straight into the global row (every client row was
-        if self.compression == "q8":                      # copied from it at the start of the round; nothing reads it until the next one)
+        if self.p2p is not None and self.compression is None:
+            self.p2p.reduce(rows, w, lay.P)               # partial sum + cross-GPU reduction + broadcast: one kernel
+            self.round_number += 1
+            self._round_w = w
+            return
+        # the aggregate is written straight into the global row (every client row was copied from it at the start of the
+        # round; nothing reads it until the next one); with peer memory the codec paths stage their partial sum first
+        partial = self.global_row[:lay.P] if self.p2p is None else self._stage_row[:lay.P]
+        if self.compression == "q8":
             seg = lay.seg_off(self.device)
             q, scale, zp = ops.q8_quantize(rows, seg, P=lay.P, absmax=absmax)
             partial = ops.fedavg_weighted_sum_q8(q, scale, zp, seg, w, lay.P, out=partial)
@@ -213,7 +233,9 @@ class FederatedRoundEngine:
             ops.fedavg_weighted_sum(dense, w, P=lay.P, out=partial)
         else:
             ops.fedavg_weighted_sum(rows, w, P=lay.P, out=partial)
-        if self.world_size > 1:
+        if self.p2p is not None:
+            self.p2p.reduce(self._stage_row, [1.0], lay.P)                # 0 + 1 * x is exact: the same kernel, one row
+        elif self.world_size > 1:
             # the rank's partial sum lands directly in the global row and is all-reduced in place: the collective is the
             # client -> coordinator hop AND the next round's broadcast; no staging copy on either side of it
             import torch.distributed as dist

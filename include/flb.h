@@ -35,6 +35,32 @@ int flb_fedavg_weighted_sum_q8(const uint8_t* q, long long ldq, const float* sca
                                const long long* seg_off, const float* w, float* out,
                                int K, int L, long long P, void* stream);
 
+/* ---- multi-GPU FedAvg: the rank's partial sum fused with the cross-GPU reduction over NVLink peer memory ------------------
+ * One process per GPU, client i on rank i mod G (the reference's client -> coordinator hop, src/client/grpc_client.py ->
+ * src/aggregation/fedavg.py:56-124, then the coordinator -> client broadcast of the new global model).  Every rank owns one
+ * device region (flb_p2p_alloc, laid out by flb_p2p_region_layout), exports it (flb_p2p_export: a 64-byte cudaIpcMemHandle the
+ * caller ships to the other processes, e.g. with torch.distributed.all_gather) and maps the peers' regions (flb_p2p_open).
+ * flb_fedavg_allreduce_p2p then leaves  sum_ranks sum_k w[k] * theta[k]  in the `global` row (region + off_global) of EVERY
+ * rank, bit-identical on all of them (rank-ordered sums): ONE kernel per rank, the partial sums travel chunk by chunk while
+ * later chunks are still being summed (csrc/p2p_reduce.cu).  `epoch` must be >= 1, the same on all ranks for one call and
+ * larger for every later call.  All ranks must call it for the collective to complete (like any collective). */
+#define FLB_P2P_MAX_RANKS 16
+#define FLB_P2P_HANDLE_BYTES 64
+typedef struct flb_p2p_layout {
+    long long bytes, off_flags_a, off_flags_b, off_inbox, off_global, ld;
+    int world, chunk;
+} flb_p2p_layout;
+/* fills *out for rows of ld floats (ld % 4 == 0), `world` ranks and chunks of `chunk` floats; returns the region size or -1 */
+long long flb_p2p_region_layout(long long ld, int world, int chunk, flb_p2p_layout* out);
+int flb_p2p_alloc(void** ptr, long long bytes);                 /* cudaMalloc + zero; synchronises the device */
+int flb_p2p_free(void* ptr);
+int flb_p2p_export(const void* ptr, unsigned char* handle64);
+int flb_p2p_open(const unsigned char* handle64, void** ptr);    /* enables peer access to the exporting device */
+int flb_p2p_close(void* ptr);
+/* regions: HOST array of lay->world device pointers, regions[rank] being the caller's own region */
+int flb_fedavg_allreduce_p2p(const float* theta, long long ld_theta, const float* w, int K, long long P,
+                             const flb_p2p_layout* lay, void* const* regions, int rank, unsigned int epoch, void* stream);
+
 /* ---- update-level DP: src/shared/privacy.py:107-144,183-254 + src/client/federated_trainer.py:428-469 */
 /* norm2[k] = sum_p (local[k*ld+p] - global[p])^2 in double; global may be NULL (local is the delta). */
 int flb_dp_sumsq(const float* local, long long ld, const float* global_w, double* norm2,

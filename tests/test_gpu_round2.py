@@ -278,10 +278,14 @@ def _round_on(device, rank, world, pg, K, sizes, precision, compression):
     return outs
 
 
-def _two_gpu_worker(rank, world, port, K, sizes, precision, compression, q):
+def _two_gpu_worker(rank, world, port, K, sizes, precision, compression, q, collective="p2p"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if collective == "nccl":
+        os.environ["FLB_NO_P2P"] = "1"
+    else:
+        os.environ.pop("FLB_NO_P2P", None)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -291,11 +295,66 @@ def _two_gpu_worker(rank, world, port, K, sizes, precision, compression, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision,compression", [("fp32", None), ("tf32", "q8")])
-def test_two_gpu_round_equals_one_gpu_round(cuda_device, precision, compression):
+def _peer_fedavg_worker(rank, world, port, q):
+    """PeerFedAvg.reduce alone: random client rows per rank, several calls (epochs), ragged P (not a multiple of the chunk)."""
+    import torch.distributed as dist
+    from flb200 import ops
+    from flb200.p2p import PeerFedAvg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    P, ld, K = 421642, 421664, 3 + rank
+    red = PeerFedAvg(ld, dev, rank, world, dist.group.WORLD)
+    outs = []
+    for call in range(3):
+        g = torch.Generator().manual_seed(100 * call + rank)
+        theta = torch.randn((K, ld), generator=g).to(dev)
+        w = (torch.rand(K, generator=g) / (K * world)).tolist()
+        got = red.reduce(theta, w, P).clone()
+        part = ops.fedavg_weighted_sum(theta, w, P=P)                 # this rank's partial sum by the single-GPU kernel
+        parts = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(parts, part)
+        ref = parts[0].clone()
+        for r in range(1, world):
+            ref = ref + parts[r]                                      # rank order, fp32: what the owners compute
+        outs.append((got.cpu().numpy(), ref.cpu().numpy()))
+    q.put((rank, outs))
+    dist.barrier()
+    red.close()
+    dist.destroy_process_group()
+
+
+def test_peer_fedavg_reduce_is_bit_exact(cuda_device):
+    """flb_fedavg_allreduce_p2p (FedAvg partial sum fused with the NVLink reduction) against the single-GPU FedAvg kernel +
+    a rank-ordered fp32 sum of the all-gathered partial sums: bit-identical, on every rank, call after call."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_fedavg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(2):
+        for got, ref in res[r]:
+            assert np.array_equal(got, ref)
+        for (a, _), (b, _) in zip(res[0], res[r]):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision,compression,collective", [("fp32", None, "p2p"), ("tf32", "q8", "p2p"), ("fp32", None, "nccl")])
+def test_two_gpu_round_equals_one_gpu_round(cuda_device, precision, compression, collective):
     """client i -> rank i mod G, Philox streams (dropout masks, DP noise) keyed by the GLOBAL client
-    index, partial sums with globally normalised weights + one all-reduce.  The aggregate after two rounds on 2 GPUs must
-    equal the 1-GPU aggregate up to fp32 re-association (Philox-generated noise and masks included, not injected)."""
+    index, partial sums with globally normalised weights, reduced across the GPUs by the fused peer-memory kernel (p2p) or by
+    the FedAvg kernel + one NCCL all-reduce (FLB_NO_P2P).  The aggregate after two rounds on 2 GPUs must equal the 1-GPU
+    aggregate up to fp32 re-association (Philox-generated noise and masks included, not injected)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -304,7 +363,7 @@ def test_two_gpu_round_equals_one_gpu_round(cuda_device, precision, compression)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, K, sizes, precision, compression, q)) for r in range(2)]
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, K, sizes, precision, compression, q, collective)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=600) for _ in range(2))
