@@ -25,6 +25,11 @@ if os.environ.get("FLB_TRACE") == "1":          # per-role timeline of the resid
     NVCC_FLAGS.append("-DFLB_TRACE=1")
 
 
+# per-file flags.  fedavg.cu: every fp32 operation of the aggregation is rounded separately (bit-exact with the reference's
+# python loop); nvcc contracts the PACKED intrinsics (__fmul2_rn + __fadd2_rn -> FFMA2) unless contraction is off for the file.
+FILE_FLAGS = {"fedavg.cu": ["-fmad=false"]}
+
+
 def _nvcc() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -57,10 +62,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
         stamp = obj + ".sha"
-        want = _digest([src]) + hdr_digest
+        extra = FILE_FLAGS.get(os.path.basename(src), [])
+        want = _digest([src]) + hdr_digest + " ".join(extra)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
             return obj, ""
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -99,19 +99,38 @@ fedavg_ptrs_kernel(const float* const* __restrict__ ptrs, const long long* __res
 // Each thread owns 16 consecutive parameters (one 16 B load per client row).  float(q) - zp is formed exactly in ONE
 // add through the 2^23 mantissa trick (as_float(0x4B000000 | q) = 2^23 + q; both q and zp are integers below 2^24),
 // the remaining fp32 multiply, multiply, add are rounded separately in the reference's order.
+// The kernel is bound by the fp32 pipe (four dependent fp32 operations per BYTE of input, none of which may be fused or
+// reassociated), so the four operations run as packed f32x2 instructions (sm_100 add.rn.f32x2 / mul.rn.f32x2: two IEEE
+// results per issue slot, each lane rounded exactly like the scalar instruction), and the byte -> 2^23 + q expansion is one
+// PRMT per element (byte e of the word under the constant's upper three bytes) instead of shift + and + or.
 __device__ __forceinline__ void q8_accum4(uint32_t word, float magic_z, float s, float wk, float* acc) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float qf = __uint_as_float(0x4B000000u | ((word >> (8 * e)) & 0xffu));       // 2^23 + q, exact
-        acc[e] = __fadd_rn(acc[e], __fmul_rn(wk, __fmul_rn(__fsub_rn(qf, magic_z), s)));   // (q - zp) * scale, then w * (.), then +=
-    }
+    const float2 q01 = make_float2(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540)),      // 2^23 + q, exact
+                                   __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7541)));
+    const float2 q23 = make_float2(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7542)),
+                                   __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7543)));
+    const float2 nz = make_float2(-magic_z, -magic_z), s2 = make_float2(s, s), w2 = make_float2(wk, wk);
+    // (q - zp) exactly, * scale, then w * (.), then += : every step rounded separately, in the reference's order
+    const float2 t01 = __fmul2_rn(w2, __fmul2_rn(__fadd2_rn(q01, nz), s2));
+    const float2 t23 = __fmul2_rn(w2, __fmul2_rn(__fadd2_rn(q23, nz), s2));
+    // the accumulation stays scalar: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever --fmad says,
+    // which would round once where the reference rounds twice (caught by test_q8_fused_dequant_average)
+    acc[0] = __fadd_rn(acc[0], t01.x); acc[1] = __fadd_rn(acc[1], t01.y);
+    acc[2] = __fadd_rn(acc[2], t23.x); acc[3] = __fadd_rn(acc[3], t23.y);
 }
 
 // EPT = parameters per thread: 16 (one 16 B load per client row) for long rows; 4 (one 4 B load, a warp still reads whole
 // 128 B lines) when P / 16 threads would leave most of the machine idle -- the client loop cannot be split, its adds
 // must stay in client order to remain bit-exact.
+// streaming 16-byte load that the compiler may not sink next to its first use (volatile asm statements keep their order):
+// the U loads of an unrolled group are all issued before the first dequantisation starts
+__device__ __forceinline__ uint4 ldcs_u4_pinned(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <int EPT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __restrict__ scale,
                  const float* __restrict__ zp, const long long* __restrict__ seg_off,
                  const float* __restrict__ w, float* __restrict__ out, int K, int L, long long P) {
@@ -130,18 +149,59 @@ fedavg_q8_kernel(const uint8_t* __restrict__ q, long long ldq, const float* __re
             float acc[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) acc[e] = 0.f;
-#pragma unroll(EPT == 16 ? 2 : 8)
-            for (int k = 0; k < K; ++k) {
-                const float s = __ldg(&scale[(long long)k * L + lo]);
-                const float magic_z = 8388608.0f + __ldg(&zp[(long long)k * L + lo]);     // exact: zp is an integer < 2^16
-                const float wk = __ldg(&w[k]);
-                if (EPT == 16) {
+            if (EPT == 16) {
+                // ncu (K = 100, P = 10 M): with one or two client rows in flight per thread the kernel idles on the long scoreboard
+                // (11 stalled warps per issue, 46 % of the DRAM peak, fma pipe 49 % busy): latency-, not ALU-bound.
+                // ptxas (12.9) sinks every load of a straight-line group behind the arithmetic of the previous row (the PTX has the
+                // four loads first; the SASS has one load, 150 dependent instructions, the next load ...), so the prefetch is
+                // carried across the loop back-edge instead: group g + 1 is requested before group g is dequantised.
+                constexpr int U = 3;
+                const int Kfull = K - K % U;
+                uint4 cur[U], nxt[U];
+                float csc[U], cmz[U], cwk[U], nsc[U], nmz[U], nwk[U];
+                auto fetch = [&](int k0, uint4 (&v)[U], float (&sc)[U], float (&mz)[U], float (&wk)[U]) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        v[u] = ldcs_u4_pinned(q + (long long)(k0 + u) * ldq + p);
+                        sc[u] = __ldg(&scale[(long long)(k0 + u) * L + lo]);
+                        mz[u] = __ldg(&zp[(long long)(k0 + u) * L + lo]);
+                        wk[u] = __ldg(&w[k0 + u]);
+                    }
+                };
+                if (Kfull > 0) fetch(0, cur, csc, cmz, cwk);
+                int k = 0;
+                for (; k < Kfull; k += U) {
+                    const bool more = k + U < Kfull;
+                    if (more) fetch(k + U, nxt, nsc, nmz, nwk);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float magic_z = 8388608.0f + cmz[u];                        // exact: zp is an integer < 2^16
+                        q8_accum4(cur[u].x, magic_z, csc[u], cwk[u], acc);
+                        q8_accum4(cur[u].y, magic_z, csc[u], cwk[u], acc + 4);
+                        q8_accum4(cur[u].z, magic_z, csc[u], cwk[u], acc + 8);
+                        q8_accum4(cur[u].w, magic_z, csc[u], cwk[u], acc + 12);
+                    }
+                    if (more) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { cur[u] = nxt[u]; csc[u] = nsc[u]; cmz[u] = nmz[u]; cwk[u] = nwk[u]; }
+                    }
+                }
+                for (; k < K; ++k) {
+                    const float s = __ldg(&scale[(long long)k * L + lo]);
+                    const float magic_z = 8388608.0f + __ldg(&zp[(long long)k * L + lo]);
+                    const float wk1 = __ldg(&w[k]);
                     const uint4 v = __ldcs(reinterpret_cast<const uint4*>(q + (long long)k * ldq + p));
-                    q8_accum4(v.x, magic_z, s, wk, acc);
-                    q8_accum4(v.y, magic_z, s, wk, acc + 4);
-                    q8_accum4(v.z, magic_z, s, wk, acc + 8);
-                    q8_accum4(v.w, magic_z, s, wk, acc + 12);
-                } else {
+                    q8_accum4(v.x, magic_z, s, wk1, acc);
+                    q8_accum4(v.y, magic_z, s, wk1, acc + 4);
+                    q8_accum4(v.z, magic_z, s, wk1, acc + 8);
+                    q8_accum4(v.w, magic_z, s, wk1, acc + 12);
+                }
+            } else {
+#pragma unroll 8
+                for (int k = 0; k < K; ++k) {
+                    const float s = __ldg(&scale[(long long)k * L + lo]);
+                    const float magic_z = 8388608.0f + __ldg(&zp[(long long)k * L + lo]);     // exact: zp is an integer < 2^16
+                    const float wk = __ldg(&w[k]);
                     q8_accum4(__ldcs(reinterpret_cast<const uint32_t*>(q + (long long)k * ldq + p)), magic_z, s, wk, acc);
                 }
             }
