@@ -71,6 +71,26 @@ def test_single_gemm_on_tensor_cores_matches_fp32_path(cuda_device, name):
             assert _rel(got["G"][k, o:o + cnt], ref["G"][k, o:o + cnt]) < btol, (name, k, pname)
 
 
+@pytest.mark.parametrize("mask,tol", [(BITS["conv2_dgrad"], 1e-2), (0, 5e-2)])
+def test_training_step_update_matches_fp32_path(cuda_device, mask, tol):
+    """The TRAINING-STEP launch sequence (flb_train_step: side lanes, accumulators zeroed by their consumers, optimizer) rather
+    than the gradient-only entry the other tests use.  One SGD step (momentum buffer = gradient at t = 1) exposes every
+    gradient as the weight update: tensor-core path against the fp32 path, ragged clients, several clients per CTA range."""
+    sizes = (32, 17, 8, 1, 29)
+    upd = {}
+    for prec, m in (("fp32", 0), ("tf32", mask)):
+        eng, *_ = _setup(cuda_device, prec, m, sizes)
+        w0 = eng.W.clone()
+        eng.train(1, 0.5, "sgd")
+        torch.cuda.synchronize()
+        upd[prec] = eng.W - w0
+    lay = eng.layout
+    for k in range(len(sizes)):
+        for pname in lay.names:
+            o, cnt = lay.offsets[pname], int(np.prod(lay.shapes[pname]))
+            assert _rel(upd["tf32"][k, o:o + cnt], upd["fp32"][k, o:o + cnt]) < tol, (k, pname)
+
+
 def test_all_tensor_core_step_vs_oracle(cuda_device):
     """TF32 tolerance stated in SURVEY.md 8(c): logits 2e-3 relative, gradients 1e-2 relative to the layer's max."""
     sizes = (32, 24, 1)
