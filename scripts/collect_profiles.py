@@ -19,7 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 for f in ("r02_bench_1gpu.json", "r02_reference_arm.json", "r02_bench_1gpu_cifar100_q8.json", "r02_bench_1gpu_mnist50.json",
-          "r02_bench_1gpu_per_sample_dp.json", "r02_mma_microbench.jsonl", "r02_launches_raw.csv", "r02_conv_timeline.txt",
+          "r02_bench_1gpu_per_sample_dp.json", "r02_bench_1gpu_cifar100_q8_per_sample.json", "r02_fedavg_sweep_1gpu.json", "r02_mma_microbench.jsonl", "r02_launches_raw.csv", "r02_conv_timeline.txt",
           "r02_bench_2gpu.json", "r02_bench_4gpu.json", "r02_bench_8gpu.json", "r02_2gpu_tests.log"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
