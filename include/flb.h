@@ -171,7 +171,8 @@ typedef struct flb_train_args {
     int model;                    /* 0 = simple_cnn, 1 = cifar10_cnn (models_pytorch.py:59-97, :100-165) */
     int K;                        /* resident clients                                                */
     int B;                        /* batch size, 1..32: the kernels map one batch to one 32-column MMA operand / one
-                                     warp of per-sample lanes; larger loader batches are rejected by the host layer  */
+                                     warp of per-sample lanes; LocalTrainer trains larger loader batches in minibatches
+                                     of 32 (and logs it), BatchedClientTrainer rejects them                          */
     int precision;                /* 0 = fp32 CUDA-core kernels, 1 = TF32 tcgen05 tensor-core kernels */
     int opt;                      /* 0 adam, 1 sgd(momentum), 2 adamw                                */
     int dp_mode;                  /* 0 none (reference behaviour), 1 per-sample clip + noise (cifar10_cnn: the BatchNorm
