@@ -60,6 +60,7 @@ SIGNATURES = {
     "flb_train_ws_offset": [_i, _i, _i, C.c_char_p],
     "flb_train_bn_floats": [_i],
     "flb_train_begin_epoch": [_vp, _vp],
+    "flb_train_begin_round": [_vp, _vp, _vp],
     "flb_train_step": [_vp, _vp],
     "flb_train_step_grads": [_vp, _vp, _ll, _vp],
     "flb_train_forward_backward": [_vp, _vp],

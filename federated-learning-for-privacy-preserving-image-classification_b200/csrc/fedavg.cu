@@ -18,7 +18,10 @@ constexpr int kWChunk = 1024;   // weights staged in shared memory per pass
 // theta: [K, ld] fp32 row-major, rows 16 B aligned (ld % 4 == 0).  out: [P].
 __global__ void __launch_bounds__(kThreads)
 fedavg_flat_vec4_kernel(const float* __restrict__ theta, long long ld, const float* __restrict__ w,
-                        float* __restrict__ out, int K, long long P4, int accumulate) {
+                        float* __restrict__ out, int K, long long P, int accumulate) {
+    // P4 = float4 columns, the last one possibly partial (P % 4 != 0): its loads stay inside the row (ld % 4 == 0, ld >= P),
+    // its stores are scalar -- no second launch for a two-parameter tail (SimpleCNN: P = 421 642)
+    const long long P4 = (P + 3) >> 2;
     __shared__ float sw[kWChunk];
     const long long stride = (long long)gridDim.x * kThreads;
     const float4* __restrict__ t4 = reinterpret_cast<const float4*>(theta);
@@ -27,7 +30,13 @@ fedavg_flat_vec4_kernel(const float* __restrict__ theta, long long ld, const flo
         const long long c = base + threadIdx.x;
         const bool live = c < P4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (accumulate && live) acc = reinterpret_cast<const float4*>(out)[c];
+        const int nvalid = live ? (int)min(4ll, P - 4 * c) : 0;
+        if (accumulate && nvalid == 4) acc = reinterpret_cast<const float4*>(out)[c];
+        else if (accumulate && nvalid > 0) {
+            acc.x = out[4 * c];
+            if (nvalid > 1) acc.y = out[4 * c + 1];
+            if (nvalid > 2) acc.z = out[4 * c + 2];
+        }
         for (int k0 = 0; k0 < K; k0 += kWChunk) {
             const int kc = min(kWChunk, K - k0);
             __syncthreads();
@@ -57,7 +66,12 @@ fedavg_flat_vec4_kernel(const float* __restrict__ theta, long long ld, const flo
                 acc.w = __fadd_rn(acc.w, __fmul_rn(wk, v.w));
             }
         }
-        if (live) reinterpret_cast<float4*>(out)[c] = acc;
+        if (nvalid == 4) reinterpret_cast<float4*>(out)[c] = acc;
+        else if (nvalid > 0) {
+            out[4 * c] = acc.x;
+            if (nvalid > 1) out[4 * c + 1] = acc.y;
+            if (nvalid > 2) out[4 * c + 2] = acc.z;
+        }
     }
 }
 
@@ -243,15 +257,9 @@ extern "C" int flb_fedavg_weighted_sum(const float* theta, long long ld, const f
     if (P == 0) return FLB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = (ld % 4 == 0) && ((uintptr_t)theta % 16 == 0) && ((uintptr_t)out % 16 == 0);
-    long long P4 = vec ? (P >> 2) : 0;
-    if (P4 > 0) {
-        fedavg_flat_vec4_kernel<<<grid_for(P4), kThreads, 0, st>>>(theta, ld, w, out, K, P4, accumulate);
-        FLB_LAUNCH_CHECK();
-    }
-    if ((P4 << 2) < P) {
-        fedavg_flat_scalar_kernel<<<grid_for(P - (P4 << 2)), kThreads, 0, st>>>(theta, ld, w, out, K, P4 << 2, P, accumulate);
-        FLB_LAUNCH_CHECK();
-    }
+    if (vec) fedavg_flat_vec4_kernel<<<grid_for((P + 3) >> 2), kThreads, 0, st>>>(theta, ld, w, out, K, P, accumulate);
+    else fedavg_flat_scalar_kernel<<<grid_for(P), kThreads, 0, st>>>(theta, ld, w, out, K, 0, P, accumulate);
+    FLB_LAUNCH_CHECK();
     return FLB_OK;
 }
 

@@ -183,6 +183,25 @@ __global__ void advance_kernel(flb_train_args a) {
     if (k == 0) *a.step_ctr += 1;
 }
 
+// Start of a federated round: every resident client takes the global model and a fresh optimizer (the reference builds a new
+// LocalTrainer -- new torch.optim state -- per round and loads the downloaded weights, src/client/federated_trainer.py:367-392).
+// One pass instead of a broadcast copy and three fills: W[k] = global, M[k] = V[k] = 0 over the whole padded row, tcount = 0.
+__global__ void __launch_bounds__(256) round_begin_kernel(flb_train_args a, const float* __restrict__ global_row) {
+    const int k = blockIdx.y;
+    const long long ld4 = a.ld >> 2;
+    float4* W = reinterpret_cast<float4*>(a.W + (long long)k * a.ld);
+    float4* M = reinterpret_cast<float4*>(a.M + (long long)k * a.ld);
+    float4* V = reinterpret_cast<float4*>(a.V + (long long)k * a.ld);
+    const float4* g = reinterpret_cast<const float4*>(global_row);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long c = (long long)blockIdx.x * 256 + threadIdx.x; c < ld4; c += (long long)gridDim.x * 256) {
+        W[c] = __ldg(&g[c]);
+        M[c] = z;
+        V[c] = z;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.tcount[k] = 0;
+}
+
 __global__ void begin_epoch_kernel(flb_train_args a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < a.K) { a.loss_sum[k] = 0.f; a.correct[k] = 0; a.nbatch[k] = 0; a.nseen[k] = 0; }
@@ -242,6 +261,17 @@ extern "C" int flb_train_begin_epoch(const flb_train_args* a, void* stream) {
     if (t.n) tc_repack_kernel<0><<<dim3(repack_blocks(*a, t), a->K), 256, 0, (cudaStream_t)stream>>>(*a, t);
     if (a->model == 0)
         if (int rc = simplecnn::begin_epoch_zero(*a, (cudaStream_t)stream)) return rc;
+    FLB_LAUNCH_CHECK();
+    return FLB_OK;
+}
+
+extern "C" int flb_train_begin_round(const flb_train_args* a, const float* global_row, void* stream) {
+    if (int rc = check_args(a)) return rc;
+    FLB_CHECK_ARG(global_row != nullptr && a->ld % 4 == 0 && ((uintptr_t)global_row % 16) == 0,
+                  "flb_train_begin_round: need a 16-byte aligned global row of ld floats, ld %% 4 == 0");
+    static const int resident = flb_resident_ctas(round_begin_kernel, 256);
+    const int blocks = max(1, min(flb_cdiv(a->ld / 4, 256), resident / a->K));
+    round_begin_kernel<<<dim3(blocks, a->K), 256, 0, (cudaStream_t)stream>>>(*a, global_row);
     FLB_LAUNCH_CHECK();
     return FLB_OK;
 }

@@ -188,9 +188,8 @@ class FederatedRoundEngine:
         when that epoch has drained -- measured with scripts/dbg_e2e.py.)"""
         tr, lay = self.trainer, self.layout
         self._t0 = time.time()
-        tr.set_global_row(self.global_row)
+        tr.begin_round(self.global_row)                    # global model into every client row, fresh optimizer state: one launch
         tr._fill_args(self.lr, self.optimizer_type, train=True)
-        tr.M.zero_(); tr.V.zero_(); tr.tcount.zero_()
         for _ in range(self.local_epochs):
             tr._run_epoch()
         rows = tr.W

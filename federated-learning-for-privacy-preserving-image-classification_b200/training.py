@@ -123,6 +123,16 @@ class BatchedClientTrainer:
         """Every client starts the round from the same global model (src/client/federated_trainer.py:378)."""
         self.W.copy_(row.to(self.device).view(1, -1).expand(self.K, -1))
 
+    def begin_round(self, row: torch.Tensor) -> None:
+        """Global model into every client row + fresh optimizer state (moments and step counts zero), one launch."""
+        if self.x is None or row.device != self.W.device or row.numel() < self.layout.ld or row.data_ptr() % 16:
+            self.set_global_row(row)
+            self.M.zero_(); self.V.zero_(); self.tcount.zero_()
+            return
+        self._fill_args(0.0, "adam", train=True)
+        with torch.cuda.device(self.device):
+            L.call("flb_train_begin_round", C.byref(self.args), L.ptr(row), L.stream_ptr(self.device))
+
     def set_client_weights(self, k: int, weights: Dict[str, torch.Tensor]) -> None:
         self.layout.flatten_into(self.W[k], weights)
 

@@ -193,6 +193,10 @@ long long flb_train_bn_floats(int model);
 long long flb_train_ws_offset(int model, int K, int B, const char* name);
 /* zero the epoch accumulators and step counter (start of _train_epoch, training.py:178-182) */
 int flb_train_begin_epoch(const flb_train_args* a, void* stream);
+/* Start of a federated round: W[k] = global_row, M[k] = V[k] = 0 over the whole padded row, tcount[k] = 0 for every resident
+ * client, one pass (a new LocalTrainer -- fresh torch.optim state -- around the downloaded weights,
+ * src/client/federated_trainer.py:367-392).  global_row: ld floats, 16-byte aligned. */
+int flb_train_begin_round(const flb_train_args* a, const float* global_row, void* stream);
 /* one minibatch step for all K clients; clients that have run out of samples are skipped */
 int flb_train_step(const flb_train_args* a, void* stream);
 /* same step, and grads_out[k*ld_out + p] (p < P) receives the minibatch gradient the optimizer applied (what
