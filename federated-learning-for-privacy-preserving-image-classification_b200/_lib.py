@@ -31,6 +31,7 @@ _vp, _i, _ll, _ull, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_d
 SIGNATURES = {
     "flb_version": [],
     "flb_init": [_i],
+    "flb_l2_persist_window": [_vp, _ll, _vp],
     "flb_fedavg_weighted_sum": [_vp, _ll, _vp, _vp, _i, _ll, _i, _vp],
     "flb_fedavg_weighted_sum_ptrs": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "flb_fedavg_weighted_sum_q8": [_vp, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
@@ -71,7 +72,7 @@ SIGNATURES = {
     "flb_mma_microbench": [_i, _i, _i, _i, _i, _i, _vp, _vp],
     "flb_train_step_profiled": [_vp, _vp, C.c_char_p, _i, _vp, _i],
 }
-_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset", "flb_train_bn_floats", "flb_p2p_region_layout"}
+_RESTYPE_LL = {"flb_train_ws_bytes", "flb_train_ws_offset", "flb_train_bn_floats", "flb_p2p_region_layout", "flb_l2_persist_window"}
 
 
 class P2pLayout(C.Structure):

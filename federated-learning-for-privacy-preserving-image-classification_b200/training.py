@@ -84,10 +84,13 @@ class BatchedClientTrainer:
         self.sample_numel = math.prod(INPUT_SHAPES[model_name])
         dev, K = self.device, self.K
         lay = self.layout
-        self.W = lay.new_rows(K, dev)
-        self.G = lay.new_rows(K, dev)
-        self.M = lay.new_rows(K, dev)
-        self.V = lay.new_rows(K, dev)
+        # gradients | parameters | Adam moments back to back in one allocation: ONE L2 access-policy window can cover a suffix
+        # of it (see _launch_epoch).  FLB_L2_WINDOW = mv (default) | wmv | gwmv selects the suffix, FLB_NO_L2_PERSIST=1 none.
+        self._state = torch.zeros((4, K, lay.ld), dtype=torch.float32, device=dev)
+        self.G, self.W, self.M, self.V = self._state[0], self._state[1], self._state[2], self._state[3]
+        first = {"mv": 2, "wmv": 1, "gwmv": 0}[os.environ.get("FLB_L2_WINDOW", "mv")]
+        self._MV = self._state[first:]
+        self.l2_persist = os.environ.get("FLB_NO_L2_PERSIST") is None
         self.tcount = torch.zeros(K, dtype=torch.int32, device=dev)
         self.step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)
         self.epoch_nonce = torch.zeros(1, dtype=torch.int64, device=dev)   # +1 per epoch on the device, never reset (flb.h)
@@ -293,6 +296,11 @@ class BatchedClientTrainer:
     def _launch_epoch(self) -> None:
         st = L.stream_ptr(self.device)
         ap = C.byref(self.args)
+        # The Adam moments are touched once per step by the optimizer kernel; when they fit the L2 set-aside (about 10 SimpleCNN
+        # clients) they are pinned there for the epoch instead of being evicted by the activations in between.  The window is a
+        # stream attribute (recorded into the kernel nodes when this runs under capture); larger states get no window at all.
+        if self.l2_persist:
+            L.load().flb_l2_persist_window(L.ptr(self._MV), self._MV.numel() * 4, st)
         L.call("flb_train_begin_epoch", ap, st)
         n = self.max_steps()
         for s in range(n):
@@ -307,6 +315,8 @@ class BatchedClientTrainer:
         with torch.cuda.device(self.device):
             if self.keep_last_grads and self.last_grads is None:
                 self.last_grads = self.layout.new_rows(self.K, self.device)      # before any capture: no allocation inside
+            if self.l2_persist:               # sizes (or gives back) the device's L2 set-aside for THIS engine, replays included
+                L.load().flb_l2_persist_window(L.ptr(self._MV), self._MV.numel() * 4, L.stream_ptr(self.device))
             key = (bytes(self.args), self.max_steps(), self.keep_last_grads)
             if self.use_graph and key in self._graphs:
                 self._graphs[key].replay()

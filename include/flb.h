@@ -21,6 +21,12 @@ const char* flb_last_error(void);
 int flb_version(void);
 int flb_init(int device);            /* checks a sm_100 device exists; idempotent */
 
+/* L2 residency hint (no reference counterpart; a property of this implementation's memory layout): marks [base, base + bytes)
+ * as persisting in L2 for kernels launched on `stream` from now on (captured into CUDA-graph kernel nodes); bytes <= 0, or a
+ * range larger than the device's L2 set-aside, clears the window.  Used for the Adam moments of the batched trainer.
+ * Returns the bytes covered (0: no window). */
+long long flb_l2_persist_window(const void* base, long long bytes, void* stream);
+
 /* ---- FedAvg: src/aggregation/fedavg.py:267-289 (_weighted_average) -------------------------- */
 /* out[p] = sum_k w[k] * theta[k*ld + p], sequential over k in fp32 (bit-exact with the reference loop).
  * accumulate != 0 starts from the current contents of out (chunked / multi-call aggregation). */
