@@ -101,7 +101,10 @@ def test_validation_loader_leaves_optimizer_state_alone(cuda_device):
     w0 = OM.init_weights(MODEL, 12)
     num = sum(float(((out[1][0][n] - out[0][0][n]).double() ** 2).sum()) for n in w)
     den = sum(float(((out[0][0][n] - w0[n]).double() ** 2).sum()) for n in w)
-    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+    # Two IDENTICAL runs (no validation in either) differ by ~1e-6 in 7 of 8 cases and by exactly 1.04e-2 in the eighth: one
+    # ReLU / max-pool near-tie decided the other way by the order of the fp32 atomics (tests/tools/dbg_valnoise.py, 24 pairs).
+    # The bound leaves room for a few such flips and stays far below the tens of per cent of an inflated step count.
+    assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
     for name in w:
         assert float((out[1][0][name] - out[0][0][name]).abs().max()) <= 2e-3
         assert float((out[1][0][name] - w[name]).abs().max()) <= 5e-3       # Adam, 15 steps of +-lr: conftest.adam_trajectory_check scale
