@@ -106,7 +106,8 @@ class FederatedRoundEngine:
             from .p2p import PeerFedAvg
             try:
                 self.p2p = PeerFedAvg(self.layout.ld, self.device, rank, world_size, process_group)
-            except L.FlbError:
+            except L.FlbError as e:
+                logging.getLogger(__name__).info("peer-memory FedAvg unavailable (%s): FedAvg kernel + NCCL all_reduce", e)
                 self.p2p = None
         self.global_row = (self.p2p.global_row if self.p2p is not None
                            else torch.zeros(self.layout.ld, dtype=torch.float32, device=self.device))
